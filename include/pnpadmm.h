@@ -1,0 +1,179 @@
+/*
+ * pnpadmm.h — C ABI of the B200-native ADMM / PnP-ADMM CS-MRI reconstruction path.
+ *
+ * This is the drop-in boundary for ONE hot path of zj15001/PNP_ADMM_CNC_MRI: the ADMM
+ * iteration loop that is copy-pasted into every entry script of the reference.  The
+ * reference has no FFI of its own for this path (it is inline NumPy inside Python
+ * functions), so every entry point below cites the reference code block it replaces
+ * (file:line, script aliases S1 = "【1】ADMM_L1.py", S3 = "【3】PNP_ADMM_L1_D  .py",
+ * S4 = "【4】ADMM_CNC .py", S6 = "【6】PNP_ADMM_CNC_D .py").  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every array pointer is a DEVICE pointer on the current CUDA device unless its name
+ *     starts with "h_" (host).  The *_host entry points take host pointers and do their
+ *     own staged H2D / D2H copies.
+ *   - images are row-major [B][N][N]; complex arrays are interleaved (re, im), i.e.
+ *     [B][N][N][2]; masks are uint8 {0,1} with the DC bin at [0][0] (no fftshift),
+ *     exactly like CS_MRI/Q_*.mat['Q1'].
+ *   - N is a power of two, 16 <= N <= 2048 (f32) / 1024 (f64).  N == 256 in f32 selects the
+ *     thread-block-cluster kernel (whole state resident in distributed shared memory);
+ *     everything else uses the streaming kernels.
+ *   - the library never allocates per call: the caller owns a workspace of
+ *     pnpadmm_workspace_bytes() bytes.  Work is stream-ordered on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream); no host sync inside.
+ *   - all functions return 0 on success or a negative PNPADMM_ERR_* code and never throw.
+ *     pnpadmm_last_error_string() describes the last failure on the calling thread.
+ *   - scalar parameters are passed as double in both precisions and rounded once inside.
+ */
+#ifndef PNPADMM_H_
+#define PNPADMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNPADMM_ABI_VERSION 1
+
+#define PNPADMM_OK                 0
+#define PNPADMM_ERR_BAD_ARG       -1   /* NULL pointer, B <= 0, iters < 0, unknown enum ...          */
+#define PNPADMM_ERR_BAD_SIZE      -2   /* N not a power of two or outside the supported range        */
+#define PNPADMM_ERR_WORKSPACE     -3   /* workspace NULL / too small / misaligned (256 B)            */
+#define PNPADMM_ERR_CUDA          -4   /* a CUDA runtime call or kernel launch failed                */
+#define PNPADMM_ERR_UNSUPPORTED   -5   /* e.g. cluster kernel requested for N != 256 or on a non-sm_100 device */
+
+#define PNPADMM_PROX_L1    0           /* S1:123                                                    */
+#define PNPADMM_PROX_CNC   1           /* S4:127-129                                                */
+
+#define PNPADMM_KERNEL_AUTO       0    /* cluster kernel when N == 256 && f32, else streaming        */
+#define PNPADMM_KERNEL_CLUSTER    1    /* K1: 8-CTA cluster, state resident in DSMEM (N == 256, f32) */
+#define PNPADMM_KERNEL_STREAMING  2    /* K2: two passes per iteration through L2 / HBM              */
+
+typedef void* pnpadmm_stream_t;        /* cudaStream_t */
+
+int         pnpadmm_abi_version(void);
+const char* pnpadmm_last_error_string(void);
+
+/* sm_count, max co-resident 8-CTA clusters of the N=256 kernel (0 if it cannot launch),
+ * compute capability.  Any out pointer may be NULL. */
+int pnpadmm_device_info(int* sm_count, int* max_clusters_256, int* cc_major, int* cc_minor);
+
+/* Bytes of device workspace needed by every call below for (B, N, precision, mask layout). */
+size_t pnpadmm_workspace_bytes(int B, int N, int is_f64, int mask_batched);
+
+/* ---------------------------------------------------------------------------------------
+ * a2  acquisition:  y = fft2(img) * mask + noises           (S1:99 == S4:103 == S3:242 == S6:251)
+ *   img   [B][N][N] real in [0,1];  mask [N][N] or [B][N][N] u8;  noise [N][N][2] or [B][N][N][2]
+ *   y     [B][N][N][2] out.  Noise is added on EVERY bin, sampled or not, like the reference.
+ * ------------------------------------------------------------------------------------- */
+int pnpadmm_acquire_f32(const float* img, const uint8_t* mask, const float* noise, float* y,
+                        int B, int N, int mask_batched, int noise_batched,
+                        void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+int pnpadmm_acquire_f64(const double* img, const uint8_t* mask, const double* noise, double* y,
+                        int B, int N, int mask_batched, int noise_batched,
+                        void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+
+/* zero-filled start  x0 = |ifft2(y)|  (complex magnitude)              (S1:100,104 == S4:104,108) */
+int pnpadmm_zero_filled_f32(const float* y, float* x0, int B, int N,
+                            void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+int pnpadmm_zero_filled_f64(const double* y, double* x0, int B, int N,
+                            void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Data-term preparation for the x-update (S1:97,117-118: index = nonzero(mask), La2 = 1/(2 reo)).
+ * Builds, inside the workspace, the pair-packed Hermitian-symmetrised measurement term and the
+ * per-bin blend coefficient for `reo`.  Must precede pnpadmm_xupdate_* / pnpadmm_iterate_* and be
+ * repeated when y, mask or reo change.  (pnpadmm_solve_* calls it itself.)
+ * ------------------------------------------------------------------------------------- */
+int pnpadmm_prepare_f32(const float* y, const uint8_t* mask, int B, int N, int mask_batched,
+                        double reo, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+int pnpadmm_prepare_f64(const double* y, const uint8_t* mask, int B, int N, int mask_batched,
+                        double reo, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a3  closed-form x-update                (S1:115-120 == S4:119-124 == S3:259-264 == S6:266-271)
+ *     X = fft2(z - w);  X[idx] = (La2 X[idx] + y[idx]) / (1 + La2);  x = |Re(ifft2(X))|
+ *   z, w, x : [B][N][N].  xpw (may be NULL) additionally receives x + w (the PnP-L1 denoiser
+ *   input, S3:290).  Uses the workspace prepared by pnpadmm_prepare_*.
+ * ------------------------------------------------------------------------------------- */
+int pnpadmm_xupdate_f32(const float* z, const float* w, float* x, float* xpw,
+                        int B, int N, int mask_batched, int kernel,
+                        void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+int pnpadmm_xupdate_f64(const double* z, const double* w, double* x, double* xpw,
+                        int B, int N, int mask_batched, int kernel,
+                        void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The ADMM loop proper          (S1:111-126 for PROX_L1, S4:115-132 for PROX_CNC), `iters` times:
+ *     x-update (a3);  z-update (a4: S1:123 | a5: S4:127-129);  w = w + x - z (a6: S1:126)
+ *   z, w : in/out state [B][N][N];  x : out, the last x-update (what the reference returns in
+ *   out[n], S1:132).  Needs pnpadmm_prepare_* first.  iters == 0 leaves z, w untouched, x undefined.
+ * ------------------------------------------------------------------------------------- */
+int pnpadmm_iterate_f32(float* x, float* z, float* w, int B, int N, int mask_batched,
+                        int prox, int iters, double lambda1, double reo, double alpha, double b,
+                        int kernel, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+int pnpadmm_iterate_f64(double* x, double* z, double* w, int B, int N, int mask_batched,
+                        int prox, int iters, double lambda1, double reo, double alpha, double b,
+                        int kernel, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+
+/* Whole reconstruction from measurements (S1:100-126 / S4:104-132):
+ *     x = |ifft2(y)|; z = x; w = 0; prepare; iterate.       Outputs x, z, w : [B][N][N]. */
+int pnpadmm_solve_f32(const float* y, const uint8_t* mask, float* x, float* z, float* w,
+                      int B, int N, int mask_batched,
+                      int prox, int iters, double lambda1, double reo, double alpha, double b,
+                      int kernel, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+int pnpadmm_solve_f64(const double* y, const uint8_t* mask, double* x, double* z, double* w,
+                      int B, int N, int mask_batched,
+                      int prox, int iters, double lambda1, double reo, double alpha, double b,
+                      int kernel, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Reference-facing convenience with HOST buffers (what `ADMM_L1(mask, noises, **opts)` /
+ * `ADMM_CNC(...)` do per image, S1:97-132 / S4:101-138, batched):  h_img u8 [B][N][N] gray
+ * levels (divided by 255 on the device like utils_image.uint2single, utils_image.py:181),
+ * h_mask u8 [N][N], h_noise complex64 [N][N][2] (already x3, S1:186), h_x f32 [B][N][N] out.
+ * d_scratch: device buffer of pnpadmm_host_scratch_bytes(B, N) bytes (holds img, y, x, z, w);
+ * copies run on `stream`; returns after the D2H copy has been enqueued (caller syncs the
+ * stream).  Host buffers should be pinned for the copies to be asynchronous.
+ * ------------------------------------------------------------------------------------- */
+size_t pnpadmm_host_scratch_bytes(int B, int N);
+int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, const float* h_noise,
+                                 float* h_x, int B, int N,
+                                 int prox, int iters, double lambda1, double reo, double alpha, double b,
+                                 int kernel, void* d_scratch, size_t scratch_bytes,
+                                 void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pointwise pieces used by the PnP variants (denoiser runs outside this library).
+ * ------------------------------------------------------------------------------------- */
+/* a1  soft(x, c) = fmax(|x| - c, 0) * sign(x), sign(0) = 0                       (S1:18-19) */
+int pnpadmm_soft_f32(const float* x, float* out, double c, size_t n, pnpadmm_stream_t stream);
+int pnpadmm_soft_f64(const double* x, double* out, double c, size_t n, pnpadmm_stream_t stream);
+
+/* a8  t = (1 - alpha) z + alpha (x + w) + coef (z - s),  coef = alpha*reo*lambda1*b
+ *                                                                   (S6:301 == S6:518) */
+int pnpadmm_cnc_combine_f32(const float* z, const float* x, const float* w, const float* s, float* t,
+                            double alpha, double coef, size_t n, pnpadmm_stream_t stream);
+int pnpadmm_cnc_combine_f64(const double* z, const double* x, const double* w, const double* s, double* t,
+                            double alpha, double coef, size_t n, pnpadmm_stream_t stream);
+
+/* a6 + PnP clamps:  w = w + x - z;  if (clamp01) x, z, w = clamp(., 0, 1)
+ *                                                   (S3:293-296 == S6:305-308 == S6:522-525) */
+int pnpadmm_dual_update_f32(float* x, float* z, float* w, int clamp01, size_t n, pnpadmm_stream_t stream);
+int pnpadmm_dual_update_f64(double* x, double* z, double* w, int clamp01, size_t n, pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Measurement helper: runs `iters` dependent-FMA loops on every SM and returns the achieved
+ * non-tensor FP32 FLOP/s in *flops (device-timed with CUDA events, synchronous).  Used by
+ * bench.py as the measured denominator of the FP32 FFT roofline.
+ * ------------------------------------------------------------------------------------- */
+int pnpadmm_measure_fp32_peak(double* flops, pnpadmm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNPADMM_H_ */

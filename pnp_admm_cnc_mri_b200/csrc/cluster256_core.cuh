@@ -1,0 +1,283 @@
+// cluster256_core.cuh — K1: per-thread phases of the cluster-resident 256x256 ADMM solve.
+//
+// One 8-CTA thread-block cluster owns one packed plane (two real images a + i b) for the whole
+// solve.  CTA `rank` owns image rows [32 rank, 32 rank + 32) in the ROW phases and frequency
+// columns [32 rank, 32 rank + 32) in the COLUMN phases; the two all-to-all transposes per iteration
+// are remote shared-memory stores (DSMEM).  512 threads x 16 points = the CTA's whole 32x256 tile
+// lives in registers while it is transformed, so the tile buffers double as the exchange scratch.
+//
+//   shared memory per CTA (fp32):
+//     Zs [32][256] float2   z of image a / b interleaved                         64 KB
+//     B1 [32][256] float2   row-layout tile   (written remotely by the column phase) 64 KB
+//     B2 [256][32] float2   column-layout tile (written remotely by the row phase)   64 KB
+//     TW [16][16]  float2   W_256^(k1*n2)                                           2 KB
+//   registers per thread: 16 complex points + the dual w of its 16 pixels x 2 images (32 floats,
+//   resident for the whole solve).
+//
+// 256-point FFT = 16 x 16 Cooley-Tukey: thread t of a 16-thread group holds x[t + 16 j];
+//   step 1: 16-point DFT over j  -> b[k1];  b[k1] *= W_256^(t k1)
+//   exchange (16x16 transpose inside the group through shared memory)
+//   step 2: 16-point DFT over n2 -> X[t + 16 k2]          (same "t + 16 j" layout as the input)
+// Row phases: group = half-warp (exchange guarded by __syncwarp, XOR-swizzled slots).
+// Column phases: lane = column, warp = t (exchange guarded by __syncthreads, conflict-free
+// because lanes are always contiguous), so every remote store is a 256 B contiguous segment.
+//
+// All functions are HOST+DEVICE: tests/host_emu/ runs the same code for 8 x 512 emulated threads.
+#pragma once
+
+#include "common.cuh"
+
+namespace pnp {
+namespace k1 {
+
+typedef cx<float> cf32;
+
+constexpr int kN = 256;
+constexpr int kCluster = 8;
+constexpr int kRows = 32;          // rows (columns) per CTA
+constexpr int kThreads = 512;
+
+// shared-memory byte offsets
+constexpr int kOffZs = 0;
+constexpr int kOffB1 = kOffZs + kRows * kN * 8;
+constexpr int kOffB2 = kOffB1 + kRows * kN * 8;
+constexpr int kOffTW = kOffB2 + kN * kRows * 8;
+constexpr int kSmemBytes = kOffTW + 256 * 8;
+
+struct ThreadState {
+    cf32 a[16];      // working points
+    float w[32];     // dual variable: w[2j] image a, w[2j+1] image b, pixel column t + 16 j
+};
+
+struct Ctx {
+    int rank;                 // CTA rank in the cluster
+    int tid;                  // thread index in the CTA
+    unsigned char* smem;      // this CTA's dynamic shared memory
+    PNP_HD cf32* Zs() const { return reinterpret_cast<cf32*>(smem + kOffZs); }
+    PNP_HD cf32* B1() const { return reinterpret_cast<cf32*>(smem + kOffB1); }
+    PNP_HD cf32* B2() const { return reinterpret_cast<cf32*>(smem + kOffB2); }
+    PNP_HD const cf32* TW() const { return reinterpret_cast<const cf32*>(smem + kOffTW); }
+    // row-phase mapping: half-warp = one row
+    PNP_HD int row() const { return (tid >> 5) * 2 + ((tid >> 4) & 1); }
+    PNP_HD int rt() const { return tid & 15; }
+    // column-phase mapping: warp = t, lane = column
+    PNP_HD int ct() const { return tid >> 5; }
+    PNP_HD int cc() const { return tid & 31; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// 16-point DFT, natural order in / natural order out, radix 4 x 4, fully unrolled in registers.
+// ---------------------------------------------------------------------------------------------
+#define PNP_C8  0.92387953251128673848f   /* cos(pi/8) */
+#define PNP_S8  0.38268343236508978178f   /* sin(pi/8) */
+#define PNP_R2  0.70710678118654752440f   /* sqrt(1/2) */
+
+template <bool INV> PNP_HD cf32 mul_w16_1(cf32 a) { return twmul<INV>(a, mk<float>(PNP_C8, -PNP_S8)); }
+template <bool INV> PNP_HD cf32 mul_w16_3(cf32 a) { return twmul<INV>(a, mk<float>(PNP_S8, -PNP_C8)); }
+template <bool INV> PNP_HD cf32 mul_w16_9(cf32 a) { return twmul<INV>(a, mk<float>(-PNP_C8, PNP_S8)); }
+// W16^2 = r(1 - i), W16^6 = -r(1 + i)   (conjugated for the inverse)
+template <bool INV> PNP_HD cf32 mul_w16_2(cf32 a) {
+    return INV ? mk<float>(PNP_R2 * (a.re - a.im), PNP_R2 * (a.re + a.im))
+               : mk<float>(PNP_R2 * (a.re + a.im), PNP_R2 * (a.im - a.re));
+}
+template <bool INV> PNP_HD cf32 mul_w16_6(cf32 a) {
+    return INV ? mk<float>(-PNP_R2 * (a.re + a.im), PNP_R2 * (a.re - a.im))
+               : mk<float>(PNP_R2 * (a.im - a.re), -PNP_R2 * (a.re + a.im));
+}
+
+template <bool INV>
+PNP_HD void dft4(cf32 v0, cf32 v1, cf32 v2, cf32 v3, cf32& y0, cf32& y1, cf32& y2, cf32& y3) {
+    cf32 a0 = v0 + v2, a1 = v0 - v2, a2 = v1 + v3, a3 = rot90<INV>(v1 - v3);
+    y0 = a0 + a2; y1 = a1 + a3; y2 = a0 - a2; y3 = a1 - a3;
+}
+
+template <bool INV>
+PNP_HD void fft16(const cf32 (&x)[16], cf32 (&X)[16]) {
+    cf32 t[16];   // t[4*k1 + n2]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2)
+        dft4<INV>(x[n2], x[4 + n2], x[8 + n2], x[12 + n2], t[n2], t[4 + n2], t[8 + n2], t[12 + n2]);
+    // twiddles W16^(n2*k1)
+    t[5] = mul_w16_1<INV>(t[5]);   t[6] = mul_w16_2<INV>(t[6]);    t[7] = mul_w16_3<INV>(t[7]);
+    t[9] = mul_w16_2<INV>(t[9]);   t[10] = rot90<INV>(t[10]);      t[11] = mul_w16_6<INV>(t[11]);
+    t[13] = mul_w16_3<INV>(t[13]); t[14] = mul_w16_6<INV>(t[14]);  t[15] = mul_w16_9<INV>(t[15]);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+        dft4<INV>(t[4 * k1], t[4 * k1 + 1], t[4 * k1 + 2], t[4 * k1 + 3], X[k1], X[k1 + 4], X[k1 + 8], X[k1 + 12]);
+}
+
+// step 1 of the 256-point transform for group-thread t: 16-pt DFT over j, then W_256^(t*k1)
+template <bool INV>
+PNP_HD void fft256_step1(cf32 (&a)[16], int t, const cf32* TW) {
+    cf32 b[16];
+    fft16<INV>(a, b);
+    a[0] = b[0];
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) a[k1] = twmul<INV>(b[k1], TW[k1 * 16 + t]);
+}
+
+template <bool INV>
+PNP_HD void fft256_step2(cf32 (&c)[16], cf32 (&out)[16]) { fft16<INV>(c, out); }
+
+// ---------------------------------------------------------------------------------------------
+// ROW phases (thread = (row, t); holds columns n = t + 16 j of image row 32*rank + row)
+// ---------------------------------------------------------------------------------------------
+struct PlaneIO {            // global-memory planes of the two images of a packed plane
+    const float* z_in_a; const float* w_in_a; const float* z_in_b; const float* w_in_b;   // b may be null
+    float* x_a; float* z_a; float* w_a; float* xpw_a;
+    float* x_b; float* z_b; float* w_b; float* xpw_b;
+};
+
+// prologue: global z, w -> Zs / registers; a = z - w
+PNP_HD void row_load_state(const Ctx& c, ThreadState& s, const PlaneIO& io) {
+    const int row = c.row(), t = c.rt();
+    const int g0 = (kRows * c.rank + row) * kN;
+    cf32* Zs = c.Zs() + row * kN;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int n = t + 16 * j;
+        const float za = io.z_in_a[g0 + n], wa = io.w_in_a[g0 + n];
+        float zb = 0.f, wb = 0.f;
+        if (io.z_in_b) { zb = io.z_in_b[g0 + n]; wb = io.w_in_b[g0 + n]; }
+        Zs[n] = mk<float>(za, zb);
+        s.w[2 * j] = wa; s.w[2 * j + 1] = wb;
+        s.a[j] = mk<float>(za - wa, zb - wb);
+    }
+}
+
+PNP_HD void row_load(const Ctx& c, ThreadState& s) {
+    const cf32* src = c.B1() + c.row() * kN + c.rt();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s.a[j] = src[16 * j];
+}
+
+// step 1 + scatter into the exchange scratch (= this row's slot of B1), XOR swizzle
+template <bool INV>
+PNP_HD void row_step1_write(const Ctx& c, ThreadState& s) {
+    const int t = c.rt();
+    fft256_step1<INV>(s.a, t, c.TW());
+    cf32* sc = c.B1() + c.row() * kN;
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) sc[k1 * 16 + (t ^ k1)] = s.a[k1];
+}
+
+template <bool INV>
+PNP_HD void row_read_step2(const Ctx& c, ThreadState& s) {
+    const int t = c.rt();
+    const cf32* sc = c.B1() + c.row() * kN + t * 16;
+    cf32 v[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = sc[n2 ^ t];
+    fft256_step2<INV>(v, s.a);
+}
+
+// after the inverse row FFT: x = |Re|, |Im|; prox; dual; next FFT input a = z - w.
+// `last`: write x, z, w (and x + w) to global memory.
+PNP_HD void row_prox(const Ctx& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last,
+                     const PlaneIO& io) {
+    const int row = c.row(), t = c.rt();
+    const int g0 = (kRows * c.rank + row) * kN;
+    cf32* Zs = c.Zs() + row * kN;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int n = t + 16 * j;
+        const float xa = pabs(s.a[j].re);
+        const float xb = has_b ? pabs(s.a[j].im) : 0.f;
+        cf32 zz = Zs[n];
+        float za = zz.re, zb = zz.im, wa = s.w[2 * j], wb = s.w[2 * j + 1];
+        if (p.prox == PROX_NONE) {
+            io.x_a[g0 + n] = xa;
+            if (io.xpw_a) io.xpw_a[g0 + n] = xa + wa;
+            if (has_b) {
+                io.x_b[g0 + n] = xb;
+                if (io.xpw_b) io.xpw_b[g0 + n] = xb + wb;
+            }
+            continue;
+        }
+        prox_dual(p, xa, za, wa);
+        if (has_b) prox_dual(p, xb, zb, wb);
+        s.w[2 * j] = wa; s.w[2 * j + 1] = wb;
+        if (last) {
+            io.x_a[g0 + n] = xa; io.z_a[g0 + n] = za; io.w_a[g0 + n] = wa;
+            if (has_b) { io.x_b[g0 + n] = xb; io.z_b[g0 + n] = zb; io.w_b[g0 + n] = wb; }
+        } else {
+            Zs[n] = mk<float>(za, zb);
+            s.a[j] = mk<float>(za - wa, zb - wb);
+        }
+    }
+}
+
+// forward row FFT output X[row][k = t + 16 j] -> CTA (k / 32), B2[32*rank + row][k % 32]
+template <class Remote>
+PNP_HD void row_store_remote(const Ctx& c, const ThreadState& s, const Remote& R) {
+    const int t = c.rt();
+    const int grow = kRows * c.rank + c.row();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int off = kOffB2 + (grow * kRows + t + 16 * (j & 1)) * 8;
+        R.st(j >> 1, off, s.a[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// COLUMN phases (thread = (t = warp, c = lane); holds rows r = t + 16 j of column 32*rank + c)
+// ---------------------------------------------------------------------------------------------
+PNP_HD void col_load(const Ctx& c, ThreadState& s) {
+    const cf32* src = c.B2() + c.ct() * kRows + c.cc();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s.a[j] = src[16 * j * kRows];
+}
+
+template <bool INV>
+PNP_HD void col_step1_write(const Ctx& c, ThreadState& s) {
+    const int t = c.ct();
+    fft256_step1<INV>(s.a, t, c.TW());
+    cf32* sc = c.B2() + t * kRows + c.cc();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) sc[k1 * 16 * kRows] = s.a[k1];
+}
+
+template <bool INV>
+PNP_HD void col_read_step2(const Ctx& c, ThreadState& s) {
+    const cf32* sc = c.B2() + (c.ct() * 16) * kRows + c.cc();
+    cf32 v[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = sc[n2 * kRows];
+    fft256_step2<INV>(v, s.a);
+}
+
+// data-consistency blend on the packed spectrum: a = cf[mcode] * a + G      (see streaming.cuh)
+PNP_HD void col_blend(const Ctx& c, ThreadState& s, const cf32* G, const uint8_t* mcode,
+                      float cf0, float cf1, float cf2) {
+    const int kc = kRows * c.rank + c.cc();
+    const int t = c.ct();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int g = (t + 16 * j) * kN + kc;
+        const cf32 gg = G[g];
+        const int code = mcode[g];
+        const float cf = code == 0 ? cf0 : (code == 1 ? cf1 : cf2);
+        s.a[j] = mk<float>(cf * s.a[j].re + gg.re, cf * s.a[j].im + gg.im);
+    }
+}
+
+// inverse column FFT output at image row r = t + 16 j, column kc -> CTA (r / 32), B1[r % 32][kc]
+template <class Remote>
+PNP_HD void col_store_remote(const Ctx& c, const ThreadState& s, const Remote& R) {
+    const int t = c.ct();
+    const int kc = kRows * c.rank + c.cc();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int off = kOffB1 + ((t + 16 * (j & 1)) * kN + kc) * 8;
+        R.st(j >> 1, off, s.a[j]);
+    }
+}
+
+// TW[k1*16 + n2] = W_256^(k1*n2) from the master table W_4096^m
+PNP_HD void fill_tw(cf32* TW, const cf32* master4096, int i) {
+    const int k1 = i >> 4, n2 = i & 15;
+    TW[i] = master4096[(k1 * n2 * 16) & 4095];
+}
+
+}  // namespace k1
+}  // namespace pnp

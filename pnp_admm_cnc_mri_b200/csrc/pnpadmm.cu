@@ -1,0 +1,627 @@
+// pnpadmm.cu — C ABI (include/pnpadmm.h) of the B200-native ADMM CS-MRI path.
+// Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -shared ... pnpadmm.cu
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/pnpadmm.h"
+#include "cluster256.cuh"
+#include "streaming.cuh"
+
+using namespace pnp;
+
+namespace {
+
+thread_local char g_err[512] = "no error";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(PNPADMM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                  \
+    do {                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(PNPADMM_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int kMaxDevices = 64;
+constexpr size_t kAlign = 256;
+constexpr int kMaxSmemOptin = 227 * 1024;
+
+struct DeviceState {
+    bool ready = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    int max_clusters_256 = 0;
+};
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mu;
+
+size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+template <typename T> constexpr int max_n() { return sizeof(T) == 4 ? 2048 : 1024; }
+
+int check_n(int N, bool f64) {
+    const int mx = f64 ? 1024 : 2048;
+    if (N < 16 || N > mx || (N & (N - 1)) != 0)
+        return fail(PNPADMM_ERR_BAD_SIZE, "N=%d unsupported: need a power of two in [16, %d] for %s", N, mx, f64 ? "f64" : "f32");
+    return PNPADMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// tile shapes of the streaming kernels
+// ------------------------------------------------------------------------------------------
+template <typename T> int rows_lines(int N) { int l = 2048 / N; return l < 1 ? 1 : l; }
+template <typename T> int cols_lines(int N) {
+    const int cap = sizeof(T) == 4 ? 8 : 4;
+    const int maxpts = sizeof(T) == 4 ? 8192 : 4096;
+    int l = maxpts / N;
+    if (l > cap) l = cap;
+    if (l < 1) l = 1;
+    return l;
+}
+template <typename T> size_t rows_smem(int N) { return (size_t)(2 * rows_lines<T>(N) * N + N) * sizeof(cx<T>); }
+template <typename T> size_t cols_smem(int N) { return (size_t)(2 * cols_lines<T>(N) * (N + 4) + N) * sizeof(cx<T>); }
+
+template <typename T>
+cudaError_t set_stream_attrs() {
+    cudaError_t e;
+#define SET_ATTR(k)                                                                             \
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin);    \
+    if (e != cudaSuccess) return e;
+    SET_ATTR((rows_kernel<T, RM_FWD_ZW>))
+    SET_ATTR((rows_kernel<T, RM_FWD_IMG>))
+    SET_ATTR((rows_kernel<T, RM_INV_X>))
+    SET_ATTR((rows_kernel<T, RM_INV_ABS>))
+    SET_ATTR((rows_kernel<T, RM_INV_PROX_FWD>))
+    SET_ATTR((cols_kernel<T, CM_FWD_ACQ>))
+    SET_ATTR((cols_kernel<T, CM_INV>))
+    SET_ATTR((cols_kernel<T, CM_FWD_BLEND_INV>))
+#undef SET_ATTR
+    return cudaSuccess;
+}
+
+int ensure_device(DeviceState** out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(PNPADMM_ERR_CUDA, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState& d = g_dev[dev];
+    if (!d.ready) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        d.sm_count = prop.multiProcessorCount;
+        d.cc_major = prop.major;
+        d.cc_minor = prop.minor;
+        if (prop.major != 10)
+            return fail(PNPADMM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                        dev, prop.major, prop.minor);
+        // master twiddle tables, computed in double precision
+        std::vector<float2> tf(kTwMax);
+        std::vector<double2> td(kTwMax);
+        for (int i = 0; i < kTwMax; ++i) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * i / kTwMax;
+            td[i] = make_double2((double)cosl(a), (double)sinl(a));
+            tf[i] = make_float2((float)td[i].x, (float)td[i].y);
+        }
+        CUDA_TRY(cudaMemcpyToSymbol(g_tw_f32, tf.data(), sizeof(float2) * kTwMax));
+        CUDA_TRY(cudaMemcpyToSymbol(g_tw_f64, td.data(), sizeof(double2) * kTwMax));
+        CUDA_TRY(set_stream_attrs<float>());
+        CUDA_TRY(set_stream_attrs<double>());
+        CUDA_TRY(cudaFuncSetAttribute(k1::cluster256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1::kSmemBytes));
+        // how many 8-CTA clusters of K1 can be co-resident
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(k1::kCluster * d.sm_count);
+        cfg.blockDim = dim3(k1::kThreads);
+        cfg.dynamicSmemBytes = k1::kSmemBytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = k1::kCluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int ncl = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k1::cluster256_kernel, &cfg);
+        if (e != cudaSuccess) { ncl = 0; (void)cudaGetLastError(); }
+        d.max_clusters_256 = ncl;
+        d.ready = true;
+    }
+    *out = &d;
+    return PNPADMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct Workspace {
+    T* cf;            // [3] blend coefficients written by prepare
+    cx<T>* K;         // [P][N][N]
+    cx<T>* G;         // [P][N][N]
+    cx<T>* T1;        // [B][N][N] per-image complex scratch
+    uint8_t* mcode;   // [N][N] or [P][N][N]
+    int P, solo;
+};
+
+size_t ws_bytes_impl(int B, int N, size_t elt, int mask_batched) {
+    const size_t nn = (size_t)N * N;
+    const size_t P = mask_batched ? (size_t)B : (size_t)(B + 1) / 2;
+    size_t s = kAlign;                       // header (cf table)
+    s += align_up((size_t)B * nn * 2 * elt); // T1
+    s += align_up(P * nn * 2 * elt);         // K
+    s += align_up(P * nn * 2 * elt);         // G
+    s += align_up((mask_batched ? P : 1) * nn);
+    return s;
+}
+
+// `scratch_only`: the call touches only the header + per-image scratch T1 (acquire, zero_filled),
+// whose position does not depend on the pairing, so any workspace sized for (B, N) is accepted.
+template <typename T>
+int carve(void* ws, size_t ws_bytes, int B, int N, int mask_batched, Workspace<T>* out, bool scratch_only = false) {
+    if (!ws) return fail(PNPADMM_ERR_WORKSPACE, "workspace is NULL");
+    if (((uintptr_t)ws) % kAlign) return fail(PNPADMM_ERR_WORKSPACE, "workspace must be %zu-byte aligned", kAlign);
+    const size_t nn = (size_t)N * N;
+    const size_t need = scratch_only ? kAlign + align_up((size_t)B * nn * 2 * sizeof(T))
+                                     : ws_bytes_impl(B, N, sizeof(T), mask_batched);
+    if (ws_bytes < need) return fail(PNPADMM_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, need);
+    const size_t P = mask_batched ? (size_t)B : (size_t)(B + 1) / 2;
+    unsigned char* p = (unsigned char*)ws;
+    out->cf = (T*)p; p += kAlign;
+    out->T1 = (cx<T>*)p; p += align_up((size_t)B * nn * 2 * sizeof(T));
+    out->K = (cx<T>*)p; p += align_up(P * nn * 2 * sizeof(T));
+    out->G = (cx<T>*)p; p += align_up(P * nn * 2 * sizeof(T));
+    out->mcode = p;
+    out->P = (int)P;
+    out->solo = mask_batched ? 1 : 0;
+    return PNPADMM_OK;
+}
+
+template <typename T>
+ProxParams<T> make_prox(int prox, double lambda1, double reo, double alpha, double b) {
+    ProxParams<T> p;
+    p.prox = prox;
+    p.thr_l1 = (T)(reo * lambda1);
+    p.inv_b = (T)(1.0 / b);
+    p.one_m_alpha = (T)(1.0 - alpha);
+    p.alpha = (T)alpha;
+    p.coef = (T)(alpha * reo * lambda1 * b);
+    p.thr_cnc = (T)(alpha * reo * lambda1);
+    return p;
+}
+
+int check_prox(int prox, int iters, double reo, double b) {
+    if (prox != PNPADMM_PROX_L1 && prox != PNPADMM_PROX_CNC) return fail(PNPADMM_ERR_BAD_ARG, "unknown prox %d", prox);
+    if (iters < 0) return fail(PNPADMM_ERR_BAD_ARG, "iters=%d < 0", iters);
+    if (!(reo > 0.0)) return fail(PNPADMM_ERR_BAD_ARG, "reo=%g must be > 0", reo);
+    if (prox == PNPADMM_PROX_CNC && b == 0.0) return fail(PNPADMM_ERR_BAD_ARG, "b must be non-zero for PROX_CNC");
+    return PNPADMM_OK;
+}
+
+template <typename T>
+StreamParams<T> base_params(const Workspace<T>& w, int B, int N) {
+    StreamParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.log2N = ilog2(N); p.B = B; p.P = w.P; p.solo = w.solo;
+    p.K = w.K; p.G = w.G; p.mcode = w.mcode; p.mcode_batched = w.solo;
+    p.cf = w.cf;
+    p.scale = (T)(1.0 / ((double)N * N));
+    return p;
+}
+
+int grid_1d(size_t n, int sm_count) {
+    size_t g = (n + 255) / 256;
+    const size_t cap = (size_t)sm_count * 16;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------
+// implementations (templated on precision)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int acquire_impl(const T* img, const uint8_t* mask, const T* noise, T* y, int B, int N, int mask_batched,
+                 int noise_batched, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!img || !mask || !noise || !y || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "acquire: NULL pointer or B <= 0");
+    int rc = check_n(N, sizeof(T) == 8); if (rc) return rc;
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, 0, &w, true); if (rc) return rc;
+    StreamParams<T> p = base_params(w, B, N);
+    p.img = img; p.cout = w.T1;
+    p.lines = rows_lines<T>(N);
+    rows_kernel<T, RM_FWD_IMG><<<dim3(N / p.lines, B), 256, rows_smem<T>(N), st>>>(p);
+    LAUNCH_CHECK("rows_kernel<FWD_IMG>");
+    p.cin = w.T1; p.cout = reinterpret_cast<cx<T>*>(y);
+    p.mask = mask; p.mask_batched = mask_batched;
+    p.noise = reinterpret_cast<const cx<T>*>(noise); p.noise_batched = noise_batched;
+    p.lines = cols_lines<T>(N);
+    cols_kernel<T, CM_FWD_ACQ><<<dim3(N / p.lines, B), 256, cols_smem<T>(N), st>>>(p);
+    LAUNCH_CHECK("cols_kernel<FWD_ACQ>");
+    return PNPADMM_OK;
+}
+
+template <typename T>
+int zero_filled_impl(const T* y, T* x0, int B, int N, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!y || !x0 || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "zero_filled: NULL pointer or B <= 0");
+    int rc = check_n(N, sizeof(T) == 8); if (rc) return rc;
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, 0, &w, true); if (rc) return rc;
+    StreamParams<T> p = base_params(w, B, N);
+    p.cin = reinterpret_cast<const cx<T>*>(y); p.cout = w.T1;
+    p.lines = cols_lines<T>(N);
+    cols_kernel<T, CM_INV><<<dim3(N / p.lines, B), 256, cols_smem<T>(N), st>>>(p);
+    LAUNCH_CHECK("cols_kernel<INV>");
+    p.cin = w.T1; p.x = x0;
+    p.lines = rows_lines<T>(N);
+    rows_kernel<T, RM_INV_ABS><<<dim3(N / p.lines, B), 256, rows_smem<T>(N), st>>>(p);
+    LAUNCH_CHECK("rows_kernel<INV_ABS>");
+    return PNPADMM_OK;
+}
+
+template <typename T>
+__global__ void write_cf_kernel(T* cf, T c0, T c1, T c2) { cf[0] = c0; cf[1] = c1; cf[2] = c2; }
+
+template <typename T>
+int prepare_impl(const T* y, const uint8_t* mask, int B, int N, int mask_batched, double reo, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+    if (!y || !mask || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "prepare: NULL pointer or B <= 0");
+    if (!(reo > 0.0)) return fail(PNPADMM_ERR_BAD_ARG, "reo=%g must be > 0", reo);
+    int rc = check_n(N, sizeof(T) == 8); if (rc) return rc;
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, mask_batched, &w); if (rc) return rc;
+    const double La2 = 1.0 / 2.0 / reo;            // S1:117
+    const double g = 1.0 / (1.0 + La2);
+    const double n2 = (double)N * N;
+    write_cf_kernel<T><<<1, 1, 0, st>>>(w.cf, (T)(1.0 / n2), (T)((1.0 - 0.5 * g) / n2), (T)((1.0 - g) / n2));
+    LAUNCH_CHECK("write_cf_kernel");
+    const size_t total = (size_t)w.P * N * N;
+    prepare_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const cx<T>*>(y), mask, w.G,
+                                                                      w.mcode, B, w.P, N, w.solo, mask_batched,
+                                                                      (T)(g / n2));
+    LAUNCH_CHECK("prepare_kernel");
+    return PNPADMM_OK;
+}
+
+int pick_kernel(int kernel, int N, bool f64, const DeviceState* d, bool* use_cluster) {
+    if (kernel != PNPADMM_KERNEL_AUTO && kernel != PNPADMM_KERNEL_CLUSTER && kernel != PNPADMM_KERNEL_STREAMING)
+        return fail(PNPADMM_ERR_BAD_ARG, "unknown kernel selector %d", kernel);
+    const bool can = (N == 256) && !f64 && d->max_clusters_256 > 0;
+    if (kernel == PNPADMM_KERNEL_CLUSTER && !can)
+        return fail(PNPADMM_ERR_UNSUPPORTED, "cluster kernel needs N == 256, f32 and a device that can co-schedule an 8-CTA cluster (N=%d, f64=%d, max clusters=%d)",
+                    N, (int)f64, d->max_clusters_256);
+    *use_cluster = (kernel == PNPADMM_KERNEL_STREAMING) ? false : can;
+    return PNPADMM_OK;
+}
+
+int launch_cluster(const k1::ClusterParams& cp, const DeviceState* d, cudaStream_t st) {
+    int ncl = cp.P < d->max_clusters_256 ? cp.P : d->max_clusters_256;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(ncl * k1::kCluster);
+    cfg.blockDim = dim3(k1::kThreads);
+    cfg.dynamicSmemBytes = k1::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = k1::kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_kernel, cp));
+    return PNPADMM_OK;
+}
+
+template <typename T> struct ClusterDispatch {
+    static int run(const Workspace<T>&, const T*, const T*, T*, T*, T*, T*, int, int, const ProxParams<T>&,
+                   const DeviceState*, cudaStream_t) {
+        return fail(PNPADMM_ERR_UNSUPPORTED, "cluster kernel is f32 only");
+    }
+};
+template <> struct ClusterDispatch<float> {
+    static int run(const Workspace<float>& w, const float* z_in, const float* w_in, float* x, float* z, float* wo,
+                   float* xpw, int B, int iters, const ProxParams<float>& pp, const DeviceState* d, cudaStream_t st) {
+        k1::ClusterParams cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.B = B; cp.P = w.P; cp.solo = w.solo; cp.iters = iters;
+        cp.z_in = z_in; cp.w_in = w_in; cp.x = x; cp.z = z; cp.w = wo; cp.xpw = xpw;
+        cp.G = reinterpret_cast<const k1::cf32*>(w.G); cp.mcode = w.mcode; cp.mcode_batched = w.solo;
+        cp.cf = w.cf;
+        cp.prox = pp;
+        return launch_cluster(cp, d, st);
+    }
+};
+
+template <typename T>
+int xupdate_impl(const T* z, const T* wv, T* x, T* xpw, int B, int N, int mask_batched, int kernel, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+    if (!z || !wv || !x || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "xupdate: NULL pointer or B <= 0");
+    int rc = check_n(N, sizeof(T) == 8); if (rc) return rc;
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, mask_batched, &w); if (rc) return rc;
+    bool use_cluster; rc = pick_kernel(kernel, N, sizeof(T) == 8, d, &use_cluster); if (rc) return rc;
+    if (use_cluster) {
+        ProxParams<T> pp = make_prox<T>(PROX_NONE, 0, 1, 0, 1);
+        return ClusterDispatch<T>::run(w, z, wv, x, nullptr, nullptr, xpw, B, 1, pp, d, st);
+    }
+    StreamParams<T> p = base_params(w, B, N);
+    p.z = const_cast<T*>(z); p.w = const_cast<T*>(wv); p.x = x; p.xpw = xpw;
+    p.lines = rows_lines<T>(N);
+    rows_kernel<T, RM_FWD_ZW><<<dim3(N / p.lines, w.P), 256, rows_smem<T>(N), st>>>(p);
+    LAUNCH_CHECK("rows_kernel<FWD_ZW>");
+    p.lines = cols_lines<T>(N);
+    cols_kernel<T, CM_FWD_BLEND_INV><<<dim3(N / p.lines, w.P), 256, cols_smem<T>(N), st>>>(p);
+    LAUNCH_CHECK("cols_kernel<FWD_BLEND_INV>");
+    p.lines = rows_lines<T>(N);
+    rows_kernel<T, RM_INV_X><<<dim3(N / p.lines, w.P), 256, rows_smem<T>(N), st>>>(p);
+    LAUNCH_CHECK("rows_kernel<INV_X>");
+    return PNPADMM_OK;
+}
+
+template <typename T>
+int iterate_impl(T* x, T* z, T* wv, int B, int N, int mask_batched, int prox, int iters, double lambda1, double reo,
+                 double alpha, double b, int kernel, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!x || !z || !wv || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "iterate: NULL pointer or B <= 0");
+    int rc = check_n(N, sizeof(T) == 8); if (rc) return rc;
+    rc = check_prox(prox, iters, reo, b); if (rc) return rc;
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, mask_batched, &w); if (rc) return rc;
+    bool use_cluster; rc = pick_kernel(kernel, N, sizeof(T) == 8, d, &use_cluster); if (rc) return rc;
+    if (iters == 0) return PNPADMM_OK;
+    ProxParams<T> pp = make_prox<T>(prox, lambda1, reo, alpha, b);
+    if (use_cluster) return ClusterDispatch<T>::run(w, z, wv, x, z, wv, nullptr, B, iters, pp, d, st);
+
+    StreamParams<T> p = base_params(w, B, N);
+    p.z = z; p.w = wv; p.x = x; p.prox = pp;
+    const int rl = rows_lines<T>(N), cl = cols_lines<T>(N);
+    const size_t rs = rows_smem<T>(N), cs = cols_smem<T>(N);
+    p.lines = rl;
+    rows_kernel<T, RM_FWD_ZW><<<dim3(N / rl, w.P), 256, rs, st>>>(p);
+    LAUNCH_CHECK("rows_kernel<FWD_ZW>");
+    for (int it = 0; it < iters; ++it) {
+        p.lines = cl;
+        cols_kernel<T, CM_FWD_BLEND_INV><<<dim3(N / cl, w.P), 256, cs, st>>>(p);
+        p.lines = rl;
+        p.last = (it == iters - 1);
+        rows_kernel<T, RM_INV_PROX_FWD><<<dim3(N / rl, w.P), 256, rs, st>>>(p);
+    }
+    LAUNCH_CHECK("streaming iteration kernels");
+    return PNPADMM_OK;
+}
+
+template <typename T>
+int solve_impl(const T* y, const uint8_t* mask, T* x, T* z, T* wv, int B, int N, int mask_batched, int prox, int iters,
+               double lambda1, double reo, double alpha, double b, int kernel, void* ws, size_t ws_bytes,
+               cudaStream_t st) {
+    if (!y || !mask || !x || !z || !wv || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "solve: NULL pointer or B <= 0");
+    int rc = check_n(N, sizeof(T) == 8); if (rc) return rc;
+    rc = check_prox(prox, iters, reo, b); if (rc) return rc;
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    // x = |ifft2(y)|; z = x; w = 0                                              (S1:100-105)
+    rc = zero_filled_impl<T>(y, z, B, N, ws, ws_bytes, st); if (rc) return rc;
+    const size_t n = (size_t)B * N * N;
+    copy_zero_kernel<T><<<grid_1d(n, d->sm_count), 256, 0, st>>>(z, x, wv, n);
+    LAUNCH_CHECK("copy_zero_kernel");
+    rc = prepare_impl<T>(y, mask, B, N, mask_batched, reo, ws, ws_bytes, st); if (rc) return rc;
+    return iterate_impl<T>(x, z, wv, B, N, mask_batched, prox, iters, lambda1, reo, alpha, b, kernel, ws, ws_bytes, st);
+}
+
+template <typename T>
+int soft_impl(const T* x, T* out, double c, size_t n, cudaStream_t st) {
+    if (!x || !out) return fail(PNPADMM_ERR_BAD_ARG, "soft: NULL pointer");
+    if (n == 0) return PNPADMM_OK;
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    soft_kernel<T><<<grid_1d(n, d->sm_count), 256, 0, st>>>(x, out, (T)c, n);
+    LAUNCH_CHECK("soft_kernel");
+    return PNPADMM_OK;
+}
+
+template <typename T>
+int combine_impl(const T* z, const T* x, const T* w, const T* s, T* t, double alpha, double coef, size_t n,
+                 cudaStream_t st) {
+    if (!z || !x || !w || !s || !t) return fail(PNPADMM_ERR_BAD_ARG, "cnc_combine: NULL pointer");
+    if (n == 0) return PNPADMM_OK;
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    cnc_combine_kernel<T><<<grid_1d(n, d->sm_count), 256, 0, st>>>(z, x, w, s, t, (T)(1.0 - alpha), (T)alpha, (T)coef, n);
+    LAUNCH_CHECK("cnc_combine_kernel");
+    return PNPADMM_OK;
+}
+
+template <typename T>
+int dual_impl(T* x, T* z, T* w, int clamp, size_t n, cudaStream_t st) {
+    if (!x || !z || !w) return fail(PNPADMM_ERR_BAD_ARG, "dual_update: NULL pointer");
+    if (n == 0) return PNPADMM_OK;
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    dual_update_kernel<T><<<grid_1d(n, d->sm_count), 256, 0, st>>>(x, z, w, clamp, n);
+    LAUNCH_CHECK("dual_update_kernel");
+    return PNPADMM_OK;
+}
+
+// FP32 FMA throughput probe: 8 independent FMA chains per thread.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float b, float c) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// extern "C" surface
+// ==========================================================================================
+extern "C" {
+
+int pnpadmm_abi_version(void) { return PNPADMM_ABI_VERSION; }
+const char* pnpadmm_last_error_string(void) { return g_err; }
+
+int pnpadmm_device_info(int* sm_count, int* max_clusters_256, int* cc_major, int* cc_minor) {
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    if (sm_count) *sm_count = d->sm_count;
+    if (max_clusters_256) *max_clusters_256 = d->max_clusters_256;
+    if (cc_major) *cc_major = d->cc_major;
+    if (cc_minor) *cc_minor = d->cc_minor;
+    return PNPADMM_OK;
+}
+
+size_t pnpadmm_workspace_bytes(int B, int N, int is_f64, int mask_batched) {
+    if (B <= 0 || N <= 0) return 0;
+    return ws_bytes_impl(B, N, is_f64 ? 8 : 4, mask_batched);
+}
+
+#define ST(s) ((cudaStream_t)(s))
+
+int pnpadmm_acquire_f32(const float* img, const uint8_t* mask, const float* noise, float* y, int B, int N,
+                        int mask_batched, int noise_batched, void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return acquire_impl<float>(img, mask, noise, y, B, N, mask_batched, noise_batched, ws, wsb, ST(s));
+}
+int pnpadmm_acquire_f64(const double* img, const uint8_t* mask, const double* noise, double* y, int B, int N,
+                        int mask_batched, int noise_batched, void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return acquire_impl<double>(img, mask, noise, y, B, N, mask_batched, noise_batched, ws, wsb, ST(s));
+}
+int pnpadmm_zero_filled_f32(const float* y, float* x0, int B, int N, void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return zero_filled_impl<float>(y, x0, B, N, ws, wsb, ST(s));
+}
+int pnpadmm_zero_filled_f64(const double* y, double* x0, int B, int N, void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return zero_filled_impl<double>(y, x0, B, N, ws, wsb, ST(s));
+}
+int pnpadmm_prepare_f32(const float* y, const uint8_t* mask, int B, int N, int mb, double reo, void* ws, size_t wsb,
+                        pnpadmm_stream_t s) {
+    return prepare_impl<float>(y, mask, B, N, mb, reo, ws, wsb, ST(s));
+}
+int pnpadmm_prepare_f64(const double* y, const uint8_t* mask, int B, int N, int mb, double reo, void* ws, size_t wsb,
+                        pnpadmm_stream_t s) {
+    return prepare_impl<double>(y, mask, B, N, mb, reo, ws, wsb, ST(s));
+}
+int pnpadmm_xupdate_f32(const float* z, const float* w, float* x, float* xpw, int B, int N, int mb, int kernel,
+                        void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return xupdate_impl<float>(z, w, x, xpw, B, N, mb, kernel, ws, wsb, ST(s));
+}
+int pnpadmm_xupdate_f64(const double* z, const double* w, double* x, double* xpw, int B, int N, int mb, int kernel,
+                        void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return xupdate_impl<double>(z, w, x, xpw, B, N, mb, kernel, ws, wsb, ST(s));
+}
+int pnpadmm_iterate_f32(float* x, float* z, float* w, int B, int N, int mb, int prox, int iters, double lambda1,
+                        double reo, double alpha, double b, int kernel, void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return iterate_impl<float>(x, z, w, B, N, mb, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, ST(s));
+}
+int pnpadmm_iterate_f64(double* x, double* z, double* w, int B, int N, int mb, int prox, int iters, double lambda1,
+                        double reo, double alpha, double b, int kernel, void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return iterate_impl<double>(x, z, w, B, N, mb, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, ST(s));
+}
+int pnpadmm_solve_f32(const float* y, const uint8_t* mask, float* x, float* z, float* w, int B, int N, int mb,
+                      int prox, int iters, double lambda1, double reo, double alpha, double b, int kernel, void* ws,
+                      size_t wsb, pnpadmm_stream_t s) {
+    return solve_impl<float>(y, mask, x, z, w, B, N, mb, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, ST(s));
+}
+int pnpadmm_solve_f64(const double* y, const uint8_t* mask, double* x, double* z, double* w, int B, int N, int mb,
+                      int prox, int iters, double lambda1, double reo, double alpha, double b, int kernel, void* ws,
+                      size_t wsb, pnpadmm_stream_t s) {
+    return solve_impl<double>(y, mask, x, z, w, B, N, mb, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, ST(s));
+}
+
+size_t pnpadmm_host_scratch_bytes(int B, int N) {
+    if (B <= 0 || N <= 0) return 0;
+    const size_t nn = (size_t)N * N, n = (size_t)B * nn;
+    // img u8, mask u8, noise c64, img f32, y c64, x, z, w f32
+    return align_up(n) + align_up(nn) + align_up(nn * 8) + align_up(n * 4) + align_up(n * 8) + 3 * align_up(n * 4);
+}
+
+int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, const float* h_noise, float* h_x, int B,
+                                 int N, int prox, int iters, double lambda1, double reo, double alpha, double b,
+                                 int kernel, void* d_scratch, size_t scratch_bytes, void* ws, size_t wsb,
+                                 pnpadmm_stream_t s) {
+    if (!h_img || !h_mask || !h_noise || !h_x || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host: NULL pointer or B <= 0");
+    int rc = check_n(N, false); if (rc) return rc;
+    if (!d_scratch || ((uintptr_t)d_scratch) % kAlign || scratch_bytes < pnpadmm_host_scratch_bytes(B, N))
+        return fail(PNPADMM_ERR_WORKSPACE, "reconstruct_host: d_scratch NULL, misaligned or smaller than %zu bytes",
+                    pnpadmm_host_scratch_bytes(B, N));
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    cudaStream_t st = ST(s);
+    const size_t nn = (size_t)N * N, n = (size_t)B * nn;
+    unsigned char* p = (unsigned char*)d_scratch;
+    uint8_t* d_img8 = p; p += align_up(n);
+    uint8_t* d_mask = p; p += align_up(nn);
+    float* d_noise = (float*)p; p += align_up(nn * 8);
+    float* d_img = (float*)p; p += align_up(n * 4);
+    float* d_y = (float*)p; p += align_up(n * 8);
+    float* d_x = (float*)p; p += align_up(n * 4);
+    float* d_z = (float*)p; p += align_up(n * 4);
+    float* d_w = (float*)p;
+    CUDA_TRY(cudaMemcpyAsync(d_img8, h_img, n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_mask, h_mask, nn, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_noise, h_noise, nn * 8, cudaMemcpyHostToDevice, st));
+    u8_to_unit_kernel<float><<<grid_1d(n, d->sm_count), 256, 0, st>>>(d_img8, d_img, n);
+    LAUNCH_CHECK("u8_to_unit_kernel");
+    rc = acquire_impl<float>(d_img, d_mask, d_noise, d_y, B, N, 0, 0, ws, wsb, st); if (rc) return rc;
+    rc = solve_impl<float>(d_y, d_mask, d_x, d_z, d_w, B, N, 0, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_x, d_x, n * 4, cudaMemcpyDeviceToHost, st));
+    return PNPADMM_OK;
+}
+
+int pnpadmm_soft_f32(const float* x, float* out, double c, size_t n, pnpadmm_stream_t s) { return soft_impl<float>(x, out, c, n, ST(s)); }
+int pnpadmm_soft_f64(const double* x, double* out, double c, size_t n, pnpadmm_stream_t s) { return soft_impl<double>(x, out, c, n, ST(s)); }
+int pnpadmm_cnc_combine_f32(const float* z, const float* x, const float* w, const float* sd, float* t, double alpha,
+                            double coef, size_t n, pnpadmm_stream_t s) {
+    return combine_impl<float>(z, x, w, sd, t, alpha, coef, n, ST(s));
+}
+int pnpadmm_cnc_combine_f64(const double* z, const double* x, const double* w, const double* sd, double* t,
+                            double alpha, double coef, size_t n, pnpadmm_stream_t s) {
+    return combine_impl<double>(z, x, w, sd, t, alpha, coef, n, ST(s));
+}
+int pnpadmm_dual_update_f32(float* x, float* z, float* w, int clamp01, size_t n, pnpadmm_stream_t s) { return dual_impl<float>(x, z, w, clamp01, n, ST(s)); }
+int pnpadmm_dual_update_f64(double* x, double* z, double* w, int clamp01, size_t n, pnpadmm_stream_t s) { return dual_impl<double>(x, z, w, clamp01, n, ST(s)); }
+
+int pnpadmm_measure_fp32_peak(double* flops, pnpadmm_stream_t s) {
+    if (!flops) return fail(PNPADMM_ERR_BAD_ARG, "measure_fp32_peak: NULL pointer");
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    cudaStream_t st = ST(s);
+    const int blocks = d->sm_count * 8, threads = 256, iters = 4096;
+    float* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, sizeof(float) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    fma_peak_kernel<<<blocks, threads, 0, st>>>(out, 64, 1.0001f, 0.5f);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, st));
+        fma_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 1.0001f, 0.5f);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    LAUNCH_CHECK("fma_peak_kernel");
+    *flops = 2.0 * 64.0 * iters * (double)blocks * threads / (best * 1e-3);
+    return PNPADMM_OK;
+}
+
+}  // extern "C"

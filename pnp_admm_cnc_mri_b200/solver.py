@@ -1,0 +1,243 @@
+"""Batched host API of the ADMM reconstruction path (PyTorch is plumbing only: device memory and
+streams; all arithmetic runs in libpnpadmm.so through the C ABI of include/pnpadmm.h).
+
+    x = admm_solve(images[B,N,N], mask[N,N] | [B,N,N], noises[N,N] | [B,N,N],
+                   prox='l1' | 'cnc', iter_num=, lambda1=, reo=, alpha=, b=, dtype='float32')
+
+mirrors what the reference does per image inside ``ADMM_L1`` (S1:97-132) / ``ADMM_CNC``
+(S4:101-138): acquisition ``y = fft2(img)*mask + noises``, zero-filled start, ``iter_num`` ADMM
+iterations, returns the last x-update.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _abi
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+_PROX = {'l1': _abi.PROX_L1, 'cnc': _abi.PROX_CNC}
+_KERNEL = {'auto': _abi.KERNEL_AUTO, 'cluster': _abi.KERNEL_CLUSTER, 'streaming': _abi.KERNEL_STREAMING}
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _abi.PnpAdmmError('no CUDA device visible: this package has no CPU path')
+    return torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class AdmmSolver:
+    """Owns the device workspace for a fixed (B, N, dtype, mask layout) and exposes the C-ABI calls
+    on torch CUDA tensors.  All calls are asynchronous on the current torch stream."""
+
+    def __init__(self, B: int, N: int, dtype: str = 'float32', mask_batched: bool = False, device=None):
+        if dtype not in ('float32', 'float64'):
+            raise ValueError("dtype must be 'float32' or 'float64'")
+        self.lib = _abi.load()
+        self.device = _require_cuda(device)
+        self.B, self.N = int(B), int(N)
+        self.f64 = dtype == 'float64'
+        self.sfx = 'f64' if self.f64 else 'f32'
+        self.rdtype = torch.float64 if self.f64 else torch.float32
+        self.cdtype = torch.complex128 if self.f64 else torch.complex64
+        self.mask_batched = bool(mask_batched)
+        nbytes = self.lib.pnpadmm_workspace_bytes(self.B, self.N, int(self.f64), int(self.mask_batched))
+        if nbytes == 0:
+            raise ValueError(f'bad problem size B={B}, N={N}')
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.ws_bytes = nbytes
+        self._prepared_reo = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _fn(self, name):
+        return getattr(self.lib, f'pnpadmm_{name}_{self.sfx}')
+
+    def _real(self, a: ArrayLike, name: str) -> torch.Tensor:
+        t = torch.as_tensor(a)
+        t = t.to(device=self.device, dtype=self.rdtype).contiguous()
+        if t.shape != (self.B, self.N, self.N):
+            raise ValueError(f'{name} must have shape {(self.B, self.N, self.N)}, got {tuple(t.shape)}')
+        return t
+
+    def _mask(self, mask: ArrayLike) -> torch.Tensor:
+        m = torch.as_tensor(mask)
+        m = (m != 0).to(device=self.device, dtype=torch.uint8).contiguous()
+        want = (self.B, self.N, self.N) if self.mask_batched else (self.N, self.N)
+        if m.shape != want:
+            raise ValueError(f'mask must have shape {want}, got {tuple(m.shape)}')
+        return m
+
+    def new(self) -> torch.Tensor:
+        return torch.empty((self.B, self.N, self.N), dtype=self.rdtype, device=self.device)
+
+    # -- a2 ----------------------------------------------------------------------------------
+    def acquire(self, img: ArrayLike, mask: ArrayLike, noises: ArrayLike) -> torch.Tensor:
+        """y = fft2(img) * mask + noises (S1:99)."""
+        img = self._real(img, 'img')
+        m = self._mask(mask)
+        nz = torch.as_tensor(noises).to(device=self.device, dtype=self.cdtype).contiguous()
+        if nz.shape == (self.N, self.N):
+            nb = 0
+        elif nz.shape == (self.B, self.N, self.N):
+            nb = 1
+        else:
+            raise ValueError(f'noises must be (N,N) or (B,N,N), got {tuple(nz.shape)}')
+        y = torch.empty((self.B, self.N, self.N), dtype=self.cdtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self._fn('acquire')(img.data_ptr(), m.data_ptr(), nz.data_ptr(), y.data_ptr(), self.B, self.N,
+                                           int(self.mask_batched), nb, self.ws.data_ptr(), self.ws_bytes, _stream_ptr()))
+        return y
+
+    def zero_filled(self, y: torch.Tensor) -> torch.Tensor:
+        """x0 = |ifft2(y)| (S1:100,104)."""
+        y = self._cplx(y)
+        x0 = self.new()
+        with torch.cuda.device(self.device):
+            _abi.check(self._fn('zero_filled')(y.data_ptr(), x0.data_ptr(), self.B, self.N, self.ws.data_ptr(),
+                                               self.ws_bytes, _stream_ptr()))
+        return x0
+
+    def _cplx(self, y: ArrayLike) -> torch.Tensor:
+        y = torch.as_tensor(y).to(device=self.device, dtype=self.cdtype).contiguous()
+        if y.shape != (self.B, self.N, self.N):
+            raise ValueError(f'y must have shape {(self.B, self.N, self.N)}, got {tuple(y.shape)}')
+        return y
+
+    # -- data term ----------------------------------------------------------------------------
+    def prepare(self, y: torch.Tensor, mask: ArrayLike, reo: float) -> None:
+        y = self._cplx(y)
+        m = self._mask(mask)
+        with torch.cuda.device(self.device):
+            _abi.check(self._fn('prepare')(y.data_ptr(), m.data_ptr(), self.B, self.N, int(self.mask_batched), float(reo),
+                                           self.ws.data_ptr(), self.ws_bytes, _stream_ptr()))
+        self._prepared_reo = float(reo)
+
+    # -- a3 ----------------------------------------------------------------------------------
+    def xupdate(self, z: torch.Tensor, w: torch.Tensor, want_xpw: bool = False, kernel: str = 'auto'):
+        """x = |Re(ifft2(blend(fft2(z - w))))| (S1:115-120); optionally also x + w."""
+        if self._prepared_reo is None:
+            raise _abi.PnpAdmmError('xupdate called before prepare()')
+        z, w = self._real(z, 'z'), self._real(w, 'w')
+        x = self.new()
+        xpw = self.new() if want_xpw else None
+        with torch.cuda.device(self.device):
+            _abi.check(self._fn('xupdate')(z.data_ptr(), w.data_ptr(), x.data_ptr(), _ptr(xpw), self.B, self.N,
+                                           int(self.mask_batched), _KERNEL[kernel], self.ws.data_ptr(), self.ws_bytes,
+                                           _stream_ptr()))
+        return (x, xpw) if want_xpw else x
+
+    # -- the loop -----------------------------------------------------------------------------
+    def iterate(self, x: torch.Tensor, z: torch.Tensor, w: torch.Tensor, prox: str, iter_num: int, lambda1: float,
+                reo: float, alpha: float = 0.0, b: float = 1.0, kernel: str = 'auto') -> None:
+        """`iter_num` ADMM iterations in place on (z, w); x receives the last x-update."""
+        if self._prepared_reo is None or self._prepared_reo != float(reo):
+            raise _abi.PnpAdmmError('iterate: call prepare(y, mask, reo) with the same reo first')
+        for t, n in ((x, 'x'), (z, 'z'), (w, 'w')):
+            if not (t.is_cuda and t.dtype == self.rdtype and t.is_contiguous() and t.shape == (self.B, self.N, self.N)):
+                raise ValueError(f'{n} must be a contiguous CUDA {self.rdtype} tensor of shape {(self.B, self.N, self.N)}')
+        with torch.cuda.device(self.device):
+            _abi.check(self._fn('iterate')(x.data_ptr(), z.data_ptr(), w.data_ptr(), self.B, self.N,
+                                           int(self.mask_batched), _PROX[prox], int(iter_num), float(lambda1), float(reo),
+                                           float(alpha), float(b), _KERNEL[kernel], self.ws.data_ptr(), self.ws_bytes,
+                                           _stream_ptr()))
+
+    def solve(self, y: torch.Tensor, mask: ArrayLike, prox: str, iter_num: int, lambda1: float, reo: float,
+              alpha: float = 0.0, b: float = 1.0, kernel: str = 'auto') -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """x0 = |ifft2(y)|, z = x0, w = 0, then the loop (S1:100-126 / S4:104-132). Returns (x, z, w)."""
+        if prox not in _PROX:
+            raise ValueError("prox must be 'l1' or 'cnc'")
+        y = self._cplx(y)
+        m = self._mask(mask)
+        x, z, w = self.new(), self.new(), self.new()
+        with torch.cuda.device(self.device):
+            _abi.check(self._fn('solve')(y.data_ptr(), m.data_ptr(), x.data_ptr(), z.data_ptr(), w.data_ptr(), self.B,
+                                         self.N, int(self.mask_batched), _PROX[prox], int(iter_num), float(lambda1),
+                                         float(reo), float(alpha), float(b), _KERNEL[kernel], self.ws.data_ptr(),
+                                         self.ws_bytes, _stream_ptr()))
+        self._prepared_reo = float(reo)
+        return x, z, w
+
+
+def admm_solve(images: ArrayLike, mask: ArrayLike, noises: ArrayLike, *, prox: str = 'l1', iter_num: int = 50,
+               lambda1: float = 0.1, reo: float = 0.015, alpha: float = 0.45, b: float = 64.0,
+               dtype: str = 'float32', kernel: str = 'auto', return_state: bool = False, device=None):
+    """Batched ADMM-L1 / ADMM-CNC reconstruction.
+
+    images : (B,N,N) or (N,N) real in [0,1] (the reference's ``img_L``, S1:85-90)
+    mask   : (N,N) or (B,N,N) 0/1, DC at [0,0] (``Q_*.mat['Q1']``)
+    noises : (N,N) or (B,N,N) complex, already scaled (S1:186)
+    Returns x with the input's leading shape; numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.
+    """
+    if prox not in _PROX:
+        raise ValueError("prox must be 'l1' or 'cnc' (PnP denoisers go through pnp_admm_cnc_mri_b200.pnp)")
+    as_numpy = not isinstance(images, torch.Tensor)
+    img = torch.as_tensor(images)
+    single = img.ndim == 2
+    if single:
+        img = img[None]
+    if img.ndim != 3 or img.shape[1] != img.shape[2]:
+        raise ValueError(f'images must be (B,N,N) or (N,N), got {tuple(img.shape)}')
+    B, N = int(img.shape[0]), int(img.shape[1])
+    m = torch.as_tensor(mask)
+    solver = AdmmSolver(B, N, dtype=dtype, mask_batched=(m.ndim == 3), device=device)
+    y = solver.acquire(img, m, noises)
+    x, z, w = solver.solve(y, m, prox, iter_num, lambda1, reo, alpha, b, kernel=kernel)
+
+    def out(t):
+        t = t[0] if single else t
+        return t.cpu().numpy() if as_numpy else t
+
+    if return_state:
+        return out(x), out(z), out(w), (y[0] if single else y).cpu().numpy() if as_numpy else (y[0] if single else y)
+    return out(x)
+
+
+# ---- pointwise pieces (a1, a8, a6) on CUDA tensors --------------------------------------------
+def _pw_args(*ts):
+    t0 = ts[0]
+    if t0.dtype not in (torch.float32, torch.float64):
+        raise ValueError('float32 / float64 CUDA tensors only')
+    for t in ts:
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == t0.dtype and t.shape == t0.shape):
+            raise ValueError('operands must be contiguous CUDA tensors of identical shape and dtype')
+    return 'f64' if t0.dtype == torch.float64 else 'f32'
+
+
+def soft(x: torch.Tensor, c: float) -> torch.Tensor:
+    """soft(x, c) = fmax(|x| - c, 0) * sign(x) (S1:18-19) on a CUDA tensor."""
+    sfx = _pw_args(x)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _abi.check(getattr(_abi.load(), 'pnpadmm_soft_' + sfx)(x.data_ptr(), out.data_ptr(), float(c), x.numel(), _stream_ptr()))
+    return out
+
+
+def cnc_combine(z, x, w, s, alpha: float, coef: float) -> torch.Tensor:
+    """t = (1 - alpha) z + alpha (x + w) + coef (z - s) (S6:301)."""
+    sfx = _pw_args(z, x, w, s)
+    t = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        _abi.check(getattr(_abi.load(), 'pnpadmm_cnc_combine_' + sfx)(z.data_ptr(), x.data_ptr(), w.data_ptr(), s.data_ptr(),
+                                                                      t.data_ptr(), float(alpha), float(coef), z.numel(),
+                                                                      _stream_ptr()))
+    return t
+
+
+def dual_update_(x, z, w, clamp01: bool) -> None:
+    """In place: w = w + x - z; optionally clamp x, z, w to [0,1] (S3:293-296)."""
+    sfx = _pw_args(x, z, w)
+    with torch.cuda.device(x.device):
+        _abi.check(getattr(_abi.load(), 'pnpadmm_dual_update_' + sfx)(x.data_ptr(), z.data_ptr(), w.data_ptr(), int(clamp01),
+                                                                      x.numel(), _stream_ptr()))

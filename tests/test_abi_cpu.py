@@ -1,0 +1,73 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pnpadmm.h declares; argument
+validation that needs no GPU; the package refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from pnp_admm_cnc_mri_b200 import build
+    build.build_library()                # no-op when the in-tree .so is fresh
+    from pnp_admm_cnc_mri_b200 import _abi
+    return _abi.load()
+
+
+def test_header_symbols_all_exported(lib):
+    from pnp_admm_cnc_mri_b200 import _abi
+    hdr = open(os.path.join(ROOT, 'include', 'pnpadmm.h')).read()
+    declared = sorted(set(re.findall(r'\b(pnpadmm_[a-z0-9_]+)\s*\(', hdr)))
+    assert declared == sorted(_abi.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.pnpadmm_abi_version() == 1
+
+
+def test_workspace_sizes(lib):
+    nn = 256 * 256
+    w = lib.pnpadmm_workspace_bytes(64, 256, 0, 0)
+    assert w >= (64 + 32 + 32) * nn * 8 + nn
+    assert lib.pnpadmm_workspace_bytes(64, 256, 1, 0) > w
+    assert lib.pnpadmm_workspace_bytes(64, 256, 0, 1) > w          # per-image masks: no pairing
+    assert lib.pnpadmm_workspace_bytes(0, 256, 0, 0) == 0
+    assert lib.pnpadmm_host_scratch_bytes(64, 256) >= 64 * nn * (1 + 4 + 8 + 12)
+
+
+def test_argument_validation_without_gpu(lib):
+    # bad sizes / NULLs are rejected before any CUDA call
+    rc = lib.pnpadmm_solve_f32(None, None, None, None, None, 1, 256, 0, 0, 1, 0.1, 0.1, 0.0, 1.0, 0, None, 0, None)
+    assert rc == -1
+    buf = (ctypes.c_char * 1024)()
+    p = ctypes.addressof(buf)
+    rc = lib.pnpadmm_solve_f32(p, p, p, p, p, 1, 100, 0, 0, 1, 0.1, 0.1, 0.0, 1.0, 0, p, 1024, None)
+    assert rc == -2
+    assert b'power of two' in lib.pnpadmm_last_error_string()
+    rc = lib.pnpadmm_iterate_f32(p, p, p, 1, 256, 0, 7, 1, 0.1, 0.1, 0.0, 1.0, 0, p, 1024, None)
+    assert rc == -1 and b'prox' in lib.pnpadmm_last_error_string()
+    rc = lib.pnpadmm_soft_f32(None, None, 0.1, 10, None)
+    assert rc == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import pnp_admm_cnc_mri_b200 as pk
+    with pytest.raises(pk.PnpAdmmError):
+        pk.admm_solve(np.zeros((2, 64, 64), np.float32), np.ones((64, 64)), np.zeros((64, 64), complex))
+
+
+def test_product_never_imports_oracle():
+    """The product package must not import / reference anything under oracle/."""
+    pkg = os.path.join(ROOT, 'pnp_admm_cnc_mri_b200')
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+                assert 'reference_numpy' not in src, f

@@ -1,0 +1,266 @@
+"""GPU parity: the CUDA path (through the C ABI) against the fp64 oracle on the same inputs.
+Gates (BASELINE.json north_star): fp32 rel-L2 <= 1e-4 and |dPSNR| <= 0.01 dB; fp64 rel-L2 <= 1e-10."""
+import numpy as np
+import pytest
+
+from oracle import kat_table as kat
+from oracle import reference_numpy as orc
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+TOL32, TOL64, TOL_PSNR = 1e-4, 1e-10, 0.01
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def oracle_batch(imgs, mask, noises, prox, P):
+    fn = orc.admm_l1 if prox == 'l1' else orc.admm_cnc
+    out = []
+    for i, im in enumerate(imgs):
+        m = mask[i] if mask.ndim == 3 else mask
+        n = noises[i] if noises.ndim == 3 else noises
+        out.append(fn(im, m.astype(np.float64), n, return_state=True, **P))
+    return [np.stack([o[k] for o in out]) for k in range(4)]
+
+
+@pytest.fixture(scope='module')
+def pk():
+    import pnp_admm_cnc_mri_b200 as pk
+    pk.load_library()
+    return pk
+
+
+def _imgs(cs, idx):
+    return np.stack([orc.preprocess_uint8(cs['images'][i]) for i in idx])
+
+
+# ---------------------------------------------------------------------------------------------
+# a2: acquisition and zero-filled start
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype,tol', [('float64', 1e-13), ('float32', 2e-6)])
+def test_acquire_and_zero_filled(pk, cs_inputs, dtype, tol):
+    imgs = _imgs(cs_inputs, [4, 0, 9])
+    m = cs_inputs['masks'][0]
+    s = pk.AdmmSolver(3, 256, dtype=dtype)
+    y = s.acquire(imgs, m, cs_inputs['noises'])
+    x0 = s.zero_filled(y)
+    for k in range(3):
+        yr = orc.acquire(imgs[k], m.astype(np.float64), cs_inputs['noises'])
+        assert rel(y[k].cpu().numpy(), yr) < tol
+        assert rel(x0[k].cpu().numpy(), orc.zero_filled(yr)) < tol * 4
+
+
+# ---------------------------------------------------------------------------------------------
+# configs 1 and 2 on the reference's own data
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('kernel', ['cluster', 'streaming'])
+@pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
+def test_config1_fp32_reference_outputs(pk, cs_inputs, ref_out, prox, P, kernel):
+    """05.png / Q_Random30 / defaults against the UNMODIFIED reference's stored out[0]."""
+    img = _imgs(cs_inputs, [4])
+    x = pk.admm_solve(img, cs_inputs['masks'][0], cs_inputs['noises'], prox=prox, kernel=kernel, **P)
+    assert rel(x[0], ref_out[prox]) < TOL32
+    H = cs_inputs['images'][4]
+    p = orc.calculate_psnr(x[0].astype(np.float64) * 255, H)
+    assert abs(p - kat.SET1[prox][0]) < TOL_PSNR
+
+
+@pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
+def test_config1_fp64(pk, cs_inputs, ref_out, prox, P):
+    img = _imgs(cs_inputs, [4])
+    x = pk.admm_solve(img, cs_inputs['masks'][0], cs_inputs['noises'], prox=prox, dtype='float64', **P)
+    assert rel(x[0], ref_out[prox]) < TOL64
+
+
+@pytest.mark.parametrize('kernel', ['cluster', 'streaming'])
+@pytest.mark.parametrize('mask_i', [0, 1, 2])
+@pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
+def test_kat_table_fp32(pk, cs_inputs, mask_i, prox, P, kernel):
+    """All 15 set images x 3 masks: rel-L2 vs oracle and PSNR vs the reference's log table."""
+    imgs = _imgs(cs_inputs, range(15))
+    m = cs_inputs['masks'][mask_i]
+    x = pk.admm_solve(imgs, m, cs_inputs['noises'], prox=prox, kernel=kernel, **P)
+    xr = oracle_batch(imgs, m, cs_inputs['noises'], prox, P)[0]
+    name = cs_inputs['mask_names'][mask_i]
+    for k in range(15):
+        assert rel(x[k], xr[k]) < TOL32, (name, prox, k)
+        p = orc.calculate_psnr(x[k].astype(np.float64) * 255, cs_inputs['images'][k])
+        assert abs(p - kat.PSNR[(name, prox)][k]) < TOL_PSNR, (name, prox, k, p)
+
+
+def test_config2_batch64_cnc(pk, cs_inputs):
+    """BASELINE config 2: ADMM-CNC, batch 64 (15 set images tiled cyclically), three masks."""
+    idx = [i % 15 for i in range(64)]
+    imgs = _imgs(cs_inputs, idx)
+    for mi in range(3):
+        m = cs_inputs['masks'][mi]
+        x, z, w, y = pk.admm_solve(imgs, m, cs_inputs['noises'], prox='cnc', return_state=True, **kat.CNC_DEFAULTS)
+        xr, zr, wr, yr = oracle_batch(imgs[:15], m, cs_inputs['noises'], 'cnc', kat.CNC_DEFAULTS)
+        for k in range(64):
+            assert rel(x[k], xr[k % 15]) < TOL32
+            assert rel(z[k], zr[k % 15]) < TOL32
+        # every copy of the same image must give the same answer whichever pair slot it lands in
+        assert np.abs(x[0] - x[30]).max() < 1e-4      # slot a (0) vs slot a (30): 30 = 2*15
+        assert np.abs(x[0] - x[15]).max() < 1e-4      # slot a (0) vs slot b (15)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp64 validation build over sizes, odd batches, per-image masks / noise
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('N', [16, 32, 64, 128, 256, 512])
+@pytest.mark.parametrize('prox', ['l1', 'cnc'])
+def test_fp64_sizes(pk, N, prox):
+    from pnp_admm_cnc_mri_b200 import data
+    B = 3
+    imgs = data.phantoms(B, N, seed0=10)
+    m = data.make_mask('random', N, seed=1)
+    nz = data.make_noise(N, seed=5)
+    P = dict(kat.L1_DEFAULTS) if prox == 'l1' else dict(kat.CNC_DEFAULTS)
+    P['iter_num'] = 12
+    x, z, w, y = pk.admm_solve(imgs, m, nz, prox=prox, dtype='float64', return_state=True, **P)
+    xr, zr, wr, yr = oracle_batch(imgs, m, nz, prox, P)
+    assert rel(y, yr) < 1e-13
+    assert rel(x, xr) < TOL64 and rel(z, zr) < TOL64
+    assert np.abs(w - wr).max() < 1e-10
+
+
+@pytest.mark.parametrize('N,kernel', [(64, 'streaming'), (128, 'streaming'), (256, 'cluster'), (256, 'streaming'),
+                                      (512, 'streaming'), (1024, 'streaming')])
+@pytest.mark.parametrize('prox', ['l1', 'cnc'])
+def test_fp32_sizes(pk, N, kernel, prox):
+    from pnp_admm_cnc_mri_b200 import data
+    B = 5 if N <= 512 else 2                      # odd: last packed plane has an empty slot
+    imgs = data.phantoms(B, N, seed0=20)
+    m = data.make_mask(('random', 'radial', 'cartesian')[N % 3], N, seed=2)
+    nz = data.make_noise(N, seed=6)
+    P = dict(kat.L1_DEFAULTS) if prox == 'l1' else dict(kat.CNC_DEFAULTS)
+    P['iter_num'] = 50 if N <= 256 else 10
+    x = pk.admm_solve(imgs, m, nz, prox=prox, kernel=kernel, **P)
+    xr = oracle_batch(imgs, m, nz, prox, P)[0]
+    for k in range(B):
+        assert rel(x[k], xr[k]) < TOL32, (N, prox, k)
+        assert abs(orc.calculate_psnr(x[k].astype(np.float64) * 255, imgs[k] * 255.)
+                   - orc.calculate_psnr(xr[k] * 255, imgs[k] * 255.)) < TOL_PSNR
+
+
+@pytest.mark.parametrize('dtype,kernel,tol', [('float64', 'auto', TOL64), ('float32', 'cluster', TOL32),
+                                              ('float32', 'streaming', TOL32)])
+def test_per_image_masks_and_noise(pk, dtype, kernel, tol):
+    from pnp_admm_cnc_mri_b200 import data
+    N, B = 256, 4
+    imgs = data.phantoms(B, N, seed0=30)
+    masks = np.stack([data.make_mask(k, N, seed=s) for s, k in enumerate(('random', 'radial', 'cartesian', 'random'))])
+    nz = data.make_noise(N, seed=7, B=B)
+    P = dict(kat.CNC_DEFAULTS, iter_num=20)
+    x = pk.admm_solve(imgs, masks, nz, prox='cnc', dtype=dtype, kernel=kernel, **P)
+    xr = oracle_batch(imgs, masks, nz, 'cnc', P)[0]
+    for k in range(B):
+        assert rel(x[k], xr[k]) < tol
+
+
+def test_non_default_parameters_and_single_image(pk, cs_inputs):
+    img = orc.preprocess_uint8(cs_inputs['images'][2])
+    m = cs_inputs['masks'][1]
+    for prox, P in (('l1', dict(iter_num=9, lambda1=0.3, reo=0.05)),
+                    ('cnc', dict(alpha=0.3, iter_num=7, lambda1=0.2, reo=0.1, b=16)),
+                    ('cnc', dict(alpha=0.4, iter_num=4, lambda1=0.04, reo=2.75, b=1))):   # S4:37-41 fallbacks
+        x = pk.admm_solve(img, m, cs_inputs['noises'], prox=prox, dtype='float64', **P)   # (N,N) in -> (N,N) out
+        fn = orc.admm_l1 if prox == 'l1' else orc.admm_cnc
+        assert x.shape == (256, 256)
+        assert rel(x, fn(img, m.astype(np.float64), cs_inputs['noises'], **P)) < TOL64
+        x32 = pk.admm_solve(img, m, cs_inputs['noises'], prox=prox, **P)
+        assert rel(x32, fn(img, m.astype(np.float64), cs_inputs['noises'], **P)) < TOL32
+
+
+# ---------------------------------------------------------------------------------------------
+# a3 x-update alone and the step-wise API (what the PnP variants call)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype,kernel,tol', [('float64', 'auto', 1e-12), ('float32', 'cluster', 2e-6),
+                                              ('float32', 'streaming', 2e-6)])
+def test_xupdate(pk, cs_inputs, dtype, kernel, tol):
+    rng = np.random.default_rng(0)
+    imgs = _imgs(cs_inputs, [1, 2, 3])
+    m = cs_inputs['masks'][2]
+    s = pk.AdmmSolver(3, 256, dtype=dtype)
+    y = s.acquire(imgs, m, cs_inputs['noises'])
+    s.prepare(y, m, reo=0.26)
+    z = rng.uniform(0, 1, (3, 256, 256))
+    w = rng.uniform(-0.1, 0.1, (3, 256, 256))
+    x, xpw = s.xupdate(torch.as_tensor(z), torch.as_tensor(w), want_xpw=True, kernel=kernel)
+    idx = np.nonzero(m)
+    for k in range(3):
+        yr = orc.acquire(imgs[k], m.astype(np.float64), cs_inputs['noises'])
+        xr = orc.x_update(z[k], w[k], yr, idx, 0.26)
+        assert rel(x[k].cpu().numpy(), xr) < tol
+        assert rel(xpw[k].cpu().numpy(), xr + w[k]) < tol * 2
+
+
+def test_stepwise_iterate_equals_solve(pk, cs_inputs):
+    imgs = _imgs(cs_inputs, [5, 6])
+    m = cs_inputs['masks'][0]
+    P = kat.CNC_DEFAULTS
+    for kernel in ('cluster', 'streaming'):
+        s = pk.AdmmSolver(2, 256)
+        y = s.acquire(imgs, m, cs_inputs['noises'])
+        x1, z1, w1 = s.solve(y, m, 'cnc', P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'], kernel=kernel)
+        z = s.zero_filled(y)
+        w = torch.zeros_like(z)
+        x = torch.empty_like(z)
+        s.prepare(y, m, P['reo'])
+        # 50 iterations as 20 + 30 through the warm-start entry point
+        s.iterate(x, z, w, 'cnc', 20, P['lambda1'], P['reo'], P['alpha'], P['b'], kernel=kernel)
+        s.iterate(x, z, w, 'cnc', 30, P['lambda1'], P['reo'], P['alpha'], P['b'], kernel=kernel)
+        assert torch.equal(x, x1) and torch.equal(z, z1) and torch.equal(w, w1)
+
+
+def test_cluster_and_streaming_agree(pk, cs_inputs):
+    imgs = _imgs(cs_inputs, range(6))
+    m = cs_inputs['masks'][1]
+    a = pk.admm_solve(imgs, m, cs_inputs['noises'], prox='l1', kernel='cluster', **kat.L1_DEFAULTS)
+    b = pk.admm_solve(imgs, m, cs_inputs['noises'], prox='l1', kernel='streaming', **kat.L1_DEFAULTS)
+    assert rel(a, b.astype(np.float64)) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# pointwise pieces
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dt', [torch.float32, torch.float64])
+def test_pointwise(pk, dt):
+    g = torch.Generator(device='cuda').manual_seed(0)
+    sh = (3, 64, 64)
+    z, x, w, s = (torch.rand(sh, generator=g, device='cuda', dtype=dt) - 0.3 for _ in range(4))
+    x[0, 0, :5] = 0.0
+    npdt = np.float64 if dt == torch.float64 else np.float32
+    assert np.array_equal(pk.soft(x, 0.2).cpu().numpy(), orc.soft(x.cpu().numpy(), npdt(0.2)).astype(npdt))
+    t = pk.cnc_combine(z, x, w, s, 1.2, 0.54).cpu().numpy()
+    zz, xx, ww, ss = (a.cpu().numpy().astype(np.float64) for a in (z, x, w, s))
+    tr = (1 - 1.2) * zz + 1.2 * (xx + ww) + 0.54 * (zz - ss)
+    assert np.abs(t - tr).max() < (1e-14 if dt == torch.float64 else 1e-6)
+    x2, z2, w2 = x.clone(), z.clone(), w.clone()
+    pk.dual_update_(x2, z2, w2, True)
+    assert np.allclose(w2.cpu().numpy(), np.clip(ww + xx - zz, 0, 1), atol=1e-6)
+    assert np.array_equal(x2.cpu().numpy(), np.clip(x.cpu().numpy(), 0, 1))
+    x3, z3, w3 = x.clone(), z.clone(), w.clone()
+    pk.dual_update_(x3, z3, w3, False)
+    assert torch.equal(x3, x) and torch.equal(z3, z)
+    assert np.allclose(w3.cpu().numpy(), ww + xx - zz, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour of the boundary
+# ---------------------------------------------------------------------------------------------
+def test_error_codes(pk):
+    with pytest.raises(ValueError):
+        pk.AdmmSolver(2, 100)                                     # not a power of two -> workspace fine, call fails
+        pk.admm_solve(np.zeros((2, 100, 100), np.float32), np.ones((100, 100)), np.zeros((100, 100), complex))
+    with pytest.raises(ValueError):
+        pk.admm_solve(np.zeros((2, 64, 64), np.float32), np.ones((64, 64)), np.zeros((64, 64), complex), prox='bm3d')
+    with pytest.raises(pk.PnpAdmmError):
+        pk.admm_solve(np.zeros((2, 64, 64), np.float32), np.ones((64, 64)), np.zeros((64, 64), complex), kernel='cluster')
+    with pytest.raises(ValueError):
+        pk.admm_solve(np.zeros((2, 64, 64), np.float32), np.ones((64, 64)), np.zeros((64, 64), complex), reo=0.0)
