@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the ADMM-CNC reconstruction path (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch: ADMM-CNC (reference defaults S4:176:
+alpha 0.45, 50 iterations, lambda 0.5, reo 0.05, b 64) on 64 synthetic 256x256 phantoms per GPU
+with one 30 % sampling mask (cartesian / radial / random cycling step by step) and complex
+Gaussian noise.  metric = ADMM iterations/s = images x iter_num / time (whole job, all ranks).
+
+  value    : device-resident images -> acquisition + zero-fill + prepare + 50 iterations, CUDA events
+  e2e      : same through the host-buffer C-ABI call (pnpadmm_reconstruct_host_f32): pinned host
+             uint8 images in, float32 reconstructions out, copies inside the timed region
+  roofline : the cluster-resident kernel alone (K1) against the non-tensor FP32 peak, nominal FFT
+             flops 10 N^2 log2(N^2) per image-iteration
+  cpu_baseline / --impl reference : the reference's NumPy loop (oracle restatement, bit-identical
+             to the unmodified scripts) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N = 256
+B_PER_GPU = 64
+CNC = dict(alpha=0.45, iter_num=50, lambda1=0.5, reo=0.05, b=64)      # S4:176
+MASK_KINDS = ('cartesian', 'radial', 'random')
+FLOP_PER_IMAGE_ITER = 10 * N * N * math.log2(N * N)                   # 10 485 760
+FP32_LANES_PER_SM = 128
+
+
+def synth_inputs(B, seed0=0):
+    from pnp_admm_cnc_mri_b200 import data
+    base = [np.uint8((data.phantom(N, seed0 + i) * 255.0).round()) for i in range(min(B, 16))]
+    imgs = np.stack([base[i % len(base)] for i in range(B)])             # uint8 gray levels
+    masks = np.stack([data.make_mask(k, N, seed=s) for s, k in enumerate(MASK_KINDS)])
+    noise = data.make_noise(N, seed=1234)                                # sigma 15 per component (= noises.mat x 3)
+    return imgs, masks, noise
+
+
+# --------------------------------------------------------------------------------------------
+# CPU reference arm (oracle restatement of S4:101-132, NumPy fp64)
+# --------------------------------------------------------------------------------------------
+def _cpu_one(args):
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    from oracle import reference_numpy as orc
+    img, mask, noise = args
+    x = orc.admm_cnc(np.float32(img / 255.), mask.astype(np.float64), noise, **CNC)
+    return float(x.sum())
+
+
+def cpu_throughput(n_images, cores):
+    """iterations/s of the reference loop over `n_images` images on 1 process (cpu_baseline leg)."""
+    imgs, masks, noise = synth_inputs(n_images)
+    jobs = [(imgs[i], masks[i % 3], noise) for i in range(n_images)]
+    _cpu_one(jobs[0])                      # warm-up (imports, FFT plans)
+    t0 = time.perf_counter()
+    for j in jobs:
+        _cpu_one(j)
+    dt = time.perf_counter() - t0
+    return n_images * CNC['iter_num'] / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on all host cores (one image per task)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_img = max(cores * 2, 16)
+    imgs, masks, noise = synth_inputs(n_img)
+    jobs = [(imgs[i], masks[i % 3], noise) for i in range(n_img)]
+    t_tot = 0.0
+    with mp.get_context('fork').Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_one, jobs[:cores], chunksize=1)
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_one, jobs, chunksize=1)
+            t_tot += time.perf_counter() - t0
+    value = n_img * CNC['iter_num'] * args.steps / t_tot
+    line = {
+        'impl': 'reference', 'metric': 'admm_cnc_iterations_per_s', 'value': value, 'unit': 'iterations/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'ADMM-CNC 256x256, 30% cartesian/radial/random masks, reference defaults (S4:176)',
+                   'images_per_step': n_img, 'iter_num': CNC['iter_num']},
+        'cpu_baseline': {'value': value, 'unit': 'iterations/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{n_img} images x 50 iterations per step, one process per core (NumPy fp64, '
+                                   f'oracle restatement bit-identical to the unmodified reference script)'},
+        'e2e': {'value': value, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [s.strip() for s in r.split(',')]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import pnp_admm_cnc_mri_b200 as pk
+    from pnp_admm_cnc_mri_b200 import _abi
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('for --gpus N > 1 launch with torch.distributed.run --nproc-per-node N')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    lib = _abi.load()
+    dev = torch.device('cuda', local)
+
+    B = B_PER_GPU
+    imgs_u8, masks, noise = synth_inputs(B, seed0=1000 * rank)
+    solver = pk.AdmmSolver(B, N)
+    d_imgs = torch.as_tensor(np.float32(imgs_u8 / 255.)).to(dev)
+    d_masks = torch.as_tensor(masks).to(dev)
+    d_noise = torch.as_tensor(noise).to(dev, torch.complex64)
+    # host-side buffers of the e2e path (pinned)
+    h_img = torch.as_tensor(imgs_u8).pin_memory()
+    h_masks = [torch.as_tensor(masks[i]).pin_memory() for i in range(3)]
+    h_noise = torch.view_as_real(torch.as_tensor(noise).to(torch.complex64)).contiguous().pin_memory()
+    h_x = torch.empty((B, N, N), dtype=torch.float32).pin_memory()
+    scratch = torch.empty(lib.pnpadmm_host_scratch_bytes(B, N), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        y = solver.acquire(d_imgs, d_masks[i % 3], d_noise)
+        return solver.solve(y, d_masks[i % 3], 'cnc', CNC['iter_num'], CNC['lambda1'], CNC['reo'], CNC['alpha'], CNC['b'])
+
+    def step_host(i):
+        st = torch.cuda.current_stream().cuda_stream
+        _abi.check(lib.pnpadmm_reconstruct_host_f32(
+            h_img.data_ptr(), h_masks[i % 3].data_ptr(), h_noise.data_ptr(), h_x.data_ptr(), B, N, _abi.PROX_CNC,
+            CNC['iter_num'], CNC['lambda1'], CNC['reo'], CNC['alpha'], CNC['b'], _abi.KERNEL_AUTO,
+            scratch.data_ptr(), scratch.numel(), solver.ws.data_ptr(), solver.ws_bytes, st))
+        torch.cuda.current_stream().synchronize()        # the user reads h_x
+        return float(h_x[0, 0, 0])
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            flush.fill_(i & 1)                            # L2 flush between timed iterations (untimed)
+            evs[i][0].record()
+            fn(i)
+            evs[i][1].record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps, args.warmup)
+    ms_e2e = timed(step_host, args.steps, args.warmup)
+
+    # K1 alone for the roofline: iterate() on prepared state, one launch per timed region
+    y = solver.acquire(d_imgs, d_masks[0], d_noise)
+    z0 = solver.zero_filled(y)
+    solver.prepare(y, d_masks[0], CNC['reo'])
+    x = torch.empty_like(z0)
+    k1_ms = []
+    for r in range(args.warmup + args.steps):
+        z, w = z0.clone(), torch.zeros_like(z0)
+        flush.fill_(r & 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        solver.iterate(x, z, w, 'cnc', CNC['iter_num'], CNC['lambda1'], CNC['reo'], CNC['alpha'], CNC['b'])
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= args.warmup:
+            k1_ms.append(e0.elapsed_time(e1))
+    k1_ms = float(np.mean(k1_ms))
+    clocks = sampler.stop() if rank == 0 else None
+
+    fl = ctypes.c_double()
+    _abi.check(lib.pnpadmm_measure_fp32_peak(fl, None))
+    sm, ncl = ctypes.c_int(), ctypes.c_int()
+    _abi.check(lib.pnpadmm_device_info(sm, ncl, None, None))
+
+    if rank == 0:
+        its_step = world * B * CNC['iter_num']
+        value = its_step * args.steps / (ms_dev * 1e-3)
+        e2e = its_step * args.steps / (ms_e2e * 1e-3)
+        achieved = B * CNC['iter_num'] * FLOP_PER_IMAGE_ITER / (k1_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        sm_max = peaks.get('sm_max_mhz', 1965.0)
+        nominal_peak = sm.value * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
+        cores = os.cpu_count() or 1
+        cpu_v, cpu_dt = cpu_throughput(8, 1) if world == 1 else (None, None)
+        line = {
+            'metric': 'admm_cnc_iterations_per_s', 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'images_per_s': value / CNC['iter_num'],
+            'config': {'workload': 'BASELINE config 2: ADMM-CNC 256x256, batch 64 per GPU, 30% cartesian/radial/random '
+                                   'masks cycling per step, reference defaults (alpha .45, 50 it, lambda .5, reo .05, b 64)',
+                       'batch_per_gpu': B, 'iter_num': CNC['iter_num'], 'kernel': 'cluster256 (K1)',
+                       'l2': 'flushed (256 MiB fill) between timed steps', 'sharding': f'batch x{world}, no collective'},
+            'e2e': {'value': e2e, 'unit': 'iterations/s', 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': int(h_img.numel() + h_masks[0].numel() + h_noise.numel() * 4),
+                    'd2h_bytes_per_step': int(h_x.numel() * 4), 'api': 'pnpadmm_reconstruct_host_f32 (pinned host buffers)'},
+            'gpu_launches': 8 * args.steps,
+            'launches_per_step': {'device': 8, 'e2e': 9,
+                                  'kernels': 'rows<FWD_IMG>, cols<FWD_ACQ>, cols<INV>, rows<INV_ABS>, copy_zero, write_cf, '
+                                             'prepare, cluster256 (+ u8_to_unit in e2e)'},
+            'roofline': {'bound': 'fp32', 'kernel': 'cluster256_kernel', 'achieved': achieved, 'peak': nominal_peak,
+                         'unit': 'TFLOP/s', 'frac': achieved / nominal_peak, 'traffic': None,
+                         'peak_source': f'nominal non-tensor FP32: {sm.value} SMs x 128 lanes x 2 x {sm_max:.0f} MHz '
+                                        f'(MEASURED_PEAKS.json has no fp32 entry); measured FFMA probe in this run: '
+                                        f'{fl.value / 1e12:.1f} TFLOP/s',
+                         'measured_fma_peak': fl.value / 1e12, 'frac_of_measured_fma': achieved / (fl.value / 1e12),
+                         'flop_model': '10 N^2 log2(N^2) = 10485760 per image-iteration (nominal radix-2 count of 2 '
+                                       'complex 2-D FFTs; executed flops are lower: pair-packing + radix-16)',
+                         'launch_ms': k1_ms, 'resident_clusters': ncl.value},
+            'clocks': clocks,
+        }
+        if cpu_v is not None:
+            line['cpu_baseline'] = {'value': cpu_v, 'unit': 'iterations/s', 'cores': 1, 'kind': 'port',
+                                    'sample': '8 images x 50 iterations, 1 thread, NumPy fp64 oracle restatement '
+                                              '(bit-identical to the unmodified reference script); host has '
+                                              f'{cores} cores, all-cores number: bench.py --impl reference'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -69,12 +69,17 @@ size_t pnpadmm_workspace_bytes(int B, int N, int is_f64, int mask_batched);
  * a2  acquisition:  y = fft2(img) * mask + noises           (S1:99 == S4:103 == S3:242 == S6:251)
  *   img   [B][N][N] real in [0,1];  mask [N][N] or [B][N][N] u8;  noise [N][N][2] or [B][N][N][2]
  *   y     [B][N][N][2] out.  Noise is added on EVERY bin, sampled or not, like the reference.
+ *   spectrum_f32 (f64 entry only): the reference's image is float32 (utils_image.uint2single) and
+ *   NumPy >= 2 evaluates fft2 of a float32 array in single precision, rounding each 1-D pass to
+ *   complex64 before `* mask + noises` promotes to complex128.  Non-zero reproduces that rounding
+ *   (the reference as it runs today); zero keeps the full double-precision spectrum (NumPy 1.x, the
+ *   author's environment).  The f32 entry computes in float32 throughout.
  * ------------------------------------------------------------------------------------- */
 int pnpadmm_acquire_f32(const float* img, const uint8_t* mask, const float* noise, float* y,
                         int B, int N, int mask_batched, int noise_batched,
                         void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
 int pnpadmm_acquire_f64(const double* img, const uint8_t* mask, const double* noise, double* y,
-                        int B, int N, int mask_batched, int noise_batched,
+                        int B, int N, int mask_batched, int noise_batched, int spectrum_f32,
                         void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
 
 /* zero-filled start  x0 = |ifft2(y)|  (complex magnitude)              (S1:100,104 == S4:104,108) */

@@ -55,7 +55,7 @@ def load() -> ctypes.CDLL:
     lib.pnpadmm_host_scratch_bytes.argtypes = [i, i]
     for sfx in ('f32', 'f64'):
         f = getattr(lib, 'pnpadmm_acquire_' + sfx); f.restype = i
-        f.argtypes = [p, p, p, p, i, i, i, i, p, z, p]
+        f.argtypes = [p, p, p, p, i, i, i, i, p, z, p] if sfx == 'f32' else [p, p, p, p, i, i, i, i, i, p, z, p]
         f = getattr(lib, 'pnpadmm_zero_filled_' + sfx); f.restype = i
         f.argtypes = [p, p, i, i, p, z, p]
         f = getattr(lib, 'pnpadmm_prepare_' + sfx); f.restype = i

@@ -239,13 +239,13 @@ int grid_1d(size_t n, int sm_count) {
 // ------------------------------------------------------------------------------------------
 template <typename T>
 int acquire_impl(const T* img, const uint8_t* mask, const T* noise, T* y, int B, int N, int mask_batched,
-                 int noise_batched, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 int noise_batched, int round_f32, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (!img || !mask || !noise || !y || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "acquire: NULL pointer or B <= 0");
     int rc = check_n(N, sizeof(T) == 8); if (rc) return rc;
     DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
     Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, 0, &w, true); if (rc) return rc;
     StreamParams<T> p = base_params(w, B, N);
-    p.img = img; p.cout = w.T1;
+    p.img = img; p.cout = w.T1; p.round_f32 = (sizeof(T) == 8) ? round_f32 : 0;
     p.lines = rows_lines<T>(N);
     rows_kernel<T, RM_FWD_IMG><<<dim3(N / p.lines, B), 256, rows_smem<T>(N), st>>>(p);
     LAUNCH_CHECK("rows_kernel<FWD_IMG>");
@@ -497,11 +497,12 @@ size_t pnpadmm_workspace_bytes(int B, int N, int is_f64, int mask_batched) {
 
 int pnpadmm_acquire_f32(const float* img, const uint8_t* mask, const float* noise, float* y, int B, int N,
                         int mask_batched, int noise_batched, void* ws, size_t wsb, pnpadmm_stream_t s) {
-    return acquire_impl<float>(img, mask, noise, y, B, N, mask_batched, noise_batched, ws, wsb, ST(s));
+    return acquire_impl<float>(img, mask, noise, y, B, N, mask_batched, noise_batched, 0, ws, wsb, ST(s));
 }
 int pnpadmm_acquire_f64(const double* img, const uint8_t* mask, const double* noise, double* y, int B, int N,
-                        int mask_batched, int noise_batched, void* ws, size_t wsb, pnpadmm_stream_t s) {
-    return acquire_impl<double>(img, mask, noise, y, B, N, mask_batched, noise_batched, ws, wsb, ST(s));
+                        int mask_batched, int noise_batched, int spectrum_f32, void* ws, size_t wsb,
+                        pnpadmm_stream_t s) {
+    return acquire_impl<double>(img, mask, noise, y, B, N, mask_batched, noise_batched, spectrum_f32, ws, wsb, ST(s));
 }
 int pnpadmm_zero_filled_f32(const float* y, float* x0, int B, int N, void* ws, size_t wsb, pnpadmm_stream_t s) {
     return zero_filled_impl<float>(y, x0, B, N, ws, wsb, ST(s));
@@ -577,7 +578,7 @@ int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, co
     CUDA_TRY(cudaMemcpyAsync(d_noise, h_noise, nn * 8, cudaMemcpyHostToDevice, st));
     u8_to_unit_kernel<float><<<grid_1d(n, d->sm_count), 256, 0, st>>>(d_img8, d_img, n);
     LAUNCH_CHECK("u8_to_unit_kernel");
-    rc = acquire_impl<float>(d_img, d_mask, d_noise, d_y, B, N, 0, 0, ws, wsb, st); if (rc) return rc;
+    rc = acquire_impl<float>(d_img, d_mask, d_noise, d_y, B, N, 0, 0, 0, ws, wsb, st); if (rc) return rc;
     rc = solve_impl<float>(d_y, d_mask, d_x, d_z, d_w, B, N, 0, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(h_x, d_x, n * 4, cudaMemcpyDeviceToHost, st));

@@ -107,6 +107,7 @@ struct StreamParams {
     const uint8_t* mask; int mask_batched;
     const cx<T>* noise; int noise_batched;
     T scale;          // 1/N^2 for the zero-filled inverse
+    int round_f32;    // acquire: round each FFT pass to float32 (NumPy >= 2 semantics for a float32 image)
     int last;         // rows-prox pass: last iteration (emit x, no forward FFT)
     ProxParams<T> prox;
 };
@@ -150,7 +151,11 @@ __global__ void __launch_bounds__(256) rows_kernel(const StreamParams<T> p) {
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) buf0[i] = mk<T>(p.img[plane_off + i], T(0));
         __syncthreads();
         cx<T>* res = fft_lines<false, T>(buf0, buf1, tw, lines, N, p.log2N, N);
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) p.cout[plane_off + i] = res[i];
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            cx<T> v = res[i];
+            if (p.round_f32) v = mk<T>((T)(float)v.re, (T)(float)v.im);
+            p.cout[plane_off + i] = v;
+        }
     } else if (MODE == RM_INV_ABS) {
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) buf0[i] = p.cin[plane_off + i];
         __syncthreads();
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(256) cols_kernel(const StreamParams<T> p) {
             const int r = i >> ll, c = i & (lines - 1);
             const size_t g = (size_t)r * N + c;
             cx<T> v = res[c * pitch + r];
+            if (p.round_f32) v = mk<T>((T)(float)v.re, (T)(float)v.im);
             const T mm = m[g] ? T(1) : T(0);
             cx<T> n = nz[g];
             out[base + g] = mk<T>(v.re * mm + n.re, v.im * mm + n.im);

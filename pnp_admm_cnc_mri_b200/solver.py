@@ -83,8 +83,16 @@ class AdmmSolver:
         return torch.empty((self.B, self.N, self.N), dtype=self.rdtype, device=self.device)
 
     # -- a2 ----------------------------------------------------------------------------------
-    def acquire(self, img: ArrayLike, mask: ArrayLike, noises: ArrayLike) -> torch.Tensor:
-        """y = fft2(img) * mask + noises (S1:99)."""
+    def acquire(self, img: ArrayLike, mask: ArrayLike, noises: ArrayLike, spectrum: str = 'numpy') -> torch.Tensor:
+        """y = fft2(img) * mask + noises (S1:99).
+
+        spectrum='numpy' follows NumPy's dtype rule in the float64 build: a float32 image (what the
+        reference feeds, utils_image.uint2single) gets a complex64-rounded spectrum (NumPy >= 2), a
+        float64 image a full double one.  'double' never rounds (NumPy 1.x, the author's setup)."""
+        if spectrum not in ('numpy', 'double'):
+            raise ValueError("spectrum must be 'numpy' or 'double'")
+        src_dtype = torch.as_tensor(img).dtype
+        round_f32 = int(spectrum == 'numpy' and src_dtype in (torch.float32, torch.float16, torch.uint8))
         img = self._real(img, 'img')
         m = self._mask(mask)
         nz = torch.as_tensor(noises).to(device=self.device, dtype=self.cdtype).contiguous()
@@ -96,8 +104,10 @@ class AdmmSolver:
             raise ValueError(f'noises must be (N,N) or (B,N,N), got {tuple(nz.shape)}')
         y = torch.empty((self.B, self.N, self.N), dtype=self.cdtype, device=self.device)
         with torch.cuda.device(self.device):
+            extra = (round_f32,) if self.f64 else ()
             _abi.check(self._fn('acquire')(img.data_ptr(), m.data_ptr(), nz.data_ptr(), y.data_ptr(), self.B, self.N,
-                                           int(self.mask_batched), nb, self.ws.data_ptr(), self.ws_bytes, _stream_ptr()))
+                                           int(self.mask_batched), nb, *extra, self.ws.data_ptr(), self.ws_bytes,
+                                           _stream_ptr()))
         return y
 
     def zero_filled(self, y: torch.Tensor) -> torch.Tensor:

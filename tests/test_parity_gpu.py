@@ -14,7 +14,8 @@ TOL32, TOL64, TOL_PSNR = 1e-4, 1e-10, 0.01
 
 
 def rel(a, b):
-    a = np.asarray(a, dtype=np.float64)
+    a, b = np.asarray(a), np.asarray(b)
+    a = a.astype(np.complex128 if np.iscomplexobj(a) else np.float64)
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
@@ -42,7 +43,7 @@ def _imgs(cs, idx):
 # ---------------------------------------------------------------------------------------------
 # a2: acquisition and zero-filled start
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('dtype,tol', [('float64', 1e-13), ('float32', 2e-6)])
+@pytest.mark.parametrize('dtype,tol', [('float64', 1e-11), ('float32', 2e-6)])
 def test_acquire_and_zero_filled(pk, cs_inputs, dtype, tol):
     imgs = _imgs(cs_inputs, [4, 0, 9])
     m = cs_inputs['masks'][0]
@@ -124,7 +125,7 @@ def test_fp64_sizes(pk, N, prox):
     P['iter_num'] = 12
     x, z, w, y = pk.admm_solve(imgs, m, nz, prox=prox, dtype='float64', return_state=True, **P)
     xr, zr, wr, yr = oracle_batch(imgs, m, nz, prox, P)
-    assert rel(y, yr) < 1e-13
+    assert rel(y, yr) < 1e-11
     assert rel(x, xr) < TOL64 and rel(z, zr) < TOL64
     assert np.abs(w - wr).max() < 1e-10
 
