@@ -171,7 +171,7 @@ PNP_HD void row_read_step2(const Ctx& c, ThreadState& s) {
     fft256_step2<INV>(v, s.a);
 }
 
-// after the inverse row FFT: x = |Re|, |Im|; prox; dual; next FFT input a = z - w.
+// after the inverse row FFT (a = r, the residual correction): x = |v + r|; prox; dual; next a = z - w.
 // `last`: write x, z, w (and x + w) to global memory.
 PNP_HD void row_prox(const Ctx& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last,
                      const PlaneIO& io) {
@@ -181,10 +181,11 @@ PNP_HD void row_prox(const Ctx& c, ThreadState& s, const ProxParams<float>& p, b
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const int n = t + 16 * j;
-        const float xa = pabs(s.a[j].re);
-        const float xb = has_b ? pabs(s.a[j].im) : 0.f;
         cf32 zz = Zs[n];
         float za = zz.re, zb = zz.im, wa = s.w[2 * j], wb = s.w[2 * j + 1];
+        // residual form: x = |v + r|, v = z - w the very value that was transformed
+        const float xa = pabs((za - wa) + s.a[j].re);
+        const float xb = has_b ? pabs((zb - wb) + s.a[j].im) : 0.f;
         if (p.prox == PROX_NONE) {
             io.x_a[g0 + n] = xa;
             if (io.xpw_a) io.xpw_a[g0 + n] = xa + wa;
@@ -246,7 +247,7 @@ PNP_HD void col_read_step2(const Ctx& c, ThreadState& s) {
     fft256_step2<INV>(v, s.a);
 }
 
-// data-consistency blend on the packed spectrum: a = cf[mcode] * a + G      (see streaming.cuh)
+// data-consistency residual on the packed spectrum: a = G - cf[mcode] * a     (see streaming.cuh)
 PNP_HD void col_blend(const Ctx& c, ThreadState& s, const cf32* G, const uint8_t* mcode,
                       float cf0, float cf1, float cf2) {
     const int kc = kRows * c.rank + c.cc();
@@ -257,7 +258,7 @@ PNP_HD void col_blend(const Ctx& c, ThreadState& s, const cf32* G, const uint8_t
         const cf32 gg = G[g];
         const int code = mcode[g];
         const float cf = code == 0 ? cf0 : (code == 1 ? cf1 : cf2);
-        s.a[j] = mk<float>(cf * s.a[j].re + gg.re, cf * s.a[j].im + gg.im);
+        s.a[j] = mk<float>(gg.re - cf * s.a[j].re, gg.im - cf * s.a[j].im);
     }
 }
 

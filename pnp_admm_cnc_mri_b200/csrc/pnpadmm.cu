@@ -69,7 +69,7 @@ int check_n(int N, bool f64) {
 // ------------------------------------------------------------------------------------------
 // tile shapes of the streaming kernels
 // ------------------------------------------------------------------------------------------
-template <typename T> int rows_lines(int N) { int l = 2048 / N; return l < 1 ? 1 : l; }
+template <typename T> int rows_lines(int N) { int l = 2048 / N; if (l > N) l = N; return l < 1 ? 1 : l; }
 template <typename T> int cols_lines(int N) {
     const int cap = sizeof(T) == 4 ? 8 : 4;
     const int maxpts = sizeof(T) == 4 ? 8192 : 4096;
@@ -155,7 +155,7 @@ int ensure_device(DeviceState** out) {
 // ------------------------------------------------------------------------------------------
 template <typename T>
 struct Workspace {
-    T* cf;            // [3] blend coefficients written by prepare
+    T* cf;            // [3] residual coefficients g*mcode/(2N^2) written by prepare
     cx<T>* K;         // [P][N][N]
     cx<T>* G;         // [P][N][N]
     cx<T>* T1;        // [B][N][N] per-image complex scratch
@@ -290,7 +290,7 @@ int prepare_impl(const T* y, const uint8_t* mask, int B, int N, int mask_batched
     const double La2 = 1.0 / 2.0 / reo;            // S1:117
     const double g = 1.0 / (1.0 + La2);
     const double n2 = (double)N * N;
-    write_cf_kernel<T><<<1, 1, 0, st>>>(w.cf, (T)(1.0 / n2), (T)((1.0 - 0.5 * g) / n2), (T)((1.0 - g) / n2));
+    write_cf_kernel<T><<<1, 1, 0, st>>>(w.cf, (T)0, (T)(0.5 * g / n2), (T)(g / n2));
     LAUNCH_CHECK("write_cf_kernel");
     const size_t total = (size_t)w.P * N * N;
     prepare_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const cx<T>*>(y), mask, w.G,

@@ -7,11 +7,15 @@
 // Two real images are packed into one complex plane (a + i b).  Because the mask blend of the
 // reference (S1:117-118) is followed by Re(ifft2(.)) (S1:119), it can be replaced by the blend
 // with the Hermitian-symmetrised data term, which is linear with REAL coefficients and therefore
-// acts on the packed plane directly:
-//     C' = cf .* C + G,   cf = (1 - g*(m[k]+m[-k])/2) / N^2,   g = 1/(1+La2)
-//     G  = g/N^2 * (Ys_a + i Ys_b),  Ys[k] = (m[k] y[k] + m[-k] conj(y[-k])) / 2
-// and x_a = |Re(ifft2_unnormalised(C'))|, x_b = |Im(...)|.  (Verified to 1e-14 against the
-// reference restatement in fp64; see DESIGN.md.)
+// acts on the packed plane directly.  With v = z - w (packed V = v_a + i v_b), C = fft2(V),
+// g = 1/(1+La2), ms[k] = (m[k]+m[-k])/2 and Ys[k] = (m[k] y[k] + m[-k] conj(y[-k]))/2:
+//     Re ifft2(blend(fft2 v)) = v + ifft2_unnormalised(R),   R = G - cf .* C
+//     G = g/N^2 * (Ys_a + i Ys_b),   cf = g * ms / N^2  in {0, g/2N^2, g/N^2}
+//     x_a = |v_a + Re r|,  x_b = |v_b + Im r|,  r = ifft2_unnormalised(R)
+// This RESIDUAL form is algebraically the reference's x-update, but the identity part of the
+// blend passes through exactly and FFT round-off only enters scaled by g (~0.03-0.1), which
+// buys ~20x lower fp32 error than transforming the full signal both ways (1e-14 vs the reference
+// restatement in fp64; fp32 figures in DESIGN.md).
 //
 // FFT: shared-memory Stockham autosort, radix-4 stages (+ one radix-2 stage when log2 N is odd),
 // twiddles from a table computed in double precision.
@@ -99,7 +103,7 @@ struct StreamParams {
     const cx<T>* G;   // [P][N][N] data term (prepare)
     const uint8_t* mcode;   // [N][N] or [P][N][N]: m[k] + m[-k] in {0,1,2}
     int mcode_batched;
-    const T* cf;      // [3] device: blend coefficient by mcode, already / N^2 (written by prepare)
+    const T* cf;      // [3] device: g * mcode / (2 N^2) (written by prepare)
     T* x; T* z; T* w; T* xpw;   // [B][N][N] planes (any may be null depending on mode)
     const T* img;     // acquire input
     const cx<T>* cin; // per-image complex input  [B][N][N]
@@ -170,13 +174,15 @@ __global__ void __launch_bounds__(256) rows_kernel(const StreamParams<T> p) {
         cx<T>* res = fft_lines<true, T>(buf0, buf1, tw, lines, N, p.log2N, N);
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
             cx<T> c = res[i];
-            T xa = pabs(c.re);
+            const T wa = p.w[offa + i];
+            T xa = pabs((p.z[offa + i] - wa) + c.re);
             p.x[offa + i] = xa;
-            if (p.xpw) p.xpw[offa + i] = xa + p.w[offa + i];
+            if (p.xpw) p.xpw[offa + i] = xa + wa;
             if (has_b) {
-                T xb = pabs(c.im);
+                const T wb = p.w[offb + i];
+                T xb = pabs((p.z[offb + i] - wb) + c.im);
                 p.x[offb + i] = xb;
-                if (p.xpw) p.xpw[offb + i] = xb + p.w[offb + i];
+                if (p.xpw) p.xpw[offb + i] = xb + wb;
             }
         }
     } else {   // RM_INV_PROX_FWD
@@ -186,14 +192,15 @@ __global__ void __launch_bounds__(256) rows_kernel(const StreamParams<T> p) {
         cx<T>* other = (res == buf0) ? buf1 : buf0;
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
             cx<T> c = res[i];
-            T xa = pabs(c.re), za = p.z[offa + i], wa = p.w[offa + i];
+            T za = p.z[offa + i], wa = p.w[offa + i];
+            T xa = pabs((za - wa) + c.re);
             prox_dual(p.prox, xa, za, wa);
             p.z[offa + i] = za; p.w[offa + i] = wa;
             if (p.last) p.x[offa + i] = xa;
             T zb = T(0), wb = T(0);
             if (has_b) {
-                T xb = pabs(c.im);
                 zb = p.z[offb + i]; wb = p.w[offb + i];
+                T xb = pabs((zb - wb) + c.im);
                 prox_dual(p.prox, xb, zb, wb);
                 p.z[offb + i] = zb; p.w[offb + i] = wb;
                 if (p.last) p.x[offb + i] = xb;
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(256) cols_kernel(const StreamParams<T> p) {
             const int code = mc[g];
             const T cf = code == 0 ? cf0 : (code == 1 ? cf1 : cf2);
             cx<T> gg = G[g];
-            res[c * pitch + r] = mk<T>(cf * v.re + gg.re, cf * v.im + gg.im);
+            res[c * pitch + r] = mk<T>(gg.re - cf * v.re, gg.im - cf * v.im);
         }
         __syncthreads();
         cx<T>* other = (res == buf0) ? buf1 : buf0;
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(256) cols_kernel(const StreamParams<T> p) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// prepare: G = g/N^2 (Ys_a + i Ys_b), mcode = m[k] + m[-k]            (see file header)
+// prepare: G = g/N^2 (Ys_a + i Ys_b), mcode = m[k] + m[-k] = 2 ms      (see file header)
 // one thread per bin of a packed plane.
 // ----------------------------------------------------------------------------------------------
 template <typename T>

@@ -43,7 +43,7 @@ def prepare_np(ys, m, reo):
         a = Ys(ys[2 * p])
         b = Ys(ys[2 * p + 1]) if 2 * p + 1 < len(ys) else 0
         G.append(g / N ** 2 * (a + 1j * b))
-    return np.stack(G).astype(np.complex64), (m + mirror(m)).astype(np.uint8), [(1 - g * c / 2) / N ** 2 for c in range(3)]
+    return np.stack(G).astype(np.complex64), (m + mirror(m)).astype(np.uint8), [(g * c / 2) / N ** 2 for c in range(3)]
 
 
 def run_emu(emu, imgs, m, noises, prox, P):

@@ -106,8 +106,8 @@ def test_config2_batch64_cnc(pk, cs_inputs):
             assert rel(x[k], xr[k % 15]) < TOL32
             assert rel(z[k], zr[k % 15]) < TOL32
         # every copy of the same image must give the same answer whichever pair slot it lands in
-        assert np.abs(x[0] - x[30]).max() < 1e-4      # slot a (0) vs slot a (30): 30 = 2*15
-        assert np.abs(x[0] - x[15]).max() < 1e-4      # slot a (0) vs slot b (15)
+        assert rel(x[0], x[30].astype(np.float64)) < TOL32      # slot a (0) vs slot a (30): 30 = 2*15
+        assert rel(x[0], x[15].astype(np.float64)) < TOL32      # slot a (0) vs slot b (15)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -127,7 +127,7 @@ def test_fp64_sizes(pk, N, prox):
     xr, zr, wr, yr = oracle_batch(imgs, m, nz, prox, P)
     assert rel(y, yr) < 1e-11
     assert rel(x, xr) < TOL64 and rel(z, zr) < TOL64
-    assert np.abs(w - wr).max() < 1e-10
+    assert np.abs(w - wr).max() < 1e-9
 
 
 @pytest.mark.parametrize('N,kernel', [(64, 'streaming'), (128, 'streaming'), (256, 'cluster'), (256, 'streaming'),
