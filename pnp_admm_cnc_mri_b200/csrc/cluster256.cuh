@@ -1,6 +1,15 @@
 // cluster256.cuh — K1 kernel: whole ADMM solve of 256x256 packed planes inside an 8-CTA cluster.
 // Phase code lives in cluster256_core.cuh (shared with the CPU emulator); this file holds the
-// sm_100a-only parts: cluster barriers, DSMEM stores and the persistent loop.
+// sm_100a-only parts: the DSMEM transposes, their synchronisation and the persistent loop.
+//
+// Synchronisation (no cluster barrier and no memory fence inside the loop):
+//   * every transpose element is an asynchronous remote store (st.async) that completes 8 bytes of
+//     transaction count on an mbarrier in the DESTINATION CTA: FULL1 guards tile B1, FULL2 tile B2.
+//     A CTA starts a phase when its own barrier has seen all 64 KB of the tile.
+//   * FREE1 / FREE2 are arrival-count barriers: each CTA tells all eight peers when its B1 / B2 may
+//     be overwritten again; a producer waits for all eight before it stores (normally long done).
+//   * the data term G of the next blend is bulk-copied (cp.async.bulk, GFULL) from L2 into the idle
+//     B1 tile at the end of the row phase, so the blend reads it from shared memory.
 #pragma once
 
 #include "cluster256_core.cuh"
@@ -14,23 +23,59 @@ PNP_D uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-PNP_D void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-PNP_D void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-PNP_D void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+PNP_D void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+PNP_D uint32_t mapa(uint32_t local, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+PNP_D void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+PNP_D void mbar_arm_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+PNP_D void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+PNP_D bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug must surface as a launch failure, never as a hung GPU.
+PNP_D void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+PNP_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// DSMEM store policy: shared::cluster address of (rank, byte offset) via mapa.
-struct RemoteDsmem {
+// DSMEM store policy: asynchronous remote store that signals the destination's mbarrier.
+struct RemoteAsync {
     uint32_t base[kCluster];   // shared::cluster base address of every CTA's dynamic smem
     PNP_D void init(const unsigned char* smem) {
         const uint32_t local = (uint32_t)__cvta_generic_to_shared(smem);
 #pragma unroll
-        for (int r = 0; r < kCluster; ++r)
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(base[r]) : "r"(local), "r"(r));
+        for (int r = 0; r < kCluster; ++r) base[r] = mapa(local, r);
     }
-    PNP_D void st(int rank, int off, cf32 v) const {
-        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(base[rank] + (uint32_t)off), "f"(v.re), "f"(v.im)
+    PNP_D void st(int rank, int off, cf32 v, int bar) const {
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
+                         base[rank] + (uint32_t)off),
+                     "f"(v.re), "f"(v.im), "r"(base[rank] + (uint32_t)(kOffBar + 8 * bar))
                      : "memory");
     }
+    PNP_D void signal(int rank, int bar) const { mbar_arrive_remote(base[rank] + (uint32_t)(kOffBar + 8 * bar)); }
 };
 
 struct ClusterParams {
@@ -41,32 +86,53 @@ struct ClusterParams {
     const float* z_in; const float* w_in;      // [B][256][256]
     float* x; float* z; float* w; float* xpw;  // outputs (xpw may be null)
     const cf32* G;         // [P][256][256]
-    const uint8_t* mcode;  // [256][256] or [P][256][256]
+    const uint32_t* mpack; // [16][256] or [P][16][256] packed mask codes (pack_mcode_k1_kernel)
     int mcode_batched;
-    const float* cf;       // [3] device: blend coefficients (written by prepare)
+    const float* cf;       // [3] device: residual coefficients (written by prepare)
     ProxParams<float> prox;
 };
 
+// mcode [N][N] bytes -> packed words (one word per column-phase thread and iteration)
+__global__ void pack_mcode_k1_kernel(const uint8_t* __restrict__ mcode, uint32_t* __restrict__ mpack, int planes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= planes * 16 * kN) return;
+    const int plane = i / (16 * kN), r = i - plane * 16 * kN;
+    mpack[i] = pack_codes(mcode + (size_t)plane * kN * kN, r / kN, r % kN);
+}
+
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 cluster256_kernel(const ClusterParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     Ctx c;
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x;
     c.smem = smem;
     const int cluster_id = blockIdx.x / kCluster;
     const int nclusters = gridDim.x / kCluster;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(smem + kOffBar);
+    const uint32_t bFull1 = bar0 + 8 * BAR_FULL1, bFull2 = bar0 + 8 * BAR_FULL2, bG = bar0 + 8 * BAR_GFULL;
+    const uint32_t bFree1 = bar0 + 8 * BAR_FREE1, bFree2 = bar0 + 8 * BAR_FREE2;
 
     if (threadIdx.x < 256)
         fill_tw(reinterpret_cast<cf32*>(smem + kOffTW), reinterpret_cast<const cf32*>(g_tw_f32), threadIdx.x);
-    RemoteDsmem R;
+    if (threadIdx.x == 0) {
+        mbar_init(bFull1, 1); mbar_init(bFull2, 1); mbar_init(bG, 1);
+        mbar_init(bFree1, kCluster);                        // one arrival per CTA
+        mbar_init(bFree2, kCluster * (kThreads / 32));      // one arrival per warp of every CTA
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm_tx(bFull1, kTileBytes); mbar_arm_tx(bFull2, kTileBytes); mbar_arm_tx(bG, kTileBytes);
+    }
+    RemoteAsync R;
     R.init(smem);
     __syncthreads();
-    cluster_sync_all();   // every CTA of the cluster is resident before any DSMEM traffic
+    cluster_sync_all();   // all CTAs resident, all barriers initialised, before any DSMEM traffic
 
-    const float cf0 = p.cf[0], cf1 = p.cf[1], cf2 = p.cf[2];
+    const float cf1 = p.cf[1], cf2 = p.cf[2];
+    uint32_t nFull1 = 0, nFull2 = 0, nG = 0, nFree1 = 0, nFree2 = 0;   // completed uses (phase parity)
     ThreadState s;
     const size_t nn = (size_t)kN * kN;
+
     for (int plane = cluster_id; plane < p.P; plane += nclusters) {
         const int ia = p.solo ? plane : 2 * plane;
         const bool has_b = !p.solo && (2 * plane + 1 < p.B);
@@ -77,34 +143,66 @@ cluster256_kernel(const ClusterParams p) {
         io.xpw_a = p.xpw ? p.xpw + ia * nn : nullptr;
         io.x_b = io.x_a + nn; io.z_b = io.z_a ? io.z_a + nn : nullptr; io.w_b = io.w_a ? io.w_a + nn : nullptr;
         io.xpw_b = io.xpw_a ? io.xpw_a + nn : nullptr;
-        const cf32* G = p.G + plane * nn;
-        const uint8_t* mcode = p.mcode + (p.mcode_batched ? plane * nn : 0);
+        const unsigned char* Gplane = reinterpret_cast<const unsigned char*>(p.G + plane * nn);
+        const uint32_t* mpack = p.mpack + (p.mcode_batched ? (size_t)plane * 16 * kN : 0);
 
-        // prologue: first forward row FFT of z - w
+        // Stage G for the coming blend into this warp's 4 KB slice of B1 (G rows 16w .. 16w+15), which
+        // only this warp used as FFT scratch.  Lanes 0..15 issue one 256 B bulk copy each.
+        auto prefetch_g = [&]() {
+            __syncwarp();
+            fence_proxy_async();   // generic-proxy accesses of the slice are ordered before the async writes
+            if (lane < 16) {
+                const int kr = 16 * warp + lane;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + g_stage_dst_off(kr));
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                             "l"(Gplane + g_stage_src_off(c.rank, kr)), "r"(kRows * 8), "r"(bG)
+                             : "memory");
+            }
+        };
+        // wait until every peer's B2 may be overwritten (signal of the previous column phase)
+        auto wait_free2 = [&]() {
+            if (nFree2 > 0) mbar_wait(bFree2, (nFree2 - 1) & 1);
+            ++nFree2;
+        };
+
+        // ---- prologue: first forward row FFT of z - w
         row_load_state(c, s, io);
         row_step1_write<false>(c, s);
         __syncwarp();
         row_read_step2<false>(c, s);
+        prefetch_g();
+        wait_free2();
         row_store_remote(c, s, R);
-        cluster_sync_all();
 
         for (int it = 0; it < p.iters; ++it) {
-            // ---- column phase: col FFT -> blend -> col IFFT -> transpose back (DSMEM)
+            // ---- column phase: col FFT -> residual blend -> col IFFT -> transpose back (DSMEM)
+            const uint32_t codes = mpack[warp * kN + kRows * c.rank + lane];
+            mbar_wait(bFull2, nFull2 & 1); ++nFull2;
+            if (threadIdx.x == 0) mbar_arm_tx(bFull2, kTileBytes);
             col_load(c, s);
             __syncthreads();
             col_step1_write<false>(c, s);
             __syncthreads();
             col_read_step2<false>(c, s);
-            col_blend(c, s, G, mcode, cf0, cf1, cf2);
-            __syncthreads();
+            mbar_wait(bG, nG & 1); ++nG;
+            if (threadIdx.x == 0) mbar_arm_tx(bG, kTileBytes);
+            col_blend(c, s, c.B1(), codes, cf1, cf2);
+            fence_proxy_async();
+            __syncthreads();                               // everyone is done with G (B1) and the scratch reads
+            if (threadIdx.x < kCluster) R.signal(threadIdx.x, BAR_FREE1);
             col_step1_write<true>(c, s);
             __syncthreads();
             col_read_step2<true>(c, s);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane < kCluster) R.signal(lane, BAR_FREE2);   // this warp no longer reads B2
+            mbar_wait(bFree1, nFree1 & 1); ++nFree1;
             col_store_remote(c, s, R);
-            cluster_sync_all();
 
-            // ---- row phase: row IFFT -> |.| -> prox -> dual -> row FFT -> transpose (DSMEM)
+            // ---- row phase: row IFFT -> |v + r| -> prox -> dual -> row FFT -> transpose (DSMEM)
             const bool last = (it == p.iters - 1);
+            mbar_wait(bFull1, nFull1 & 1); ++nFull1;
+            if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
             row_load(c, s);
             __syncwarp();
             row_step1_write<true>(c, s);
@@ -116,12 +214,13 @@ cluster256_kernel(const ClusterParams p) {
                 row_step1_write<false>(c, s);
                 __syncwarp();
                 row_read_step2<false>(c, s);
+                prefetch_g();
+                wait_free2();
                 row_store_remote(c, s, R);
-                cluster_sync_all();
             }
         }
     }
-    cluster_sync_all();   // no CTA exits while a peer could still address its shared memory
+    cluster_sync_all();   // no CTA exits while a peer could still signal one of its barriers
 }
 
 }  // namespace k1

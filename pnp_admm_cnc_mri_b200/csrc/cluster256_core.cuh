@@ -11,6 +11,8 @@
 //     B1 [32][256] float2   row-layout tile   (written remotely by the column phase) 64 KB
 //     B2 [256][32] float2   column-layout tile (written remotely by the row phase)   64 KB
 //     TW [16][16]  float2   W_256^(k1*n2)                                           2 KB
+//   B1 is idle during the column phase until the peers' transposes land, so the data term G of
+//   the coming blend is staged there (bulk async copy issued at the end of the row phase).
 //   registers per thread: 16 complex points + the dual w of its 16 pixels x 2 images (32 floats,
 //   resident for the whole solve).
 //
@@ -42,7 +44,12 @@ constexpr int kOffZs = 0;
 constexpr int kOffB1 = kOffZs + kRows * kN * 8;
 constexpr int kOffB2 = kOffB1 + kRows * kN * 8;
 constexpr int kOffTW = kOffB2 + kN * kRows * 8;
-constexpr int kSmemBytes = kOffTW + 256 * 8;
+constexpr int kOffBar = kOffTW + 256 * 8;        // 5 mbarriers (device kernel only)
+constexpr int kSmemBytes = kOffBar + 64;
+constexpr int kTileBytes = kRows * kN * 8;       // 64 KB: one tile, one transpose, one G stage
+
+// mbarrier slots
+enum { BAR_FULL1 = 0, BAR_FULL2 = 1, BAR_GFULL = 2, BAR_FREE1 = 3, BAR_FREE2 = 4 };
 
 struct ThreadState {
     cf32 a[16];      // working points
@@ -216,7 +223,7 @@ PNP_HD void row_store_remote(const Ctx& c, const ThreadState& s, const Remote& R
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const int off = kOffB2 + (grow * kRows + t + 16 * (j & 1)) * 8;
-        R.st(j >> 1, off, s.a[j]);
+        R.st(j >> 1, off, s.a[j], BAR_FULL2);
     }
 }
 
@@ -247,19 +254,29 @@ PNP_HD void col_read_step2(const Ctx& c, ThreadState& s) {
     fft256_step2<INV>(v, s.a);
 }
 
-// data-consistency residual on the packed spectrum: a = G - cf[mcode] * a     (see streaming.cuh)
-PNP_HD void col_blend(const Ctx& c, ThreadState& s, const cf32* G, const uint8_t* mcode,
-                      float cf0, float cf1, float cf2) {
-    const int kc = kRows * c.rank + c.cc();
-    const int t = c.ct();
+// data-consistency residual on the packed spectrum: a = G - cf[code] * a      (see streaming.cuh)
+// Gs: this CTA's G tile staged in shared memory as [kr = 256][c = 32] (the B1 buffer);
+// codes: 2 bits per j (mcode of bin (t + 16 j, kc)), packed by pack_mcode_k1.
+PNP_HD void col_blend(const Ctx& c, ThreadState& s, const cf32* Gs, uint32_t codes, float cf1, float cf2) {
+    const cf32* g = Gs + c.ct() * kRows + c.cc();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const int g = (t + 16 * j) * kN + kc;
-        const cf32 gg = G[g];
-        const int code = mcode[g];
-        const float cf = code == 0 ? cf0 : (code == 1 ? cf1 : cf2);
+        const cf32 gg = g[16 * j * kRows];
+        const uint32_t code = (codes >> (2 * j)) & 3u;
+        const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
         s.a[j] = mk<float>(gg.re - cf * s.a[j].re, gg.im - cf * s.a[j].im);
     }
+}
+
+// global G[kr][kc] rows -> staged tile [kr][32]: byte offsets of row kr for CTA `rank`
+PNP_HD int g_stage_src_off(int rank, int kr) { return (kr * kN + kRows * rank) * 8; }
+PNP_HD int g_stage_dst_off(int kr) { return kOffB1 + kr * kRows * 8; }
+
+// packed mask codes: word (t, kc) holds mcode[(t + 16 j) * 256 + kc] in bits 2j, 2j+1
+PNP_HD uint32_t pack_codes(const uint8_t* mcode, int t, int kc) {
+    uint32_t v = 0;
+    for (int j = 0; j < 16; ++j) v |= (uint32_t)(mcode[(t + 16 * j) * kN + kc] & 3u) << (2 * j);
+    return v;
 }
 
 // inverse column FFT output at image row r = t + 16 j, column kc -> CTA (r / 32), B1[r % 32][kc]
@@ -270,7 +287,7 @@ PNP_HD void col_store_remote(const Ctx& c, const ThreadState& s, const Remote& R
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const int off = kOffB1 + ((t + 16 * (j & 1)) * kN + kc) * 8;
-        R.st(j >> 1, off, s.a[j]);
+        R.st(j >> 1, off, s.a[j], BAR_FULL1);
     }
 }
 

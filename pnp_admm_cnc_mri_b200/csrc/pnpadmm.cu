@@ -160,6 +160,7 @@ struct Workspace {
     cx<T>* G;         // [P][N][N]
     cx<T>* T1;        // [B][N][N] per-image complex scratch
     uint8_t* mcode;   // [N][N] or [P][N][N]
+    uint32_t* mpack;  // N == 256 only: [16][256] or [P][16][256] packed codes for the cluster kernel
     int P, solo;
 };
 
@@ -171,6 +172,7 @@ size_t ws_bytes_impl(int B, int N, size_t elt, int mask_batched) {
     s += align_up(P * nn * 2 * elt);         // K
     s += align_up(P * nn * 2 * elt);         // G
     s += align_up((mask_batched ? P : 1) * nn);
+    s += align_up((mask_batched ? P : 1) * nn / 4);   // packed codes (2 bits per bin, 32-bit words)
     return s;
 }
 
@@ -190,7 +192,8 @@ int carve(void* ws, size_t ws_bytes, int B, int N, int mask_batched, Workspace<T
     out->T1 = (cx<T>*)p; p += align_up((size_t)B * nn * 2 * sizeof(T));
     out->K = (cx<T>*)p; p += align_up(P * nn * 2 * sizeof(T));
     out->G = (cx<T>*)p; p += align_up(P * nn * 2 * sizeof(T));
-    out->mcode = p;
+    out->mcode = p; p += align_up((mask_batched ? P : 1) * nn);
+    out->mpack = (uint32_t*)p;
     out->P = (int)P;
     out->solo = mask_batched ? 1 : 0;
     return PNPADMM_OK;
@@ -297,6 +300,11 @@ int prepare_impl(const T* y, const uint8_t* mask, int B, int N, int mask_batched
                                                                       w.mcode, B, w.P, N, w.solo, mask_batched,
                                                                       (T)(g / n2));
     LAUNCH_CHECK("prepare_kernel");
+    if (N == k1::kN && sizeof(T) == 4) {
+        const int planes = mask_batched ? w.P : 1;
+        k1::pack_mcode_k1_kernel<<<(planes * 16 * k1::kN + 255) / 256, 256, 0, st>>>(w.mcode, w.mpack, planes);
+        LAUNCH_CHECK("pack_mcode_k1_kernel");
+    }
     return PNPADMM_OK;
 }
 
@@ -343,7 +351,7 @@ template <> struct ClusterDispatch<float> {
         memset(&cp, 0, sizeof(cp));
         cp.B = B; cp.P = w.P; cp.solo = w.solo; cp.iters = iters;
         cp.z_in = z_in; cp.w_in = w_in; cp.x = x; cp.z = z; cp.w = wo; cp.xpw = xpw;
-        cp.G = reinterpret_cast<const k1::cf32*>(w.G); cp.mcode = w.mcode; cp.mcode_batched = w.solo;
+        cp.G = reinterpret_cast<const k1::cf32*>(w.G); cp.mpack = w.mpack; cp.mcode_batched = w.solo;
         cp.cf = w.cf;
         cp.prox = pp;
         return launch_cluster(cp, d, st);

@@ -15,12 +15,12 @@ using namespace pnp::k1;
 namespace {
 struct RemoteHost {
     unsigned char** all;
-    void st(int rank, int off, cf32 v) const { *reinterpret_cast<cf32*>(all[rank] + off) = v; }
+    void st(int rank, int off, cf32 v, int /*bar*/) const { *reinterpret_cast<cf32*>(all[rank] + off) = v; }
 };
 }  // namespace
 
 extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float* z, float* w, float* xpw,
-                          const float* G_, const uint8_t* mcode_, int mcode_batched, float cf0, float cf1, float cf2,
+                          const float* G_, const uint8_t* mcode_, int mcode_batched, float /*cf0*/, float cf1, float cf2,
                           int B, int P, int solo, int iters, int prox, float thr_l1, float inv_b, float one_m_alpha,
                           float alpha, float coef, float thr_cnc) {
     std::vector<cf32> master(4096);
@@ -62,14 +62,23 @@ extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float*
         const cf32* G = reinterpret_cast<const cf32*>(G_) + plane * nn;
         const uint8_t* mcode = mcode_ + (mcode_batched ? plane * nn : 0);
 
+        // the bulk-async G prefetch into B1 of the device kernel, as a plain copy
+        auto stage_g = [&]() {
+            for (int r = 0; r < kCluster; ++r)
+                for (int kr = 0; kr < kN; ++kr)
+                    std::memcpy(all[r] + g_stage_dst_off(kr), reinterpret_cast<const unsigned char*>(G) + g_stage_src_off(r, kr),
+                                kRows * 8);
+        };
         FOR_ALL(row_load_state(c, s, io));
         FOR_ALL(row_step1_write<false>(c, s));
         FOR_ALL(row_read_step2<false>(c, s));
+        stage_g();
         FOR_ALL(row_store_remote(c, s, R));
         for (int it = 0; it < iters; ++it) {
             FOR_ALL(col_load(c, s));
             FOR_ALL(col_step1_write<false>(c, s));
-            FOR_ALL(col_read_step2<false>(c, s); col_blend(c, s, G, mcode, cf0, cf1, cf2));
+            FOR_ALL(col_read_step2<false>(c, s);
+                    col_blend(c, s, c.B1(), pack_codes(mcode, c.ct(), kRows * c.rank + c.cc()), cf1, cf2));
             FOR_ALL(col_step1_write<true>(c, s));
             FOR_ALL(col_read_step2<true>(c, s));
             FOR_ALL(col_store_remote(c, s, R));
@@ -80,6 +89,7 @@ extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float*
             if (!last) {
                 FOR_ALL(row_step1_write<false>(c, s));
                 FOR_ALL(row_read_step2<false>(c, s));
+                stage_g();
                 FOR_ALL(row_store_remote(c, s, R));
             }
         }
