@@ -8,6 +8,9 @@
 //     A CTA starts a phase when its own barrier has seen all 64 KB of the tile.
 //   * FREE1 / FREE2 are arrival-count barriers: each CTA tells all eight peers when its B1 / B2 may
 //     be overwritten again; a producer waits for all eight before it stores (normally long done).
+//   mbarrier waits / remote arrives use the default (.cta-scoped acquire / release) forms, as CUTLASS
+//   does for cluster pipelines: the tiles live in shared memory, which no cache shadows, and the
+//   cluster-scoped forms cost an L1 invalidate (CCTL.IVALL) per wait and MEMBAR + ERRBAR per arrive.
 //   * the data term G of the next blend is bulk-copied (cp.async.bulk, GFULL) from L2 into the idle
 //     B1 tile at the end of the row phase, so the blend reads it from shared memory.
 #pragma once
@@ -39,13 +42,13 @@ PNP_D void mbar_arm_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 PNP_D void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 PNP_D bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -90,6 +93,7 @@ struct ClusterParams {
     int mcode_batched;
     const float* cf;       // [3] device: residual coefficients (written by prepare)
     ProxParams<float> prox;
+    int dbg;               // timing experiments only (results invalid): 1 = no transposes, 2 = no G staging
 };
 
 // mcode [N][N] bytes -> packed words (one word per column-phase thread and iteration)
@@ -149,6 +153,7 @@ cluster256_kernel(const ClusterParams p) {
         // Stage G for the coming blend into this warp's 4 KB slice of B1 (G rows 16w .. 16w+15), which
         // only this warp used as FFT scratch.  Lanes 0..15 issue one 256 B bulk copy each.
         auto prefetch_g = [&]() {
+            if (p.dbg & 2) return;
             __syncwarp();
             fence_proxy_async();   // generic-proxy accesses of the slice are ordered before the async writes
             if (lane < 16) {
@@ -161,6 +166,7 @@ cluster256_kernel(const ClusterParams p) {
         };
         // wait until every peer's B2 may be overwritten (signal of the previous column phase)
         auto wait_free2 = [&]() {
+            if (p.dbg & 1) return;
             if (nFree2 > 0) mbar_wait(bFree2, (nFree2 - 1) & 1);
             ++nFree2;
         };
@@ -172,37 +178,45 @@ cluster256_kernel(const ClusterParams p) {
         row_read_step2<false>(c, s);
         prefetch_g();
         wait_free2();
-        row_store_remote(c, s, R);
+        if (!(p.dbg & 1)) row_store_remote(c, s, R);
 
         for (int it = 0; it < p.iters; ++it) {
             // ---- column phase: col FFT -> residual blend -> col IFFT -> transpose back (DSMEM)
             const uint32_t codes = mpack[warp * kN + kRows * c.rank + lane];
-            mbar_wait(bFull2, nFull2 & 1); ++nFull2;
-            if (threadIdx.x == 0) mbar_arm_tx(bFull2, kTileBytes);
+            if (!(p.dbg & 1)) {
+                mbar_wait(bFull2, nFull2 & 1); ++nFull2;
+                if (threadIdx.x == 0) mbar_arm_tx(bFull2, kTileBytes);
+            }
             col_load(c, s);
             __syncthreads();
             col_step1_write<false>(c, s);
             __syncthreads();
             col_read_step2<false>(c, s);
-            mbar_wait(bG, nG & 1); ++nG;
-            if (threadIdx.x == 0) mbar_arm_tx(bG, kTileBytes);
+            if (!(p.dbg & 2)) {
+                mbar_wait(bG, nG & 1); ++nG;
+                if (threadIdx.x == 0) mbar_arm_tx(bG, kTileBytes);
+            }
             col_blend(c, s, c.B1(), codes, cf1, cf2);
             fence_proxy_async();
             __syncthreads();                               // everyone is done with G (B1) and the scratch reads
-            if (threadIdx.x < kCluster) R.signal(threadIdx.x, BAR_FREE1);
+            if (threadIdx.x < kCluster && !(p.dbg & 1)) R.signal(threadIdx.x, BAR_FREE1);
             col_step1_write<true>(c, s);
             __syncthreads();
             col_read_step2<true>(c, s);
             fence_proxy_async();
             __syncwarp();
-            if (lane < kCluster) R.signal(lane, BAR_FREE2);   // this warp no longer reads B2
-            mbar_wait(bFree1, nFree1 & 1); ++nFree1;
-            col_store_remote(c, s, R);
+            if (!(p.dbg & 1)) {
+                if (lane < kCluster) R.signal(lane, BAR_FREE2);   // this warp no longer reads B2
+                mbar_wait(bFree1, nFree1 & 1); ++nFree1;
+                col_store_remote(c, s, R);
+            }
 
             // ---- row phase: row IFFT -> |v + r| -> prox -> dual -> row FFT -> transpose (DSMEM)
             const bool last = (it == p.iters - 1);
-            mbar_wait(bFull1, nFull1 & 1); ++nFull1;
-            if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
+            if (!(p.dbg & 1)) {
+                mbar_wait(bFull1, nFull1 & 1); ++nFull1;
+                if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
+            }
             row_load(c, s);
             __syncwarp();
             row_step1_write<true>(c, s);
@@ -216,7 +230,7 @@ cluster256_kernel(const ClusterParams p) {
                 row_read_step2<false>(c, s);
                 prefetch_g();
                 wait_free2();
-                row_store_remote(c, s, R);
+                if (!(p.dbg & 1)) row_store_remote(c, s, R);
             }
         }
     }

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -354,6 +355,8 @@ template <> struct ClusterDispatch<float> {
         cp.G = reinterpret_cast<const k1::cf32*>(w.G); cp.mpack = w.mpack; cp.mcode_batched = w.solo;
         cp.cf = w.cf;
         cp.prox = pp;
+        const char* dbg = getenv("PNPADMM_K1_DEBUG");   // timing experiments only
+        cp.dbg = dbg ? atoi(dbg) : 0;
         return launch_cluster(cp, d, st);
     }
 };
