@@ -62,6 +62,12 @@ PNP_D void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 24)) __trap();
     }
 }
+PNP_D int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+PNP_D void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 PNP_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // DSMEM store policy: asynchronous remote store that signals the destination's mbarrier.
@@ -93,6 +99,12 @@ struct ClusterParams {
     int mcode_batched;
     const float* cf;       // [3] device: residual coefficients (written by prepare)
     ProxParams<float> prox;
+    // Chunked static schedule: when P is not a multiple of the resident clusters, each plane's `iters`
+    // are cut into n_chunks pieces of `chunk` iterations; task = chunk * P + plane, cluster k runs tasks
+    // k, k + nclusters, ...  A plane's z, w state is handed from one cluster to the next through global
+    // memory (L2), guarded by progress[plane][rank] (chunks completed, release/acquire at gpu scope).
+    int chunk, n_chunks;
+    int* progress;         // [P][8], zeroed before the launch (unused when n_chunks == 1)
     int dbg;               // timing experiments only (results invalid): 1 = no transposes, 2 = no G staging
 };
 
@@ -137,16 +149,33 @@ cluster256_kernel(const ClusterParams p) {
     ThreadState s;
     const size_t nn = (size_t)kN * kN;
 
-    for (int plane = cluster_id; plane < p.P; plane += nclusters) {
+    const int mode = (p.prox.prox == PROX_NONE) ? PROX_NONE : prox_mode(p.prox);
+    const int ntasks = p.P * p.n_chunks;
+    for (int task = cluster_id; task < ntasks; task += nclusters) {
+        const int plane = task % p.P, chunk = task / p.P;
+        const int it0 = chunk * p.chunk;
+        const int it1 = (it0 + p.chunk < p.iters) ? it0 + p.chunk : p.iters;
+        const bool final_chunk = (it1 == p.iters);
         const int ia = p.solo ? plane : 2 * plane;
         const bool has_b = !p.solo && (2 * plane + 1 < p.B);
         PlaneIO io;
-        io.z_in_a = p.z_in + ia * nn; io.w_in_a = p.w_in + ia * nn;
+        // first chunk starts from the caller's z, w; later chunks from the state the previous cluster left
+        const float* zsrc = (chunk == 0) ? p.z_in : p.z;
+        const float* wsrc = (chunk == 0) ? p.w_in : p.w;
+        io.z_in_a = zsrc + ia * nn; io.w_in_a = wsrc + ia * nn;
         io.z_in_b = has_b ? io.z_in_a + nn : nullptr; io.w_in_b = has_b ? io.w_in_a + nn : nullptr;
         io.x_a = p.x + ia * nn; io.z_a = p.z ? p.z + ia * nn : nullptr; io.w_a = p.w ? p.w + ia * nn : nullptr;
         io.xpw_a = p.xpw ? p.xpw + ia * nn : nullptr;
         io.x_b = io.x_a + nn; io.z_b = io.z_a ? io.z_a + nn : nullptr; io.w_b = io.w_a ? io.w_a + nn : nullptr;
         io.xpw_b = io.xpw_a ? io.xpw_a + nn : nullptr;
+        if (chunk > 0) {   // rows of this rank were written by the same rank of another cluster
+            if (threadIdx.x == 0) {
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(p.progress + plane * kCluster + c.rank) < chunk)
+                    if (++spins > (1u << 26)) __trap();
+            }
+            __syncthreads();
+        }
         const unsigned char* Gplane = reinterpret_cast<const unsigned char*>(p.G + plane * nn);
         const uint32_t* mpack = p.mpack + (p.mcode_batched ? (size_t)plane * 16 * kN : 0);
 
@@ -180,7 +209,7 @@ cluster256_kernel(const ClusterParams p) {
         wait_free2();
         if (!(p.dbg & 1)) row_store_remote(c, s, R);
 
-        for (int it = 0; it < p.iters; ++it) {
+        for (int it = it0; it < it1; ++it) {
             // ---- column phase: col FFT -> residual blend -> col IFFT -> transpose back (DSMEM)
             const uint32_t codes = mpack[warp * kN + kRows * c.rank + lane];
             if (!(p.dbg & 1)) {
@@ -212,7 +241,7 @@ cluster256_kernel(const ClusterParams p) {
             }
 
             // ---- row phase: row IFFT -> |v + r| -> prox -> dual -> row FFT -> transpose (DSMEM)
-            const bool last = (it == p.iters - 1);
+            const bool last = (it == it1 - 1);
             if (!(p.dbg & 1)) {
                 mbar_wait(bFull1, nFull1 & 1); ++nFull1;
                 if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
@@ -222,7 +251,7 @@ cluster256_kernel(const ClusterParams p) {
             row_step1_write<true>(c, s);
             __syncwarp();
             row_read_step2<true>(c, s);
-            row_prox(c, s, p.prox, has_b, last, io);
+            row_prox_dispatch(mode, c, s, p.prox, has_b, last, final_chunk, io);
             if (!last) {
                 __syncwarp();
                 row_step1_write<false>(c, s);
@@ -231,6 +260,13 @@ cluster256_kernel(const ClusterParams p) {
                 prefetch_g();
                 wait_free2();
                 if (!(p.dbg & 1)) row_store_remote(c, s, R);
+            }
+        }
+        if (!final_chunk) {   // publish this rank's rows of z, w for the cluster that continues the plane
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                st_release_gpu(p.progress + plane * kCluster + c.rank, chunk + 1);
             }
         }
     }

@@ -143,9 +143,9 @@ PNP_HD void row_load_state(const Ctx& c, ThreadState& s, const PlaneIO& io) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const int n = t + 16 * j;
-        const float za = io.z_in_a[g0 + n], wa = io.w_in_a[g0 + n];
+        const float za = ld_state(io.z_in_a + g0 + n), wa = ld_state(io.w_in_a + g0 + n);
         float zb = 0.f, wb = 0.f;
-        if (io.z_in_b) { zb = io.z_in_b[g0 + n]; wb = io.w_in_b[g0 + n]; }
+        if (io.z_in_b) { zb = ld_state(io.z_in_b + g0 + n); wb = ld_state(io.w_in_b + g0 + n); }
         Zs[n] = mk<float>(za, zb);
         s.w[2 * j] = wa; s.w[2 * j + 1] = wb;
         s.a[j] = mk<float>(za - wa, zb - wb);
@@ -179,8 +179,10 @@ PNP_HD void row_read_step2(const Ctx& c, ThreadState& s) {
 }
 
 // after the inverse row FFT (a = r, the residual correction): x = |v + r|; prox; dual; next a = z - w.
-// `last`: write x, z, w (and x + w) to global memory.
-PNP_HD void row_prox(const Ctx& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last,
+// MODE: PM_L1 / PM_CNC / PM_GENERAL, or PROX_NONE (x-update only: emit x and x + w, state untouched).
+// `last`: end of this cluster's run on the plane -> z, w go to global memory (x too if want_x).
+template <int MODE>
+PNP_HD void row_prox(const Ctx& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last, bool want_x,
                      const PlaneIO& io) {
     const int row = c.row(), t = c.rt();
     const int g0 = (kRows * c.rank + row) * kN;
@@ -193,25 +195,39 @@ PNP_HD void row_prox(const Ctx& c, ThreadState& s, const ProxParams<float>& p, b
         // residual form: x = |v + r|, v = z - w the very value that was transformed
         const float xa = pabs((za - wa) + s.a[j].re);
         const float xb = has_b ? pabs((zb - wb) + s.a[j].im) : 0.f;
-        if (p.prox == PROX_NONE) {
+        if (MODE == PROX_NONE) {
             io.x_a[g0 + n] = xa;
             if (io.xpw_a) io.xpw_a[g0 + n] = xa + wa;
             if (has_b) {
                 io.x_b[g0 + n] = xb;
                 if (io.xpw_b) io.xpw_b[g0 + n] = xb + wb;
             }
-            continue;
-        }
-        prox_dual(p, xa, za, wa);
-        if (has_b) prox_dual(p, xb, zb, wb);
-        s.w[2 * j] = wa; s.w[2 * j + 1] = wb;
-        if (last) {
-            io.x_a[g0 + n] = xa; io.z_a[g0 + n] = za; io.w_a[g0 + n] = wa;
-            if (has_b) { io.x_b[g0 + n] = xb; io.z_b[g0 + n] = zb; io.w_b[g0 + n] = wb; }
         } else {
-            Zs[n] = mk<float>(za, zb);
-            s.a[j] = mk<float>(za - wa, zb - wb);
+            prox_dual_m<MODE>(p, xa, za, wa);
+            if (has_b) prox_dual_m<MODE>(p, xb, zb, wb);
+            s.w[2 * j] = wa; s.w[2 * j + 1] = wb;
+            if (last) {
+                io.z_a[g0 + n] = za; io.w_a[g0 + n] = wa;
+                if (want_x) io.x_a[g0 + n] = xa;
+                if (has_b) {
+                    io.z_b[g0 + n] = zb; io.w_b[g0 + n] = wb;
+                    if (want_x) io.x_b[g0 + n] = xb;
+                }
+            } else {
+                Zs[n] = mk<float>(za, zb);
+                s.a[j] = mk<float>(za - wa, zb - wb);
+            }
         }
+    }
+}
+
+PNP_HD void row_prox_dispatch(int mode, const Ctx& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last,
+                              bool want_x, const PlaneIO& io) {
+    switch (mode) {
+        case PM_L1: row_prox<PM_L1>(c, s, p, has_b, last, want_x, io); break;
+        case PM_CNC: row_prox<PM_CNC>(c, s, p, has_b, last, want_x, io); break;
+        case PROX_NONE: row_prox<PROX_NONE>(c, s, p, has_b, last, want_x, io); break;
+        default: row_prox<PM_GENERAL>(c, s, p, has_b, last, want_x, io); break;
     }
 }
 

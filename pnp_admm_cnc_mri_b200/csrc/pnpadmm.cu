@@ -162,6 +162,7 @@ struct Workspace {
     cx<T>* T1;        // [B][N][N] per-image complex scratch
     uint8_t* mcode;   // [N][N] or [P][N][N]
     uint32_t* mpack;  // N == 256 only: [16][256] or [P][16][256] packed codes for the cluster kernel
+    int* progress;    // [P][8] hand-off counters of the chunked cluster schedule
     int P, solo;
 };
 
@@ -174,6 +175,7 @@ size_t ws_bytes_impl(int B, int N, size_t elt, int mask_batched) {
     s += align_up(P * nn * 2 * elt);         // G
     s += align_up((mask_batched ? P : 1) * nn);
     s += align_up((mask_batched ? P : 1) * nn / 4);   // packed codes (2 bits per bin, 32-bit words)
+    s += align_up(P * 8 * sizeof(int));               // progress counters
     return s;
 }
 
@@ -194,7 +196,8 @@ int carve(void* ws, size_t ws_bytes, int B, int N, int mask_batched, Workspace<T
     out->K = (cx<T>*)p; p += align_up(P * nn * 2 * sizeof(T));
     out->G = (cx<T>*)p; p += align_up(P * nn * 2 * sizeof(T));
     out->mcode = p; p += align_up((mask_batched ? P : 1) * nn);
-    out->mpack = (uint32_t*)p;
+    out->mpack = (uint32_t*)p; p += align_up((mask_batched ? P : 1) * nn / 4);
+    out->progress = (int*)p;
     out->P = (int)P;
     out->solo = mask_batched ? 1 : 0;
     return PNPADMM_OK;
@@ -210,6 +213,7 @@ ProxParams<T> make_prox(int prox, double lambda1, double reo, double alpha, doub
     p.alpha = (T)alpha;
     p.coef = (T)(alpha * reo * lambda1 * b);
     p.thr_cnc = (T)(alpha * reo * lambda1);
+    p.general = (p.thr_l1 < T(0) || p.inv_b < T(0) || p.thr_cnc < T(0)) ? 1 : 0;
     return p;
 }
 
@@ -320,8 +324,29 @@ int pick_kernel(int kernel, int N, bool f64, const DeviceState* d, bool* use_clu
     return PNPADMM_OK;
 }
 
-int launch_cluster(const k1::ClusterParams& cp, const DeviceState* d, cudaStream_t st) {
-    int ncl = cp.P < d->max_clusters_256 ? cp.P : d->max_clusters_256;
+// Pick the chunking of the static cluster schedule: minimise ceil(P n / ncl) * (ceil(iters / n) + hand-off).
+void plan_chunks(int P, int iters, int max_clusters, int* chunk, int* n_chunks) {
+    *chunk = iters; *n_chunks = 1;
+    if (P <= max_clusters || P % max_clusters == 0 || iters < 2) return;
+    const double handoff = 0.35;   // iterations' worth of time to spill + reload a plane's z, w through L2
+    double best = 1e30;
+    for (int n = 1; n <= 10 && n <= iters; ++n) {
+        const int c = (iters + n - 1) / n, nn = (iters + c - 1) / c;
+        const long steps = ((long)P * nn + max_clusters - 1) / max_clusters;
+        const double cost = steps * (c + (nn > 1 ? handoff : 0.0));
+        if (cost < best - 1e-9) { best = cost; *chunk = c; *n_chunks = nn; }
+    }
+}
+
+int launch_cluster(k1::ClusterParams& cp, const DeviceState* d, cudaStream_t st) {
+    plan_chunks(cp.P, cp.iters, d->max_clusters_256, &cp.chunk, &cp.n_chunks);
+    if (const char* e = getenv("PNPADMM_K1_CHUNKS")) {   // experiments: force the chunk count
+        const int n = atoi(e);
+        if (n >= 1 && n <= cp.iters) { cp.chunk = (cp.iters + n - 1) / n; cp.n_chunks = (cp.iters + cp.chunk - 1) / cp.chunk; }
+    }
+    if (cp.n_chunks > 1) CUDA_TRY(cudaMemsetAsync(cp.progress, 0, sizeof(int) * cp.P * k1::kCluster, st));
+    const long ntasks = (long)cp.P * cp.n_chunks;
+    int ncl = ntasks < d->max_clusters_256 ? (int)ntasks : d->max_clusters_256;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(ncl * k1::kCluster);
@@ -335,7 +360,7 @@ int launch_cluster(const k1::ClusterParams& cp, const DeviceState* d, cudaStream
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_kernel, cp));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_kernel, (const k1::ClusterParams)cp));
     return PNPADMM_OK;
 }
 
@@ -353,6 +378,7 @@ template <> struct ClusterDispatch<float> {
         cp.B = B; cp.P = w.P; cp.solo = w.solo; cp.iters = iters;
         cp.z_in = z_in; cp.w_in = w_in; cp.x = x; cp.z = z; cp.w = wo; cp.xpw = xpw;
         cp.G = reinterpret_cast<const k1::cf32*>(w.G); cp.mpack = w.mpack; cp.mcode_batched = w.solo;
+        cp.progress = w.progress;
         cp.cf = w.cf;
         cp.prox = pp;
         const char* dbg = getenv("PNPADMM_K1_DEBUG");   // timing experiments only

@@ -34,7 +34,7 @@ extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float*
     RemoteHost R{all};
     std::vector<ThreadState> st((size_t)kCluster * kThreads);
     ProxParams<float> pp;
-    pp.prox = prox; pp.thr_l1 = thr_l1; pp.inv_b = inv_b; pp.one_m_alpha = one_m_alpha;
+    pp.prox = prox; pp.general = 0; pp.thr_l1 = thr_l1; pp.inv_b = inv_b; pp.one_m_alpha = one_m_alpha;
     pp.alpha = alpha; pp.coef = coef; pp.thr_cnc = thr_cnc;
 
     for (int r = 0; r < kCluster; ++r)
@@ -85,7 +85,7 @@ extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float*
             const bool last = (it == iters - 1);
             FOR_ALL(row_load(c, s));
             FOR_ALL(row_step1_write<true>(c, s));
-            FOR_ALL(row_read_step2<true>(c, s); row_prox(c, s, pp, has_b, last, io));
+            FOR_ALL(row_read_step2<true>(c, s); row_prox_dispatch(prox == PROX_NONE ? PROX_NONE : prox_mode(pp), c, s, pp, has_b, last, true, io));
             if (!last) {
                 FOR_ALL(row_step1_write<false>(c, s));
                 FOR_ALL(row_read_step2<false>(c, s));

@@ -219,6 +219,20 @@ def test_stepwise_iterate_equals_solve(pk, cs_inputs):
         assert torch.equal(x, x1) and torch.equal(z, z1) and torch.equal(w, w1)
 
 
+def test_chunked_cluster_schedule_is_bit_identical(pk, cs_inputs, monkeypatch):
+    """The chunked static schedule (plane state handed between clusters through L2) must not change a bit."""
+    imgs = _imgs(cs_inputs, range(7))
+    m = cs_inputs['masks'][0]
+    monkeypatch.setenv('PNPADMM_K1_CHUNKS', '1')
+    a = pk.admm_solve(imgs, m, cs_inputs['noises'], prox='cnc', kernel='cluster', return_state=True, **kat.CNC_DEFAULTS)
+    for n in ('3', '7', '50'):
+        monkeypatch.setenv('PNPADMM_K1_CHUNKS', n)
+        b = pk.admm_solve(imgs, m, cs_inputs['noises'], prox='cnc', kernel='cluster', return_state=True, **kat.CNC_DEFAULTS)
+        for u, v in zip(a[:3], b[:3]):
+            assert np.array_equal(u, v), n
+    monkeypatch.delenv('PNPADMM_K1_CHUNKS')
+
+
 def test_cluster_and_streaming_agree(pk, cs_inputs):
     imgs = _imgs(cs_inputs, range(6))
     m = cs_inputs['masks'][1]
