@@ -281,10 +281,10 @@ def run_ours(args):
             'e2e': {'value': e2e, 'unit': 'iterations/s', 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(h_img.numel() + h_masks[0].numel() + h_noise.numel() * 4),
                     'd2h_bytes_per_step': int(h_x.numel() * 4), 'api': 'pnpadmm_reconstruct_host_f32 (pinned host buffers)'},
-            'gpu_launches': 8 * args.steps,
-            'launches_per_step': {'device': 8, 'e2e': 9,
+            'gpu_launches': 9 * args.steps,
+            'launches_per_step': {'device': 9, 'e2e': 10,
                                   'kernels': 'rows<FWD_IMG>, cols<FWD_ACQ>, cols<INV>, rows<INV_ABS>, copy_zero, write_cf, '
-                                             'prepare, cluster256 (+ u8_to_unit in e2e)'},
+                                             'prepare, pack_mcode_k1, cluster256 (+ u8_to_unit in e2e)'},
             'roofline': {'bound': 'fp32', 'kernel': 'cluster256_kernel', 'achieved': achieved, 'peak': nominal_peak,
                          'unit': 'TFLOP/s', 'frac': achieved / nominal_peak, 'traffic': None,
                          'peak_source': f'nominal non-tensor FP32: {sm.value} SMs x 128 lanes x 2 x {sm_max:.0f} MHz '

@@ -1,0 +1,139 @@
+"""GPU: PnP variants (rows a7-a10 of the scope table) and the drop-in entry points."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kat_table as kat
+from oracle import reference_numpy as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return np.load(os.path.join(GOLD, 'pnp_golden.npz'))
+
+
+@pytest.fixture(scope='module')
+def env(cs_inputs):
+    import pnp_admm_cnc_mri_b200 as pk
+    pk.load_library()
+    img = orc.preprocess_uint8(cs_inputs['images'][4])
+    return pk, img, cs_inputs['masks'][0], cs_inputs['noises']
+
+
+def _D(name, it, x8, nz, dtype=torch.float32):
+    from pnp_admm_cnc_mri_b200.denoisers import Denoiser
+    return Denoiser(name, iter_num=it, x8=x8, noises=nz, dtype=dtype, seed=0)
+
+
+def test_pnp_cnc_dncnn_vs_unmodified_reference(env, gold):
+    """PNP_ADMM_CNC_DnCNN (S6:372) with the same fp32 weights as the unmodified script run."""
+    pk, img, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_cnc
+    it = int(gold['iters'])
+    D = _D('dncnn_25', it, False, nz)
+    x = pnp_admm_cnc(img, m, nz, D, D, alpha=1.2, iter_num=it, lambda1=4, reo=0.45, b=0.3)
+    assert rel(x, gold['cnc_dncnn']) < 1e-4
+    assert np.abs(x - gold['cnc_dncnn']).max() < 1e-3
+
+
+def test_pnp_cnc_drunet_vs_unmodified_reference(env, gold):
+    pk, img, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_cnc
+    it = int(gold['iters'])
+    x = pnp_admm_cnc(img, m, nz, _D('drunet_gray', it, False, nz), None, alpha=1, iter_num=it, lambda1=0.8, reo=0.8, b=0.45)
+    assert rel(x, gold['cnc_drunet']) < 1e-4
+
+
+def test_pnp_l1_drunet_x8_vs_unmodified_reference(env, gold):
+    pk, img, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_l1
+    it = int(gold['iters'])
+    x = pnp_admm_l1(img, m, nz, _D('drunet_gray', it, True, nz), iter_num=it, reo=0.26)
+    assert rel(x, gold['l1_drunet']) < 1e-4
+
+
+@pytest.mark.parametrize('name,x8', [('ffdnet_gray', False), ('fdncnn_gray', False), ('ircnn_gray', False), ('dncnn_15', False)])
+def test_pnp_l1_other_denoisers_vs_oracle(env, name, x8):
+    """Every denoiser branch of denoising_step1 (S3:19-68), 4 iterations, batch of 3 vs the oracle per image."""
+    pk, img, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_l1
+    from pnp_admm_cnc_mri_b200.denoisers import Denoiser
+    it = 4
+    imgs = np.stack([img, img[::-1].copy(), img.T.copy()])
+    x = pnp_admm_l1(imgs, m, nz, _D(name, it, x8, nz), iter_num=it, reo=0.25)
+    Dc = Denoiser(name, iter_num=it, x8=x8, noises=nz, dtype=torch.float32, device='cpu', seed=0)
+    f = lambda a, i: Dc(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))[None, None], i)[0, 0].numpy()
+    for k in range(3):
+        xr = orc.pnp_admm_l1(imgs[k], m.astype(np.float64), nz, f, iter_num=it, reo=0.25)
+        assert rel(x[k], xr) < 1e-4, (name, k)
+
+
+def test_pnp_512_quadrant_tiling(env):
+    """Config 4 shape: DRUNet on 512x512 goes through the 4 x 288^2 quadrant path (utils_model.py:91-108)."""
+    pk, *_ = env
+    from pnp_admm_cnc_mri_b200 import data
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_l1
+    from pnp_admm_cnc_mri_b200.denoisers import Denoiser
+    N, it = 512, 2
+    imgs = data.phantoms(2, N, seed0=5)
+    m = data.make_mask('random', N, seed=3)
+    nz = data.make_noise(N, seed=4)
+    x = pnp_admm_l1(imgs, m, nz, _D('drunet_gray', it, True, nz), iter_num=it, reo=0.26)
+    Dc = Denoiser('drunet_gray', iter_num=it, x8=True, dtype=torch.float32, device='cpu', seed=0)
+    f = lambda a, i: Dc(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))[None, None], i)[0, 0].numpy()
+    xr = orc.pnp_admm_l1(imgs[0], m.astype(np.float64), nz, f, iter_num=it, reo=0.26)
+    assert rel(x[0], xr) < 1e-4
+
+
+def test_bf16_denoiser_single_call_error(env):
+    """bf16 tensor-core denoisers vs the same fp32 network: reported as single-call relative error."""
+    pk, img, m, nz = env
+    x = torch.as_tensor(img, device='cuda')[None, None].repeat(4, 1, 1, 1)
+    for name in ('dncnn_25', 'drunet_gray', 'ffdnet_gray'):
+        a = _D(name, 50, False, nz, torch.float32)(x, 3)
+        b = _D(name, 50, False, nz, torch.bfloat16)(x, 3)
+        err = float((a - b).norm() / a.norm())
+        print(f'{name}: bf16 vs fp32 single-call rel error {err:.2e}')
+        assert err < 2e-2
+
+
+def test_drop_in_entry_points(env, cs_inputs, ref_out, tmp_path, monkeypatch):
+    """Same names / kwargs / return contract as the reference functions (S1:29, S4:31, S6:372)."""
+    pk, img, m, nz = env
+    from pnp_admm_cnc_mri_b200 import reference_api as api
+    monkeypatch.chdir(tmp_path)
+    os.makedirs('testsets/Set1')
+    import cv2
+    cv2.imwrite('testsets/Set1/05.png', cs_inputs['images'][4])
+    mask64 = m.astype(np.float64)
+    out = api.ADMM_L1(mask64, nz, iter_num=50, lambda1=0.1, reo=0.015)
+    assert isinstance(out, list) and len(out) == 22 and out[1].dtype == np.uint8 and out[1].shape == (256, 256)
+    assert out[0].dtype == np.float64 and rel(out[0], ref_out['l1']) < 1e-4
+    assert os.path.exists('results/Set1_dn_ADMM_L1/05_PDG L1.png')
+    log = open('results/Set1_dn_ADMM_L1/Set1_dn_ADMM_L1.log').read()
+    assert '05.png - PSNR: 23.87 dB; SSIM: 0.5877 ; RE: 0.2028.' in log           # the reference's own log line
+    out = api.ADMM_CNC(mask64, nz, **api.PRESETS['ADMM_CNC'])
+    assert rel(out[0], ref_out['cnc']) < 1e-4
+    assert 'PSNR: 24.5765 dB; SSIM: 0.5600 ; RE: 0.1870.' in open('results/Set1_dn_ADMM_CNC/Set1_dn_ADMM_CNC.log').read()
+    # function-level fallbacks when kwargs are omitted (S4:37-41): alpha .4, 4 iterations, lambda .04, reo 2.75, b 1
+    out = api.ADMM_CNC(mask64, nz, save_E=False)
+    assert rel(out[0], orc.admm_cnc(img, mask64, nz, 0.4, 4, 0.04, 2.75, 1)) < 1e-4
+    out, psnr1 = api.PNP_ADMM_CNC_DnCNN('dncnn_25', 'dncnn_15', mask64, nz, iter_num=2, alpha=1.2, lambda1=4, reo=0.45, b=0.3,
+                                        save_E=False)
+    assert len(out) == 21 and len(psnr1) == 22 and out[0].dtype == np.float32 and psnr1[0] > 15
+    out = api.PNP_ADMM_L1_D('drunet_gray', mask64, nz, iter_num=2, reo=0.26, save_E=False)
+    assert len(out) == 22 and out[0].shape == (256, 256)
+    s = api.soft(np.array([-2.0, -0.5, 0.0, 0.5, 2.0]), 1.0)
+    assert np.array_equal(s, orc.soft(np.array([-2.0, -0.5, 0.0, 0.5, 2.0]), 1.0))
+    ns = api.analyze_parse_ADMM_CNC(0.45, 50, 0.5, 0.05, 64, argv=['--iter_num', '7'])
+    assert (ns.alpha, ns.iter_num, ns.lambda1, ns.reo, ns.b) == (0.45, 7, 0.5, 0.05, 64)
