@@ -263,8 +263,12 @@ class Denoiser:
         self.ffdnet_sigma = torch.full((1, 1, 1, 1), 15 / 255., device=self.device)                 # S3:64
 
     def _run(self, x, *extra):
-        y = self.net(x.to(self.dtype).contiguous(memory_format=torch.channels_last), *extra)
-        return y.float()
+        xin = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        if self.dtype == torch.float32 and xin.is_cuda:
+            # a float32 denoiser is the parity configuration: keep cuDNN off the TF32 path
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self.net(xin, *extra).float()
+        return self.net(xin, *extra).float()
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor, i: int = 0) -> torch.Tensor:
