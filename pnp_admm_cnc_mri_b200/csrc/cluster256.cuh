@@ -71,20 +71,17 @@ PNP_D void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s
 PNP_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // DSMEM store policy: asynchronous remote store that signals the destination's mbarrier.
+template <int CL>
 struct RemoteAsync {
-    uint32_t base[kCluster];   // shared::cluster base address of every CTA's dynamic smem
-    PNP_D void init(const unsigned char* smem) {
-        const uint32_t local = (uint32_t)__cvta_generic_to_shared(smem);
-#pragma unroll
-        for (int r = 0; r < kCluster; ++r) base[r] = mapa(local, r);
-    }
+    typedef Geo<CL> G;
+    uint32_t smem0;   // shared::cta address of this CTA's dynamic smem; peers' come from mapa per store (no register table)
+    PNP_D void init(const unsigned char* smem) { smem0 = (uint32_t)__cvta_generic_to_shared(smem); }
     PNP_D void st(int rank, int off, cf32 v, int bar) const {
-        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
-                         base[rank] + (uint32_t)off),
-                     "f"(v.re), "f"(v.im), "r"(base[rank] + (uint32_t)(kOffBar + 8 * bar))
+        const uint32_t b = mapa(smem0, rank);
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(b + (uint32_t)off),
+                     "f"(v.re), "f"(v.im), "r"(b + (uint32_t)(G::kOffBar + 8 * bar))
                      : "memory");
     }
-    PNP_D void signal(int rank, int bar) const { mbar_arrive_remote(base[rank] + (uint32_t)(kOffBar + 8 * bar)); }
 };
 
 struct ClusterParams {
@@ -104,7 +101,7 @@ struct ClusterParams {
     // k, k + nclusters, ...  A plane's z, w state is handed from one cluster to the next through global
     // memory (L2), guarded by progress[plane][rank] (chunks completed, release/acquire at gpu scope).
     int chunk, n_chunks;
-    int* progress;         // [P][8], zeroed before the launch (unused when n_chunks == 1)
+    int* progress;         // [P][CL], zeroed before the launch (unused when n_chunks == 1)
     int dbg;               // timing experiments only (results invalid): 1 = no transposes, 2 = no G staging
 };
 
@@ -116,30 +113,34 @@ __global__ void pack_mcode_k1_kernel(const uint8_t* __restrict__ mcode, uint32_t
     mpack[i] = pack_codes(mcode + (size_t)plane * kN * kN, r / kN, r % kN);
 }
 
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
-cluster256_kernel(const ClusterParams p) {
+// Cluster shape comes from the launch attribute (cudaLaunchAttributeClusterDimension = CL).
+template <int CL>
+__global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluster256_kernel(const ClusterParams p) {
+    typedef Geo<CL> G;
+    constexpr int kCluster = CL, kTileBytes = G::kTileBytes, kRows = G::kRows;
     extern __shared__ __align__(128) unsigned char smem[];
-    Ctx c;
+    Ctx<CL> c;
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x;
     c.smem = smem;
     const int cluster_id = blockIdx.x / kCluster;
     const int nclusters = gridDim.x / kCluster;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(smem + kOffBar);
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t bar0 = smem0 + G::kOffBar;
     const uint32_t bFull1 = bar0 + 8 * BAR_FULL1, bFull2 = bar0 + 8 * BAR_FULL2, bG = bar0 + 8 * BAR_GFULL;
     const uint32_t bFree1 = bar0 + 8 * BAR_FREE1, bFree2 = bar0 + 8 * BAR_FREE2;
 
     if (threadIdx.x < 256)
-        fill_tw(reinterpret_cast<cf32*>(smem + kOffTW), reinterpret_cast<const cf32*>(g_tw_f32), threadIdx.x);
+        fill_tw(reinterpret_cast<cf32*>(smem + G::kOffTW), reinterpret_cast<const cf32*>(g_tw_f32), threadIdx.x);
     if (threadIdx.x == 0) {
         mbar_init(bFull1, 1); mbar_init(bFull2, 1); mbar_init(bG, 1);
         mbar_init(bFree1, kCluster);                        // one arrival per CTA
-        mbar_init(bFree2, kCluster * (kThreads / 32));      // one arrival per warp of every CTA
+        mbar_init(bFree2, kCluster * G::kWarps);      // one arrival per warp of every CTA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_arm_tx(bFull1, kTileBytes); mbar_arm_tx(bFull2, kTileBytes); mbar_arm_tx(bG, kTileBytes);
     }
-    RemoteAsync R;
+    RemoteAsync<CL> R;
     R.init(smem);
     __syncthreads();
     cluster_sync_all();   // all CTAs resident, all barriers initialised, before any DSMEM traffic
@@ -171,7 +172,7 @@ cluster256_kernel(const ClusterParams p) {
         if (chunk > 0) {   // rows of this rank were written by the same rank of another cluster
             if (threadIdx.x == 0) {
                 uint32_t spins = 0;
-                while (ld_acquire_gpu(p.progress + plane * kCluster + c.rank) < chunk)
+                while (ld_acquire_gpu(p.progress + plane * 16 + c.rank) < chunk)
                     if (++spins > (1u << 26)) __trap();
             }
             __syncthreads();
@@ -179,17 +180,18 @@ cluster256_kernel(const ClusterParams p) {
         const unsigned char* Gplane = reinterpret_cast<const unsigned char*>(p.G + plane * nn);
         const uint32_t* mpack = p.mpack + (p.mcode_batched ? (size_t)plane * 16 * kN : 0);
 
-        // Stage G for the coming blend into this warp's 4 KB slice of B1 (G rows 16w .. 16w+15), which
-        // only this warp used as FFT scratch.  Lanes 0..15 issue one 256 B bulk copy each.
+        // Stage G for the coming blend into this warp's 4 KB slice of B1 (two image rows = 512 / R staged G
+        // rows), which only this warp used as FFT scratch.  One lane issues one 8 R byte bulk copy per row.
         auto prefetch_g = [&]() {
             if (p.dbg & 2) return;
             __syncwarp();
             fence_proxy_async();   // generic-proxy accesses of the slice are ordered before the async writes
-            if (lane < 16) {
-                const int kr = 16 * warp + lane;
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + g_stage_dst_off(kr));
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                             "l"(Gplane + g_stage_src_off(c.rank, kr)), "r"(kRows * 8), "r"(bG)
+            constexpr int kRowsPerWarp = 512 / kRows;
+            if (lane < kRowsPerWarp) {
+                const int kr = kRowsPerWarp * warp + lane;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem0 + (uint32_t)g_stage_dst_off<CL>(kr)),
+                             "l"(Gplane + g_stage_src_off<CL>(c.rank, kr)), "r"(kRows * 8), "r"(bG)
                              : "memory");
             }
         };
@@ -211,7 +213,7 @@ cluster256_kernel(const ClusterParams p) {
 
         for (int it = it0; it < it1; ++it) {
             // ---- column phase: col FFT -> residual blend -> col IFFT -> transpose back (DSMEM)
-            const uint32_t codes = mpack[warp * kN + kRows * c.rank + lane];
+            const uint32_t codes = mpack[c.ct() * kN + kRows * c.rank + c.cc()];
             if (!(p.dbg & 1)) {
                 mbar_wait(bFull2, nFull2 & 1); ++nFull2;
                 if (threadIdx.x == 0) mbar_arm_tx(bFull2, kTileBytes);
@@ -228,14 +230,14 @@ cluster256_kernel(const ClusterParams p) {
             col_blend(c, s, c.B1(), codes, cf1, cf2);
             fence_proxy_async();
             __syncthreads();                               // everyone is done with G (B1) and the scratch reads
-            if (threadIdx.x < kCluster && !(p.dbg & 1)) R.signal(threadIdx.x, BAR_FREE1);
+            if (threadIdx.x < kCluster && !(p.dbg & 1)) mbar_arrive_remote(mapa(bFree1, threadIdx.x));
             col_step1_write<true>(c, s);
             __syncthreads();
             col_read_step2<true>(c, s);
             fence_proxy_async();
             __syncwarp();
             if (!(p.dbg & 1)) {
-                if (lane < kCluster) R.signal(lane, BAR_FREE2);   // this warp no longer reads B2
+                if (lane < kCluster) mbar_arrive_remote(mapa(bFree2, lane));   // this warp no longer reads B2
                 mbar_wait(bFree1, nFree1 & 1); ++nFree1;
                 col_store_remote(c, s, R);
             }
@@ -266,7 +268,7 @@ cluster256_kernel(const ClusterParams p) {
             __syncthreads();
             if (threadIdx.x == 0) {
                 __threadfence();
-                st_release_gpu(p.progress + plane * kCluster + c.rank, chunk + 1);
+                st_release_gpu(p.progress + plane * 16 + c.rank, chunk + 1);
             }
         }
     }

@@ -1,16 +1,20 @@
 // cluster256_core.cuh — K1: per-thread phases of the cluster-resident 256x256 ADMM solve.
 //
-// One 8-CTA thread-block cluster owns one packed plane (two real images a + i b) for the whole
-// solve.  CTA `rank` owns image rows [32 rank, 32 rank + 32) in the ROW phases and frequency
-// columns [32 rank, 32 rank + 32) in the COLUMN phases; the two all-to-all transposes per iteration
-// are remote shared-memory stores (DSMEM).  512 threads x 16 points = the CTA's whole 32x256 tile
-// lives in registers while it is transformed, so the tile buffers double as the exchange scratch.
+// One thread-block cluster of CL CTAs (CL = 8 or 16) owns one packed plane (two real images
+// a + i b) for the whole solve.  With R = 256 / CL, CTA `rank` owns image rows [R rank, R rank + R)
+// in the ROW phases and frequency columns [R rank, R rank + R) in the COLUMN phases; the two
+// all-to-all transposes per iteration are remote shared-memory stores (DSMEM).  16 R threads x 16
+// points = the CTA's whole R x 256 tile lives in registers while it is transformed, so the tile
+// buffers double as the exchange scratch.
+//   CL = 8 : R = 32, 512 threads, 194 KB smem, one CTA per SM   (15 clusters co-resident on B200)
+//   CL = 16: R = 16, 256 threads,  98 KB smem, two CTAs per SM  (14 clusters co-resident): the two
+//            CTAs of an SM belong to different planes, so one computes while the other transposes.
 //
 //   shared memory per CTA (fp32):
-//     Zs [32][256] float2   z of image a / b interleaved                         64 KB
-//     B1 [32][256] float2   row-layout tile   (written remotely by the column phase) 64 KB
-//     B2 [256][32] float2   column-layout tile (written remotely by the row phase)   64 KB
-//     TW [16][16]  float2   W_256^(k1*n2)                                           2 KB
+//     Zs [R][256] float2   z of image a / b interleaved
+//     B1 [R][256] float2   row-layout tile    (written remotely by the column phase)
+//     B2 [256][R] float2   column-layout tile (written remotely by the row phase)
+//     TW [16][16] float2   W_256^(k1*n2)                                           2 KB
 //   B1 is idle during the column phase until the peers' transposes land, so the data term G of
 //   the coming blend is staged there (bulk async copy issued at the end of the row phase).
 //   registers per thread: 16 complex points + the dual w of its 16 pixels x 2 images (32 floats,
@@ -21,8 +25,9 @@
 //   exchange (16x16 transpose inside the group through shared memory)
 //   step 2: 16-point DFT over n2 -> X[t + 16 k2]          (same "t + 16 j" layout as the input)
 // Row phases: group = half-warp (exchange guarded by __syncwarp, XOR-swizzled slots).
-// Column phases: lane = column, warp = t (exchange guarded by __syncthreads, conflict-free
-// because lanes are always contiguous), so every remote store is a 256 B contiguous segment.
+// Column phases: thread = (t = tid / R, c = tid % R), lanes run along columns (exchange guarded by
+// __syncthreads, conflict-free because lanes are always contiguous), so every remote store is a
+// contiguous 8 R byte segment.
 //
 // All functions are HOST+DEVICE: tests/host_emu/ runs the same code for 8 x 512 emulated threads.
 #pragma once
@@ -35,41 +40,51 @@ namespace k1 {
 typedef cx<float> cf32;
 
 constexpr int kN = 256;
-constexpr int kCluster = 8;
-constexpr int kRows = 32;          // rows (columns) per CTA
-constexpr int kThreads = 512;
-
-// shared-memory byte offsets
-constexpr int kOffZs = 0;
-constexpr int kOffB1 = kOffZs + kRows * kN * 8;
-constexpr int kOffB2 = kOffB1 + kRows * kN * 8;
-constexpr int kOffTW = kOffB2 + kN * kRows * 8;
-constexpr int kOffBar = kOffTW + 256 * 8;        // 5 mbarriers (device kernel only)
-constexpr int kSmemBytes = kOffBar + 64;
-constexpr int kTileBytes = kRows * kN * 8;       // 64 KB: one tile, one transpose, one G stage
 
 // mbarrier slots
 enum { BAR_FULL1 = 0, BAR_FULL2 = 1, BAR_GFULL = 2, BAR_FREE1 = 3, BAR_FREE2 = 4 };
+
+// Geometry of a cluster of CL CTAs.
+template <int CL>
+struct Geo {
+    static constexpr int kCluster = CL;
+    static constexpr int kRows = kN / CL;              // rows (columns) per CTA
+    static constexpr int kThreads = 16 * kRows;
+    static constexpr int kWarps = kThreads / 32;
+    static constexpr int kTileBytes = kRows * kN * 8;  // one tile = one transpose = one G stage
+    static constexpr int kOffZs = 0;
+    static constexpr int kOffB1 = kTileBytes;
+    static constexpr int kOffB2 = 2 * kTileBytes;
+    static constexpr int kOffTW = 3 * kTileBytes;
+    static constexpr int kOffBar = kOffTW + 256 * 8;   // 5 mbarriers (device kernel only)
+    static constexpr int kSmemBytes = kOffBar + 64;
+    static constexpr int kCtasPerSm = (CL == 16) ? 2 : 1;
+    // element k = t + 16 j (t < 16) of a 256-line lives in CTA k / kRows at local index k % kRows
+    static PNP_HD int dest(int j) { return kRows == 32 ? (j >> 1) : j; }
+    static PNP_HD int local(int t, int j) { return kRows == 32 ? t + 16 * (j & 1) : t; }
+};
 
 struct ThreadState {
     cf32 a[16];      // working points
     float w[32];     // dual variable: w[2j] image a, w[2j+1] image b, pixel column t + 16 j
 };
 
+template <int CL>
 struct Ctx {
+    typedef Geo<CL> G;
     int rank;                 // CTA rank in the cluster
     int tid;                  // thread index in the CTA
     unsigned char* smem;      // this CTA's dynamic shared memory
-    PNP_HD cf32* Zs() const { return reinterpret_cast<cf32*>(smem + kOffZs); }
-    PNP_HD cf32* B1() const { return reinterpret_cast<cf32*>(smem + kOffB1); }
-    PNP_HD cf32* B2() const { return reinterpret_cast<cf32*>(smem + kOffB2); }
-    PNP_HD const cf32* TW() const { return reinterpret_cast<const cf32*>(smem + kOffTW); }
+    PNP_HD cf32* Zs() const { return reinterpret_cast<cf32*>(smem + G::kOffZs); }
+    PNP_HD cf32* B1() const { return reinterpret_cast<cf32*>(smem + G::kOffB1); }
+    PNP_HD cf32* B2() const { return reinterpret_cast<cf32*>(smem + G::kOffB2); }
+    PNP_HD const cf32* TW() const { return reinterpret_cast<const cf32*>(smem + G::kOffTW); }
     // row-phase mapping: half-warp = one row
     PNP_HD int row() const { return (tid >> 5) * 2 + ((tid >> 4) & 1); }
     PNP_HD int rt() const { return tid & 15; }
-    // column-phase mapping: warp = t, lane = column
-    PNP_HD int ct() const { return tid >> 5; }
-    PNP_HD int cc() const { return tid & 31; }
+    // column-phase mapping: t = tid / R, column = tid % R
+    PNP_HD int ct() const { return tid / G::kRows; }
+    PNP_HD int cc() const { return tid % G::kRows; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -127,7 +142,7 @@ template <bool INV>
 PNP_HD void fft256_step2(cf32 (&c)[16], cf32 (&out)[16]) { fft16<INV>(c, out); }
 
 // ---------------------------------------------------------------------------------------------
-// ROW phases (thread = (row, t); holds columns n = t + 16 j of image row 32*rank + row)
+// ROW phases (thread = (row, t); holds columns n = t + 16 j of image row R*rank + row)
 // ---------------------------------------------------------------------------------------------
 struct PlaneIO {            // global-memory planes of the two images of a packed plane
     const float* z_in_a; const float* w_in_a; const float* z_in_b; const float* w_in_b;   // b may be null
@@ -136,9 +151,10 @@ struct PlaneIO {            // global-memory planes of the two images of a packe
 };
 
 // prologue: global z, w -> Zs / registers; a = z - w
-PNP_HD void row_load_state(const Ctx& c, ThreadState& s, const PlaneIO& io) {
+template <int CL>
+PNP_HD void row_load_state(const Ctx<CL>& c, ThreadState& s, const PlaneIO& io) {
     const int row = c.row(), t = c.rt();
-    const int g0 = (kRows * c.rank + row) * kN;
+    const int g0 = (Geo<CL>::kRows * c.rank + row) * kN;
     cf32* Zs = c.Zs() + row * kN;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -152,15 +168,16 @@ PNP_HD void row_load_state(const Ctx& c, ThreadState& s, const PlaneIO& io) {
     }
 }
 
-PNP_HD void row_load(const Ctx& c, ThreadState& s) {
+template <int CL>
+PNP_HD void row_load(const Ctx<CL>& c, ThreadState& s) {
     const cf32* src = c.B1() + c.row() * kN + c.rt();
 #pragma unroll
     for (int j = 0; j < 16; ++j) s.a[j] = src[16 * j];
 }
 
 // step 1 + scatter into the exchange scratch (= this row's slot of B1), XOR swizzle
-template <bool INV>
-PNP_HD void row_step1_write(const Ctx& c, ThreadState& s) {
+template <bool INV, int CL>
+PNP_HD void row_step1_write(const Ctx<CL>& c, ThreadState& s) {
     const int t = c.rt();
     fft256_step1<INV>(s.a, t, c.TW());
     cf32* sc = c.B1() + c.row() * kN;
@@ -168,8 +185,8 @@ PNP_HD void row_step1_write(const Ctx& c, ThreadState& s) {
     for (int k1 = 0; k1 < 16; ++k1) sc[k1 * 16 + (t ^ k1)] = s.a[k1];
 }
 
-template <bool INV>
-PNP_HD void row_read_step2(const Ctx& c, ThreadState& s) {
+template <bool INV, int CL>
+PNP_HD void row_read_step2(const Ctx<CL>& c, ThreadState& s) {
     const int t = c.rt();
     const cf32* sc = c.B1() + c.row() * kN + t * 16;
     cf32 v[16];
@@ -181,11 +198,11 @@ PNP_HD void row_read_step2(const Ctx& c, ThreadState& s) {
 // after the inverse row FFT (a = r, the residual correction): x = |v + r|; prox; dual; next a = z - w.
 // MODE: PM_L1 / PM_CNC / PM_GENERAL, or PROX_NONE (x-update only: emit x and x + w, state untouched).
 // `last`: end of this cluster's run on the plane -> z, w go to global memory (x too if want_x).
-template <int MODE>
-PNP_HD void row_prox(const Ctx& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last, bool want_x,
+template <int MODE, int CL>
+PNP_HD void row_prox(const Ctx<CL>& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last, bool want_x,
                      const PlaneIO& io) {
     const int row = c.row(), t = c.rt();
-    const int g0 = (kRows * c.rank + row) * kN;
+    const int g0 = (Geo<CL>::kRows * c.rank + row) * kN;
     cf32* Zs = c.Zs() + row * kN;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -221,7 +238,8 @@ PNP_HD void row_prox(const Ctx& c, ThreadState& s, const ProxParams<float>& p, b
     }
 }
 
-PNP_HD void row_prox_dispatch(int mode, const Ctx& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last,
+template <int CL>
+PNP_HD void row_prox_dispatch(int mode, const Ctx<CL>& c, ThreadState& s, const ProxParams<float>& p, bool has_b, bool last,
                               bool want_x, const PlaneIO& io) {
     switch (mode) {
         case PM_L1: row_prox<PM_L1>(c, s, p, has_b, last, want_x, io); break;
@@ -231,62 +249,69 @@ PNP_HD void row_prox_dispatch(int mode, const Ctx& c, ThreadState& s, const Prox
     }
 }
 
-// forward row FFT output X[row][k = t + 16 j] -> CTA (k / 32), B2[32*rank + row][k % 32]
-template <class Remote>
-PNP_HD void row_store_remote(const Ctx& c, const ThreadState& s, const Remote& R) {
+// forward row FFT output X[row][k = t + 16 j] -> CTA (k / R), B2[R*rank + row][k % R]
+template <int CL, class Remote>
+PNP_HD void row_store_remote(const Ctx<CL>& c, const ThreadState& s, const Remote& R) {
+    typedef Geo<CL> G;
     const int t = c.rt();
-    const int grow = kRows * c.rank + c.row();
+    const int grow = G::kRows * c.rank + c.row();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const int off = kOffB2 + (grow * kRows + t + 16 * (j & 1)) * 8;
-        R.st(j >> 1, off, s.a[j], BAR_FULL2);
+        const int off = G::kOffB2 + (grow * G::kRows + G::local(t, j)) * 8;
+        R.st(G::dest(j), off, s.a[j], BAR_FULL2);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// COLUMN phases (thread = (t = warp, c = lane); holds rows r = t + 16 j of column 32*rank + c)
+// COLUMN phases (thread = (t, c); holds rows r = t + 16 j of column R*rank + c)
 // ---------------------------------------------------------------------------------------------
-PNP_HD void col_load(const Ctx& c, ThreadState& s) {
-    const cf32* src = c.B2() + c.ct() * kRows + c.cc();
+template <int CL>
+PNP_HD void col_load(const Ctx<CL>& c, ThreadState& s) {
+    constexpr int R = Geo<CL>::kRows;
+    const cf32* src = c.B2() + c.ct() * R + c.cc();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) s.a[j] = src[16 * j * kRows];
+    for (int j = 0; j < 16; ++j) s.a[j] = src[16 * j * R];
 }
 
-template <bool INV>
-PNP_HD void col_step1_write(const Ctx& c, ThreadState& s) {
+template <bool INV, int CL>
+PNP_HD void col_step1_write(const Ctx<CL>& c, ThreadState& s) {
+    constexpr int R = Geo<CL>::kRows;
     const int t = c.ct();
     fft256_step1<INV>(s.a, t, c.TW());
-    cf32* sc = c.B2() + t * kRows + c.cc();
+    cf32* sc = c.B2() + t * R + c.cc();
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) sc[k1 * 16 * kRows] = s.a[k1];
+    for (int k1 = 0; k1 < 16; ++k1) sc[k1 * 16 * R] = s.a[k1];
 }
 
-template <bool INV>
-PNP_HD void col_read_step2(const Ctx& c, ThreadState& s) {
-    const cf32* sc = c.B2() + (c.ct() * 16) * kRows + c.cc();
+template <bool INV, int CL>
+PNP_HD void col_read_step2(const Ctx<CL>& c, ThreadState& s) {
+    constexpr int R = Geo<CL>::kRows;
+    const cf32* sc = c.B2() + (c.ct() * 16) * R + c.cc();
     cf32 v[16];
 #pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) v[n2] = sc[n2 * kRows];
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = sc[n2 * R];
     fft256_step2<INV>(v, s.a);
 }
 
 // data-consistency residual on the packed spectrum: a = G - cf[code] * a      (see streaming.cuh)
-// Gs: this CTA's G tile staged in shared memory as [kr = 256][c = 32] (the B1 buffer);
+// Gs: this CTA's G tile staged in shared memory as [kr = 256][c = R] (the B1 buffer);
 // codes: 2 bits per j (mcode of bin (t + 16 j, kc)), packed by pack_mcode_k1.
-PNP_HD void col_blend(const Ctx& c, ThreadState& s, const cf32* Gs, uint32_t codes, float cf1, float cf2) {
-    const cf32* g = Gs + c.ct() * kRows + c.cc();
+template <int CL>
+PNP_HD void col_blend(const Ctx<CL>& c, ThreadState& s, const cf32* Gs, uint32_t codes, float cf1, float cf2) {
+    constexpr int R = Geo<CL>::kRows;
+    const cf32* g = Gs + c.ct() * R + c.cc();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const cf32 gg = g[16 * j * kRows];
+        const cf32 gg = g[16 * j * R];
         const uint32_t code = (codes >> (2 * j)) & 3u;
         const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
         s.a[j] = mk<float>(gg.re - cf * s.a[j].re, gg.im - cf * s.a[j].im);
     }
 }
 
-// global G[kr][kc] rows -> staged tile [kr][32]: byte offsets of row kr for CTA `rank`
-PNP_HD int g_stage_src_off(int rank, int kr) { return (kr * kN + kRows * rank) * 8; }
-PNP_HD int g_stage_dst_off(int kr) { return kOffB1 + kr * kRows * 8; }
+// global G[kr][kc] rows -> staged tile [kr][R]: byte offsets of row kr for CTA `rank`
+template <int CL> PNP_HD int g_stage_src_off(int rank, int kr) { return (kr * kN + Geo<CL>::kRows * rank) * 8; }
+template <int CL> PNP_HD int g_stage_dst_off(int kr) { return Geo<CL>::kOffB1 + kr * Geo<CL>::kRows * 8; }
 
 // packed mask codes: word (t, kc) holds mcode[(t + 16 j) * 256 + kc] in bits 2j, 2j+1
 PNP_HD uint32_t pack_codes(const uint8_t* mcode, int t, int kc) {
@@ -295,15 +320,16 @@ PNP_HD uint32_t pack_codes(const uint8_t* mcode, int t, int kc) {
     return v;
 }
 
-// inverse column FFT output at image row r = t + 16 j, column kc -> CTA (r / 32), B1[r % 32][kc]
-template <class Remote>
-PNP_HD void col_store_remote(const Ctx& c, const ThreadState& s, const Remote& R) {
+// inverse column FFT output at image row r = t + 16 j, column kc -> CTA (r / R), B1[r % R][kc]
+template <int CL, class Remote>
+PNP_HD void col_store_remote(const Ctx<CL>& c, const ThreadState& s, const Remote& R) {
+    typedef Geo<CL> G;
     const int t = c.ct();
-    const int kc = kRows * c.rank + c.cc();
+    const int kc = G::kRows * c.rank + c.cc();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const int off = kOffB1 + ((t + 16 * (j & 1)) * kN + kc) * 8;
-        R.st(j >> 1, off, s.a[j], BAR_FULL1);
+        const int off = G::kOffB1 + (G::local(t, j) * kN + kc) * 8;
+        R.st(G::dest(j), off, s.a[j], BAR_FULL1);
     }
 }
 

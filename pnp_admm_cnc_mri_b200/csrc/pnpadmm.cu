@@ -49,7 +49,9 @@ constexpr int kMaxSmemOptin = 227 * 1024;
 struct DeviceState {
     bool ready = false;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
-    int max_clusters_256 = 0;
+    int max_clusters_256 = 0;     // best of the two geometries below
+    int max_cl8 = 0, max_cl16 = 0;  // co-resident clusters of the 8-CTA / 16-CTA variants of K1
+    int k1_cluster = 8;           // geometry used by default
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
@@ -100,6 +102,37 @@ cudaError_t set_stream_attrs() {
     return cudaSuccess;
 }
 
+template <int CL>
+int probe_clusters(int sm_count) {
+    typedef k1::Geo<CL> G;
+    if (cudaFuncSetAttribute(k1::cluster256_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    if (CL > 8 && cudaFuncSetAttribute(k1::cluster256_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(CL * sm_count);
+    cfg.blockDim = dim3(G::kThreads);
+    cfg.dynamicSmemBytes = G::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, k1::cluster256_kernel<CL>, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return ncl;
+}
+
 int ensure_device(DeviceState** out) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -127,24 +160,13 @@ int ensure_device(DeviceState** out) {
         CUDA_TRY(cudaMemcpyToSymbol(g_tw_f64, td.data(), sizeof(double2) * kTwMax));
         CUDA_TRY(set_stream_attrs<float>());
         CUDA_TRY(set_stream_attrs<double>());
-        CUDA_TRY(cudaFuncSetAttribute(k1::cluster256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1::kSmemBytes));
-        // how many 8-CTA clusters of K1 can be co-resident
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(k1::kCluster * d.sm_count);
-        cfg.blockDim = dim3(k1::kThreads);
-        cfg.dynamicSmemBytes = k1::kSmemBytes;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = k1::kCluster;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        int ncl = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k1::cluster256_kernel, &cfg);
-        if (e != cudaSuccess) { ncl = 0; (void)cudaGetLastError(); }
-        d.max_clusters_256 = ncl;
+        d.max_cl8 = probe_clusters<8>(d.sm_count);
+        d.max_cl16 = probe_clusters<16>(d.sm_count);
+        d.k1_cluster = 8;
+        if (const char* e = getenv("PNPADMM_K1_CLUSTER")) {
+            if (atoi(e) == 16 && d.max_cl16 > 0) d.k1_cluster = 16;
+        }
+        d.max_clusters_256 = d.k1_cluster == 16 ? d.max_cl16 : d.max_cl8;
         d.ready = true;
     }
     *out = &d;
@@ -175,7 +197,7 @@ size_t ws_bytes_impl(int B, int N, size_t elt, int mask_batched) {
     s += align_up(P * nn * 2 * elt);         // G
     s += align_up((mask_batched ? P : 1) * nn);
     s += align_up((mask_batched ? P : 1) * nn / 4);   // packed codes (2 bits per bin, 32-bit words)
-    s += align_up(P * 8 * sizeof(int));               // progress counters
+    s += align_up(P * 16 * sizeof(int));              // progress counters [P][<=16 ranks]
     return s;
 }
 
@@ -338,30 +360,36 @@ void plan_chunks(int P, int iters, int max_clusters, int* chunk, int* n_chunks) 
     }
 }
 
-int launch_cluster(k1::ClusterParams& cp, const DeviceState* d, cudaStream_t st) {
-    plan_chunks(cp.P, cp.iters, d->max_clusters_256, &cp.chunk, &cp.n_chunks);
+template <int CL>
+int launch_cluster_t(k1::ClusterParams& cp, int max_clusters, cudaStream_t st) {
+    typedef k1::Geo<CL> G;
+    plan_chunks(cp.P, cp.iters, max_clusters, &cp.chunk, &cp.n_chunks);
     if (const char* e = getenv("PNPADMM_K1_CHUNKS")) {   // experiments: force the chunk count
         const int n = atoi(e);
         if (n >= 1 && n <= cp.iters) { cp.chunk = (cp.iters + n - 1) / n; cp.n_chunks = (cp.iters + cp.chunk - 1) / cp.chunk; }
     }
-    if (cp.n_chunks > 1) CUDA_TRY(cudaMemsetAsync(cp.progress, 0, sizeof(int) * cp.P * k1::kCluster, st));
+    if (cp.n_chunks > 1) CUDA_TRY(cudaMemsetAsync(cp.progress, 0, sizeof(int) * cp.P * 16, st));
     const long ntasks = (long)cp.P * cp.n_chunks;
-    int ncl = ntasks < d->max_clusters_256 ? (int)ntasks : d->max_clusters_256;
+    int ncl = ntasks < max_clusters ? (int)ntasks : max_clusters;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(ncl * k1::kCluster);
-    cfg.blockDim = dim3(k1::kThreads);
-    cfg.dynamicSmemBytes = k1::kSmemBytes;
+    cfg.gridDim = dim3(ncl * CL);
+    cfg.blockDim = dim3(G::kThreads);
+    cfg.dynamicSmemBytes = G::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = k1::kCluster;
+    attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_kernel, (const k1::ClusterParams)cp));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_kernel<CL>, (const k1::ClusterParams)cp));
     return PNPADMM_OK;
+}
+
+int launch_cluster(k1::ClusterParams& cp, const DeviceState* d, cudaStream_t st) {
+    return d->k1_cluster == 16 ? launch_cluster_t<16>(cp, d->max_cl16, st) : launch_cluster_t<8>(cp, d->max_cl8, st);
 }
 
 template <typename T> struct ClusterDispatch {

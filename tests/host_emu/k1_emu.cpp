@@ -1,8 +1,8 @@
 // CPU emulation of the K1 cluster kernel (TEST INFRASTRUCTURE).
 // Runs the SAME per-thread phase code as cluster256.cuh (cluster256_core.cuh is host+device) for
-// 8 emulated CTAs x 512 threads, with every barrier turned into a phase boundary.  It validates the
-// FFT decomposition, swizzles, thread<->pixel mappings and DSMEM offsets without a GPU; it cannot
-// detect races (compute-sanitizer on the GPU box does that).
+// CL emulated CTAs x 16*256/CL threads (CL = 8 or 16), with every barrier turned into a phase boundary.
+// It validates the FFT decomposition, swizzles, thread<->pixel mappings and DSMEM offsets without a
+// GPU; it cannot detect races (compute-sanitizer on the GPU box does that).
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -17,34 +17,36 @@ struct RemoteHost {
     unsigned char** all;
     void st(int rank, int off, cf32 v, int /*bar*/) const { *reinterpret_cast<cf32*>(all[rank] + off) = v; }
 };
-}  // namespace
 
-extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float* z, float* w, float* xpw,
-                          const float* G_, const uint8_t* mcode_, int mcode_batched, float /*cf0*/, float cf1, float cf2,
-                          int B, int P, int solo, int iters, int prox, float thr_l1, float inv_b, float one_m_alpha,
-                          float alpha, float coef, float thr_cnc) {
-    std::vector<cf32> master(4096);
+std::vector<cf32> master_table() {
+    std::vector<cf32> m(4096);
     for (int i = 0; i < 4096; ++i) {
         const double a = -2.0 * M_PI * i / 4096.0;
-        master[i] = mk<float>((float)std::cos(a), (float)std::sin(a));
+        m[i] = mk<float>((float)std::cos(a), (float)std::sin(a));
     }
-    std::vector<std::vector<unsigned char>> smem(kCluster, std::vector<unsigned char>(kSmemBytes, 0));
-    unsigned char* all[kCluster];
-    for (int r = 0; r < kCluster; ++r) all[r] = smem[r].data();
-    RemoteHost R{all};
-    std::vector<ThreadState> st((size_t)kCluster * kThreads);
-    ProxParams<float> pp;
-    pp.prox = prox; pp.general = 0; pp.thr_l1 = thr_l1; pp.inv_b = inv_b; pp.one_m_alpha = one_m_alpha;
-    pp.alpha = alpha; pp.coef = coef; pp.thr_cnc = thr_cnc;
+    return m;
+}
 
-    for (int r = 0; r < kCluster; ++r)
-        for (int i = 0; i < 256; ++i) fill_tw(reinterpret_cast<cf32*>(all[r] + kOffTW), master.data(), i);
+template <int CL>
+int emulate(const float* z_in, const float* w_in, float* x, float* z, float* w, float* xpw, const float* G_,
+            const uint8_t* mcode_, int mcode_batched, float cf1, float cf2, int B, int P, int solo, int iters,
+            const ProxParams<float>& pp) {
+    typedef Geo<CL> G;
+    std::vector<cf32> master = master_table();
+    std::vector<std::vector<unsigned char>> smem(CL, std::vector<unsigned char>(G::kSmemBytes, 0));
+    unsigned char* all[CL];
+    for (int r = 0; r < CL; ++r) all[r] = smem[r].data();
+    RemoteHost R{all};
+    std::vector<ThreadState> st((size_t)CL * G::kThreads);
+    for (int r = 0; r < CL; ++r)
+        for (int i = 0; i < 256; ++i) fill_tw(reinterpret_cast<cf32*>(all[r] + G::kOffTW), master.data(), i);
+    const int mode = pp.prox == PROX_NONE ? PROX_NONE : prox_mode(pp);
 
 #define FOR_ALL(body)                                                   \
-    for (int r = 0; r < kCluster; ++r)                                  \
-        for (int t = 0; t < kThreads; ++t) {                            \
-            Ctx c; c.rank = r; c.tid = t; c.smem = all[r];              \
-            ThreadState& s = st[(size_t)r * kThreads + t];              \
+    for (int r = 0; r < CL; ++r)                                        \
+        for (int t = 0; t < G::kThreads; ++t) {                         \
+            Ctx<CL> c; c.rank = r; c.tid = t; c.smem = all[r];          \
+            ThreadState& s = st[(size_t)r * G::kThreads + t];           \
             body;                                                       \
         }
 
@@ -59,15 +61,14 @@ extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float*
         io.xpw_a = xpw ? xpw + ia * nn : nullptr;
         io.x_b = io.x_a + nn; io.z_b = io.z_a ? io.z_a + nn : nullptr; io.w_b = io.w_a ? io.w_a + nn : nullptr;
         io.xpw_b = io.xpw_a ? io.xpw_a + nn : nullptr;
-        const cf32* G = reinterpret_cast<const cf32*>(G_) + plane * nn;
+        const cf32* Gp = reinterpret_cast<const cf32*>(G_) + plane * nn;
         const uint8_t* mcode = mcode_ + (mcode_batched ? plane * nn : 0);
-
         // the bulk-async G prefetch into B1 of the device kernel, as a plain copy
         auto stage_g = [&]() {
-            for (int r = 0; r < kCluster; ++r)
+            for (int r = 0; r < CL; ++r)
                 for (int kr = 0; kr < kN; ++kr)
-                    std::memcpy(all[r] + g_stage_dst_off(kr), reinterpret_cast<const unsigned char*>(G) + g_stage_src_off(r, kr),
-                                kRows * 8);
+                    std::memcpy(all[r] + g_stage_dst_off<CL>(kr),
+                                reinterpret_cast<const unsigned char*>(Gp) + g_stage_src_off<CL>(r, kr), G::kRows * 8);
         };
         FOR_ALL(row_load_state(c, s, io));
         FOR_ALL(row_step1_write<false>(c, s));
@@ -78,14 +79,14 @@ extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float*
             FOR_ALL(col_load(c, s));
             FOR_ALL(col_step1_write<false>(c, s));
             FOR_ALL(col_read_step2<false>(c, s);
-                    col_blend(c, s, c.B1(), pack_codes(mcode, c.ct(), kRows * c.rank + c.cc()), cf1, cf2));
+                    col_blend(c, s, c.B1(), pack_codes(mcode, c.ct(), G::kRows * c.rank + c.cc()), cf1, cf2));
             FOR_ALL(col_step1_write<true>(c, s));
             FOR_ALL(col_read_step2<true>(c, s));
             FOR_ALL(col_store_remote(c, s, R));
             const bool last = (it == iters - 1);
             FOR_ALL(row_load(c, s));
             FOR_ALL(row_step1_write<true>(c, s));
-            FOR_ALL(row_read_step2<true>(c, s); row_prox_dispatch(prox == PROX_NONE ? PROX_NONE : prox_mode(pp), c, s, pp, has_b, last, true, io));
+            FOR_ALL(row_read_step2<true>(c, s); row_prox_dispatch(mode, c, s, pp, has_b, last, true, io));
             if (!last) {
                 FOR_ALL(row_step1_write<false>(c, s));
                 FOR_ALL(row_read_step2<false>(c, s));
@@ -94,16 +95,26 @@ extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float*
             }
         }
     }
+#undef FOR_ALL
     return 0;
+}
+}  // namespace
+
+extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float* z, float* w, float* xpw,
+                          const float* G_, const uint8_t* mcode_, int mcode_batched, float /*cf0*/, float cf1, float cf2,
+                          int B, int P, int solo, int iters, int prox, float thr_l1, float inv_b, float one_m_alpha,
+                          float alpha, float coef, float thr_cnc, int cluster) {
+    ProxParams<float> pp;
+    pp.prox = prox; pp.general = 0; pp.thr_l1 = thr_l1; pp.inv_b = inv_b; pp.one_m_alpha = one_m_alpha;
+    pp.alpha = alpha; pp.coef = coef; pp.thr_cnc = thr_cnc;
+    if (cluster == 16)
+        return emulate<16>(z_in, w_in, x, z, w, xpw, G_, mcode_, mcode_batched, cf1, cf2, B, P, solo, iters, pp);
+    return emulate<8>(z_in, w_in, x, z, w, xpw, G_, mcode_, mcode_batched, cf1, cf2, B, P, solo, iters, pp);
 }
 
 // 256-point FFT of one line through the same step1 / exchange / step2 code (unit test hook)
 extern "C" void k1_fft256_line(const float* in, float* out, int inverse) {
-    std::vector<cf32> master(4096), TW(256);
-    for (int i = 0; i < 4096; ++i) {
-        const double a = -2.0 * M_PI * i / 4096.0;
-        master[i] = mk<float>((float)std::cos(a), (float)std::sin(a));
-    }
+    std::vector<cf32> master = master_table(), TW(256);
     for (int i = 0; i < 256; ++i) fill_tw(TW.data(), master.data(), i);
     cf32 a[16][16], sc[256];
     for (int t = 0; t < 16; ++t)

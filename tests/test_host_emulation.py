@@ -46,7 +46,7 @@ def prepare_np(ys, m, reo):
     return np.stack(G).astype(np.complex64), (m + mirror(m)).astype(np.uint8), [(g * c / 2) / N ** 2 for c in range(3)]
 
 
-def run_emu(emu, imgs, m, noises, prox, P):
+def run_emu(emu, imgs, m, noises, prox, P, cluster=8):
     ys = [orc.acquire(im, m.astype(np.float64), noises) for im in imgs]
     z0 = np.stack([orc.zero_filled(y) for y in ys]).astype(np.float32)
     w0 = np.zeros_like(z0)
@@ -58,7 +58,7 @@ def run_emu(emu, imgs, m, noises, prox, P):
     emu.k1_emulate(z0.ctypes.data_as(FP), w0.ctypes.data_as(FP), x.ctypes.data_as(FP), z.ctypes.data_as(FP),
                    w.ctypes.data_as(FP), None, G.ctypes.data_as(FP), mc.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), 0,
                    f(cf[0]), f(cf[1]), f(cf[2]), B, (B + 1) // 2, 0, P['iter_num'], 0 if prox == 'l1' else 1,
-                   f(reo * l), f(1 / b), f(1 - a), f(a), f(a * reo * l * b), f(a * reo * l))
+                   f(reo * l), f(1 / b), f(1 - a), f(a), f(a * reo * l * b), f(a * reo * l), cluster)
     return x, z, w
 
 
@@ -72,12 +72,13 @@ def test_fft256_line(emu):
         assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 3e-7
 
 
+@pytest.mark.parametrize('cluster', [8, 16])
 @pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
-def test_k1_emulated_solve_matches_oracle(emu, cs_inputs, prox, P):
+def test_k1_emulated_solve_matches_oracle(emu, cs_inputs, prox, P, cluster):
     idx = [4, 0, 7]                                      # odd count: last plane has an empty b slot
     imgs = [orc.preprocess_uint8(cs_inputs['images'][i]) for i in idx]
     m = cs_inputs['masks'][1]
-    x, z, w = run_emu(emu, imgs, m, cs_inputs['noises'], prox, P)
+    x, z, w = run_emu(emu, imgs, m, cs_inputs['noises'], prox, P, cluster)
     fn = orc.admm_l1 if prox == 'l1' else orc.admm_cnc
     for k, i in enumerate(idx):
         xr, zr, wr, _ = fn(imgs[k], m.astype(np.float64), cs_inputs['noises'], return_state=True, **P)
