@@ -276,7 +276,7 @@ def run_ours(args):
             'images_per_s': value / CNC['iter_num'],
             'config': {'workload': 'BASELINE config 2: ADMM-CNC 256x256, batch 64 per GPU, 30% cartesian/radial/random '
                                    'masks cycling per step, reference defaults (alpha .45, 50 it, lambda .5, reo .05, b 64)',
-                       'batch_per_gpu': B, 'iter_num': CNC['iter_num'], 'kernel': 'cluster256 (K1)',
+                       'batch_per_gpu': B, 'iter_num': CNC['iter_num'], 'kernel': 'cluster256 (K1, 16-CTA clusters, 2 CTAs/SM)',
                        'l2': 'flushed (256 MiB fill) between timed steps', 'sharding': f'batch x{world}, no collective'},
             'e2e': {'value': e2e, 'unit': 'iterations/s', 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(h_img.numel() + h_masks[0].numel() + h_noise.numel() * 4),
