@@ -44,22 +44,26 @@ PNP_D void mbar_arm_tx(uint32_t bar, uint32_t bytes) {
 PNP_D void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint
+// expires) instead of spinning through issue slots the other CTA of the SM could use.
 PNP_D bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as a launch failure, never as a hung GPU.
+// Bounded wait (~2 s of SM clock): a protocol bug must surface as a launch failure, never as a hung GPU.
 PNP_D void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
+        if ((++spins & 63u) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
 PNP_D int ld_acquire_gpu(const int* p) {
@@ -145,6 +149,11 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
     __syncthreads();
     cluster_sync_all();   // all CTAs resident, all barriers initialised, before any DSMEM traffic
 
+#ifdef PNPADMM_K1_EXPERIMENTS
+    const int dbg = p.dbg;     // timing experiments only (results invalid)
+#else
+    constexpr int dbg = 0;
+#endif
     const float cf1 = p.cf[1], cf2 = p.cf[2];
     uint32_t nFull1 = 0, nFull2 = 0, nG = 0, nFree1 = 0, nFree2 = 0;   // completed uses (phase parity)
     ThreadState s;
@@ -177,27 +186,26 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
             }
             __syncthreads();
         }
-        const unsigned char* Gplane = reinterpret_cast<const unsigned char*>(p.G + plane * nn);
+        // G arrives in tile order (prepare_kernel): this CTA's tile is one contiguous block of the plane
+        const unsigned char* Gtile = reinterpret_cast<const unsigned char*>(p.G + plane * nn) + (size_t)c.rank * kTileBytes;
         const uint32_t* mpack = p.mpack + (p.mcode_batched ? (size_t)plane * 16 * kN : 0);
 
         // Stage G for the coming blend into this warp's 4 KB slice of B1 (two image rows = 512 / R staged G
-        // rows), which only this warp used as FFT scratch.  One lane issues one 8 R byte bulk copy per row.
+        // rows), which only this warp used as FFT scratch: one 4 KB bulk copy per warp.
         auto prefetch_g = [&]() {
-            if (p.dbg & 2) return;
+            if (dbg & 2) return;
             __syncwarp();
             fence_proxy_async();   // generic-proxy accesses of the slice are ordered before the async writes
-            constexpr int kRowsPerWarp = 512 / kRows;
-            if (lane < kRowsPerWarp) {
-                const int kr = kRowsPerWarp * warp + lane;
+            if (lane == 0) {
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 smem0 + (uint32_t)g_stage_dst_off<CL>(kr)),
-                             "l"(Gplane + g_stage_src_off<CL>(c.rank, kr)), "r"(kRows * 8), "r"(bG)
+                                 smem0 + (uint32_t)(G::kOffB1 + 4096 * warp)),
+                             "l"(Gtile + 4096 * warp), "r"(4096), "r"(bG)
                              : "memory");
             }
         };
         // wait until every peer's B2 may be overwritten (signal of the previous column phase)
         auto wait_free2 = [&]() {
-            if (p.dbg & 1) return;
+            if (dbg & 1) return;
             if (nFree2 > 0) mbar_wait(bFree2, (nFree2 - 1) & 1);
             ++nFree2;
         };
@@ -209,12 +217,12 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
         row_read_step2<false>(c, s);
         prefetch_g();
         wait_free2();
-        if (!(p.dbg & 1)) row_store_remote(c, s, R);
+        if (!(dbg & 1)) row_store_remote(c, s, R);
 
         for (int it = it0; it < it1; ++it) {
             // ---- column phase: col FFT -> residual blend -> col IFFT -> transpose back (DSMEM)
             const uint32_t codes = mpack[c.ct() * kN + kRows * c.rank + c.cc()];
-            if (!(p.dbg & 1)) {
+            if (!(dbg & 1)) {
                 mbar_wait(bFull2, nFull2 & 1); ++nFull2;
                 if (threadIdx.x == 0) mbar_arm_tx(bFull2, kTileBytes);
             }
@@ -223,20 +231,20 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
             col_step1_write<false>(c, s);
             __syncthreads();
             col_read_step2<false>(c, s);
-            if (!(p.dbg & 2)) {
+            if (!(dbg & 2)) {
                 mbar_wait(bG, nG & 1); ++nG;
                 if (threadIdx.x == 0) mbar_arm_tx(bG, kTileBytes);
             }
             col_blend(c, s, c.B1(), codes, cf1, cf2);
             fence_proxy_async();
             __syncthreads();                               // everyone is done with G (B1) and the scratch reads
-            if (threadIdx.x < kCluster && !(p.dbg & 1)) mbar_arrive_remote(mapa(bFree1, threadIdx.x));
+            if (threadIdx.x < kCluster && !(dbg & 1)) mbar_arrive_remote(mapa(bFree1, threadIdx.x));
             col_step1_write<true>(c, s);
             __syncthreads();
             col_read_step2<true>(c, s);
             fence_proxy_async();
             __syncwarp();
-            if (!(p.dbg & 1)) {
+            if (!(dbg & 1)) {
                 if (lane < kCluster) mbar_arrive_remote(mapa(bFree2, lane));   // this warp no longer reads B2
                 mbar_wait(bFree1, nFree1 & 1); ++nFree1;
                 col_store_remote(c, s, R);
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
 
             // ---- row phase: row IFFT -> |v + r| -> prox -> dual -> row FFT -> transpose (DSMEM)
             const bool last = (it == it1 - 1);
-            if (!(p.dbg & 1)) {
+            if (!(dbg & 1)) {
                 mbar_wait(bFull1, nFull1 & 1); ++nFull1;
                 if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
             }
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
                 row_read_step2<false>(c, s);
                 prefetch_g();
                 wait_free2();
-                if (!(p.dbg & 1)) row_store_remote(c, s, R);
+                if (!(dbg & 1)) row_store_remote(c, s, R);
             }
         }
         if (!final_chunk) {   // publish this rank's rows of z, w for the cluster that continues the plane

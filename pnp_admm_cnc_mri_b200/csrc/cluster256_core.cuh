@@ -312,6 +312,9 @@ PNP_HD void col_blend(const Ctx<CL>& c, ThreadState& s, const cf32* Gs, uint32_t
 // global G[kr][kc] rows -> staged tile [kr][R]: byte offsets of row kr for CTA `rank`
 template <int CL> PNP_HD int g_stage_src_off(int rank, int kr) { return (kr * kN + Geo<CL>::kRows * rank) * 8; }
 template <int CL> PNP_HD int g_stage_dst_off(int kr) { return Geo<CL>::kOffB1 + kr * Geo<CL>::kRows * 8; }
+// K1-tiled copy of G written by prepare: [plane][rank][kr][c], kc = R rank + c, so the tile a CTA stages is
+// one contiguous kTileBytes block and a warp's slice of it one contiguous 4 KB piece (element offset in the plane).
+PNP_HD int g_tiled_elem(int R, int kr, int kc) { return (kc / R) * (kN * R) + kr * R + (kc % R); }
 
 // packed mask codes: word (t, kc) holds mcode[(t + 16 j) * 256 + kc] in bits 2j, 2j+1
 PNP_HD uint32_t pack_codes(const uint8_t* mcode, int t, int kc) {

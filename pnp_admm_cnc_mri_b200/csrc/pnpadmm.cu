@@ -188,6 +188,7 @@ struct Workspace {
     cx<T>* T1;        // [B][N][N] per-image complex scratch
     uint8_t* mcode;   // [N][N] or [P][N][N]
     uint32_t* mpack;  // N == 256 only: [16][256] or [P][16][256] packed codes for the cluster kernel
+    cx<T>* Gt;        // N == 256 fp32 only: G in the cluster kernel's tile order [P][rank][256][R]
     int* progress;    // [P][8] hand-off counters of the chunked cluster schedule
     int P, solo;
 };
@@ -202,6 +203,7 @@ size_t ws_bytes_impl(int B, int N, size_t elt, int mask_batched) {
     s += align_up((mask_batched ? P : 1) * nn);
     s += align_up((mask_batched ? P : 1) * nn / 4);   // packed codes (2 bits per bin, 32-bit words)
     s += align_up(P * 16 * sizeof(int));              // progress counters [P][<=16 ranks]
+    if (N == 256 && elt == 4) s += align_up(P * nn * 2 * elt);   // Gt (cluster kernel)
     return s;
 }
 
@@ -223,7 +225,8 @@ int carve(void* ws, size_t ws_bytes, int B, int N, int mask_batched, Workspace<T
     out->G = (cx<T>*)p; p += align_up(P * nn * 2 * sizeof(T));
     out->mcode = p; p += align_up((mask_batched ? P : 1) * nn);
     out->mpack = (uint32_t*)p; p += align_up((mask_batched ? P : 1) * nn / 4);
-    out->progress = (int*)p;
+    out->progress = (int*)p; p += align_up(P * 16 * sizeof(int));
+    out->Gt = (N == 256 && sizeof(T) == 4) ? (cx<T>*)p : nullptr;
     out->P = (int)P;
     out->solo = mask_batched ? 1 : 0;
     return PNPADMM_OK;
@@ -327,9 +330,11 @@ int prepare_impl(const T* y, const uint8_t* mask, int B, int N, int mask_batched
     write_cf_kernel<T><<<1, 1, 0, st>>>(w.cf, (T)0, (T)(0.5 * g / n2), (T)(g / n2));
     LAUNCH_CHECK("write_cf_kernel");
     const size_t total = (size_t)w.P * N * N;
+    const bool k1_ready = (N == k1::kN && sizeof(T) == 4 && d->max_clusters_256 > 0);
     prepare_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const cx<T>*>(y), mask, w.G,
                                                                       w.mcode, B, w.P, N, w.solo, mask_batched,
-                                                                      (T)(g / n2));
+                                                                      (T)(g / n2), k1_ready ? w.Gt : nullptr,
+                                                                      k1::kN / d->k1_cluster);
     LAUNCH_CHECK("prepare_kernel");
     if (N == k1::kN && sizeof(T) == 4) {
         const int planes = mask_batched ? w.P : 1;
@@ -409,7 +414,7 @@ template <> struct ClusterDispatch<float> {
         memset(&cp, 0, sizeof(cp));
         cp.B = B; cp.P = w.P; cp.solo = w.solo; cp.iters = iters;
         cp.z_in = z_in; cp.w_in = w_in; cp.x = x; cp.z = z; cp.w = wo; cp.xpw = xpw;
-        cp.G = reinterpret_cast<const k1::cf32*>(w.G); cp.mpack = w.mpack; cp.mcode_batched = w.solo;
+        cp.G = reinterpret_cast<const k1::cf32*>(w.Gt); cp.mpack = w.mpack; cp.mcode_batched = w.solo;
         cp.progress = w.progress;
         cp.cf = w.cf;
         cp.prox = pp;

@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(256) cols_kernel(const StreamParams<T> p) {
 template <typename T>
 __global__ void prepare_kernel(const cx<T>* __restrict__ y, const uint8_t* __restrict__ mask,
                                cx<T>* __restrict__ G, uint8_t* __restrict__ mcode,
-                               int B, int P, int N, int solo, int mask_batched, T g_over_n2) {
+                               int B, int P, int N, int solo, int mask_batched, T g_over_n2,
+                               cx<T>* __restrict__ Gt, int tileR) {
     const size_t nn = (size_t)N * N;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nn * P) return;
@@ -319,7 +320,10 @@ __global__ void prepare_kernel(const cx<T>* __restrict__ y, const uint8_t* __res
         sbi = T(0.5) * (m1 * b1.im - m2 * b2.im);
     }
     // Ys_a + i Ys_b = (sar - sbi) + i (sai + sbr)
-    G[idx] = mk<T>(g_over_n2 * (sar - sbi), g_over_n2 * (sai + sbr));
+    const cx<T> gv = mk<T>(g_over_n2 * (sar - sbi), g_over_n2 * (sai + sbr));
+    G[idx] = gv;
+    // N = 256 fp32: second copy in the cluster kernel's tile order [plane][rank][kr][c] (cluster256_core.cuh)
+    if (Gt) Gt[(size_t)plane * nn + (size_t)(c / tileR) * ((size_t)N * tileR) + (size_t)r * tileR + (c % tileR)] = gv;
     if (!mask_batched) {
         if (plane == 0) mcode[bin] = (uint8_t)((m[bin] ? 1 : 0) + (m[mbin] ? 1 : 0));
     } else {
