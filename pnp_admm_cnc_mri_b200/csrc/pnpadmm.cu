@@ -13,6 +13,7 @@
 #include "../../include/pnpadmm.h"
 #include "cluster256.cuh"
 #include "streaming.cuh"
+#include "stream2.cuh"
 
 using namespace pnp;
 
@@ -102,6 +103,74 @@ cudaError_t set_stream_attrs() {
     return cudaSuccess;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K2 register-FFT streaming kernels (stream2.cuh): fp32, N in {256, 512, 1024}
+// ------------------------------------------------------------------------------------------
+bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+template <typename T> struct S2 {
+    static bool ok(int) { return false; }
+    static cudaError_t set_attrs() { return cudaSuccess; }
+    template <int MODE> static int rows(const StreamParams<T>&, int, cudaStream_t) { return PNPADMM_ERR_UNSUPPORTED; }
+    template <int MODE> static int cols(const StreamParams<T>&, int, const uint32_t*, int, cudaStream_t) { return PNPADMM_ERR_UNSUPPORTED; }
+};
+template <> struct S2<float> {
+    static bool ok(int N) {
+        static const bool force_v1 = getenv("PNPADMM_STREAM_V1") != nullptr;   // A/B against the generic kernels
+        return !force_v1 && (N == 256 || N == 512 || N == 1024);
+    }
+    template <int N> static cudaError_t set_attrs_n() {
+        cudaError_t e;
+#define SET2(k, bytes)                                                                          \
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);            \
+    if (e != cudaSuccess) return e;
+        SET2((s2::rows2_kernel<N, RM_FWD_ZW>), s2::RowsGeo<N>::kSmemBytes)
+        SET2((s2::rows2_kernel<N, RM_FWD_IMG>), s2::RowsGeo<N>::kSmemBytes)
+        SET2((s2::rows2_kernel<N, RM_INV_X>), s2::RowsGeo<N>::kSmemBytes)
+        SET2((s2::rows2_kernel<N, RM_INV_ABS>), s2::RowsGeo<N>::kSmemBytes)
+        SET2((s2::rows2_kernel<N, RM_INV_PROX_FWD>), s2::RowsGeo<N>::kSmemBytes)
+        SET2((s2::cols2_kernel<N, CM_FWD_ACQ>), s2::ColsGeo<N>::kSmemBytes)
+        SET2((s2::cols2_kernel<N, CM_INV>), s2::ColsGeo<N>::kSmemBytes)
+        SET2((s2::cols2_kernel<N, CM_FWD_BLEND_INV>), s2::ColsGeo<N>::kSmemBytes)
+#undef SET2
+        return cudaSuccess;
+    }
+    static cudaError_t set_attrs() {
+        cudaError_t e = set_attrs_n<256>(); if (e != cudaSuccess) return e;
+        e = set_attrs_n<512>(); if (e != cudaSuccess) return e;
+        return set_attrs_n<1024>();
+    }
+    // `planes`: packed planes, or images for the per-image modes (FWD_IMG, INV_ABS, FWD_ACQ, INV)
+    template <int N, int MODE> static void rows_n(const StreamParams<float>& p, int planes, cudaStream_t st) {
+        typedef s2::RowsGeo<N> G;
+        s2::rows2_kernel<N, MODE><<<planes * (N / G::L), s2::kRowsThreads, G::kSmemBytes, st>>>(p);
+    }
+    template <int MODE> static int rows(const StreamParams<float>& p, int planes, cudaStream_t st) {
+        switch (p.N) {
+            case 256: rows_n<256, MODE>(p, planes, st); break;
+            case 512: rows_n<512, MODE>(p, planes, st); break;
+            default: rows_n<1024, MODE>(p, planes, st); break;
+        }
+        return PNPADMM_OK;
+    }
+    template <int N, int MODE> static void cols_n(StreamParams<float> p, int planes, const uint32_t* mpack, int sm_count, cudaStream_t st) {
+        typedef s2::ColsGeo<N> G;
+        p.P = planes;
+        const long ntiles = (long)planes * (N / G::C);
+        const long cap = (long)sm_count * G::kCtasPerSm;
+        s2::cols2_kernel<N, MODE><<<(unsigned)(ntiles < cap ? ntiles : cap), G::kThreads, G::kSmemBytes, st>>>(p, mpack);
+    }
+    template <int MODE> static int cols(const StreamParams<float>& p, int planes, const uint32_t* mpack, int sm_count, cudaStream_t st) {
+        switch (p.N) {
+            case 256: cols_n<256, MODE>(p, planes, mpack, sm_count, st); break;
+            case 512: cols_n<512, MODE>(p, planes, mpack, sm_count, st); break;
+            default: cols_n<1024, MODE>(p, planes, mpack, sm_count, st); break;
+        }
+        return PNPADMM_OK;
+    }
+};
+
 template <int CL>
 int probe_clusters(int sm_count) {
     typedef k1::Geo<CL> G;
@@ -160,6 +229,7 @@ int ensure_device(DeviceState** out) {
         CUDA_TRY(cudaMemcpyToSymbol(g_tw_f64, td.data(), sizeof(double2) * kTwMax));
         CUDA_TRY(set_stream_attrs<float>());
         CUDA_TRY(set_stream_attrs<double>());
+        CUDA_TRY(S2<float>::set_attrs());
         d.max_cl8 = probe_clusters<8>(d.sm_count);
         d.max_cl16 = probe_clusters<16>(d.sm_count);
         // Default geometry: 16 half-size CTAs (two planes share an SM, so one computes while the other
@@ -283,6 +353,16 @@ int acquire_impl(const T* img, const uint8_t* mask, const T* noise, T* y, int B,
     Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, 0, &w, true); if (rc) return rc;
     StreamParams<T> p = base_params(w, B, N);
     p.img = img; p.cout = w.T1; p.round_f32 = (sizeof(T) == 8) ? round_f32 : 0;
+    if (S2<T>::ok(N) && aligned16(img) && aligned16(noise) && aligned16(y)) {
+        S2<T>::template rows<RM_FWD_IMG>(p, B, st);
+        LAUNCH_CHECK("rows2_kernel<FWD_IMG>");
+        p.cin = w.T1; p.cout = reinterpret_cast<cx<T>*>(y);
+        p.mask = mask; p.mask_batched = mask_batched;
+        p.noise = reinterpret_cast<const cx<T>*>(noise); p.noise_batched = noise_batched;
+        S2<T>::template cols<CM_FWD_ACQ>(p, B, nullptr, d->sm_count, st);
+        LAUNCH_CHECK("cols2_kernel<FWD_ACQ>");
+        return PNPADMM_OK;
+    }
     p.lines = rows_lines<T>(N);
     rows_kernel<T, RM_FWD_IMG><<<dim3(N / p.lines, B), 256, rows_smem<T>(N), st>>>(p);
     LAUNCH_CHECK("rows_kernel<FWD_IMG>");
@@ -303,6 +383,14 @@ int zero_filled_impl(const T* y, T* x0, int B, int N, void* ws, size_t ws_bytes,
     Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, 0, &w, true); if (rc) return rc;
     StreamParams<T> p = base_params(w, B, N);
     p.cin = reinterpret_cast<const cx<T>*>(y); p.cout = w.T1;
+    if (S2<T>::ok(N) && aligned16(y) && aligned16(x0)) {
+        S2<T>::template cols<CM_INV>(p, B, nullptr, d->sm_count, st);
+        LAUNCH_CHECK("cols2_kernel<INV>");
+        p.cin = w.T1; p.x = x0;
+        S2<T>::template rows<RM_INV_ABS>(p, B, st);
+        LAUNCH_CHECK("rows2_kernel<INV_ABS>");
+        return PNPADMM_OK;
+    }
     p.lines = cols_lines<T>(N);
     cols_kernel<T, CM_INV><<<dim3(N / p.lines, B), 256, cols_smem<T>(N), st>>>(p);
     LAUNCH_CHECK("cols_kernel<INV>");
@@ -336,10 +424,11 @@ int prepare_impl(const T* y, const uint8_t* mask, int B, int N, int mask_batched
                                                                       (T)(g / n2), k1_ready ? w.Gt : nullptr,
                                                                       k1::kN / d->k1_cluster);
     LAUNCH_CHECK("prepare_kernel");
-    if (N == k1::kN && sizeof(T) == 4) {
+    if (sizeof(T) == 4 && (N == 256 || N == 512 || N == 1024)) {   // packed codes of the column passes (K1 and K2)
         const int planes = mask_batched ? w.P : 1;
-        k1::pack_mcode_k1_kernel<<<(planes * 16 * k1::kN + 255) / 256, 256, 0, st>>>(w.mcode, w.mpack, planes);
-        LAUNCH_CHECK("pack_mcode_k1_kernel");
+        const size_t words = (size_t)planes * (N / 16) * N;
+        s2::pack_mcode_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(w.mcode, w.mpack, planes, N);
+        LAUNCH_CHECK("pack_mcode_kernel");
     }
     return PNPADMM_OK;
 }
@@ -438,6 +527,13 @@ int xupdate_impl(const T* z, const T* wv, T* x, T* xpw, int B, int N, int mask_b
     }
     StreamParams<T> p = base_params(w, B, N);
     p.z = const_cast<T*>(z); p.w = const_cast<T*>(wv); p.x = x; p.xpw = xpw;
+    if (S2<T>::ok(N) && aligned16(z) && aligned16(wv) && aligned16(x) && aligned16(xpw)) {
+        S2<T>::template rows<RM_FWD_ZW>(p, w.P, st);
+        S2<T>::template cols<CM_FWD_BLEND_INV>(p, w.P, w.mpack, d->sm_count, st);
+        S2<T>::template rows<RM_INV_X>(p, w.P, st);
+        LAUNCH_CHECK("K2 x-update kernels");
+        return PNPADMM_OK;
+    }
     p.lines = rows_lines<T>(N);
     rows_kernel<T, RM_FWD_ZW><<<dim3(N / p.lines, w.P), 256, rows_smem<T>(N), st>>>(p);
     LAUNCH_CHECK("rows_kernel<FWD_ZW>");
@@ -465,6 +561,16 @@ int iterate_impl(T* x, T* z, T* wv, int B, int N, int mask_batched, int prox, in
 
     StreamParams<T> p = base_params(w, B, N);
     p.z = z; p.w = wv; p.x = x; p.prox = pp;
+    if (S2<T>::ok(N) && aligned16(z) && aligned16(wv) && aligned16(x)) {
+        S2<T>::template rows<RM_FWD_ZW>(p, w.P, st);
+        for (int it = 0; it < iters; ++it) {
+            S2<T>::template cols<CM_FWD_BLEND_INV>(p, w.P, w.mpack, d->sm_count, st);
+            p.last = (it == iters - 1);
+            S2<T>::template rows<RM_INV_PROX_FWD>(p, w.P, st);
+        }
+        LAUNCH_CHECK("K2 iteration kernels");
+        return PNPADMM_OK;
+    }
     const int rl = rows_lines<T>(N), cl = cols_lines<T>(N);
     const size_t rs = rows_smem<T>(N), cs = cols_smem<T>(N);
     p.lines = rl;
