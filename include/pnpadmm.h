@@ -172,6 +172,22 @@ int pnpadmm_dual_update_f32(float* x, float* z, float* w, int clamp01, size_t n,
 int pnpadmm_dual_update_f64(double* x, double* z, double* w, int clamp01, size_t n, pnpadmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Per-image quality metrics on the device: out[B][3] = (PSNR dB, SSIM, RE) of
+ * reconstructions x[B][N][N] (unit scale) against uint8 ground truth ref[B][N][N], evaluated in
+ * double precision like the reference's utils/utils_image.py calculate_psnr :543-556,
+ * calculate_ssim :570-615 (11x11 Gaussian window, valid region) and calculate_re :622-636,
+ * border = 0.  quantize = 0: img_E = 255 x (S1:133, S4:139); quantize = 1: img_E =
+ * uint8(round(255 clip(x, 0, 1))) (util.single2uint, S6:315, S6:531).  `scratch` (device,
+ * 16-byte aligned, pnpadmm_metrics_scratch_bytes(B)) holds the per-image accumulators; `out` is
+ * device memory.  Stream-ordered, no host synchronisation.
+ * ------------------------------------------------------------------------------------- */
+size_t pnpadmm_metrics_scratch_bytes(int B);
+int pnpadmm_metrics_f32(const float* x, const uint8_t* ref, int B, int N, int quantize, double* out, void* scratch,
+                        size_t scratch_bytes, pnpadmm_stream_t stream);
+int pnpadmm_metrics_f64(const double* x, const uint8_t* ref, int B, int N, int quantize, double* out, void* scratch,
+                        size_t scratch_bytes, pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helper: runs `iters` dependent-FMA loops on every SM and returns the achieved
  * non-tensor FP32 FLOP/s in *flops (device-timed with CUDA events, synchronous).  Used by
  * bench.py as the measured denominator of the FP32 FFT roofline.

@@ -275,6 +275,11 @@ def uint2single(img_u8):
     return np.float32(img_u8 / 255.)
 
 
+def single2uint(img):
+    """utils_image.py:185-186: np.uint8((img.clip(0, 1) * 255.).round()) — the img_E of S6:315 / S6:531."""
+    return np.uint8((img.clip(0, 1) * 255.).round())
+
+
 def preprocess_uint8(img_u8):
     """S1:85-90: gray uint8 (H,W) -> modcrop(8) -> /255 float32 (the clip
     round trip S1:89-90 is the identity for uint8 input)."""

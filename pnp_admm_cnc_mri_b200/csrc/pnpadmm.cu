@@ -14,6 +14,7 @@
 #include "cluster256.cuh"
 #include "streaming.cuh"
 #include "stream2.cuh"
+#include "metrics.cuh"
 
 using namespace pnp;
 
@@ -239,6 +240,10 @@ int ensure_device(DeviceState** out) {
             const int want = atoi(e);
             if (want == 16 && d.max_cl16 > 0) d.k1_cluster = 16;
             if (want == 8 && d.max_cl8 > 0) d.k1_cluster = 8;
+        }
+        if (const char* e = getenv("PNPADMM_K1_MAXCL")) {   // experiments: override the occupancy query
+            const int n = atoi(e);
+            if (n > 0) { d.max_cl8 = n; d.max_cl16 = n; }
         }
         d.max_clusters_256 = d.k1_cluster == 16 ? d.max_cl16 : d.max_cl8;
         d.ready = true;
@@ -635,6 +640,31 @@ int dual_impl(T* x, T* z, T* w, int clamp, size_t n, cudaStream_t st) {
     return PNPADMM_OK;
 }
 
+template <typename T>
+int metrics_impl(const T* x, const uint8_t* ref, int B, int N, int quantize, double* out, void* scratch,
+                 size_t scratch_bytes, cudaStream_t st) {
+    if (!x || !ref || !out || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "metrics: NULL pointer or B <= 0");
+    if (N < 16 || N > 4096) return fail(PNPADMM_ERR_BAD_SIZE, "metrics: N=%d unsupported (16 <= N <= 4096)", N);
+    if (!scratch || scratch_bytes < sizeof(MetricsAcc) * (size_t)B || ((uintptr_t)scratch & 15))
+        return fail(PNPADMM_ERR_WORKSPACE, "metrics: scratch must be 16-byte aligned and hold %zu bytes", sizeof(MetricsAcc) * (size_t)B);
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    static bool attr_set[kMaxDevices] = {};
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    if (!attr_set[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetSmemBytes));
+        attr_set[dev] = true;
+    }
+    MetricsAcc* acc = (MetricsAcc*)scratch;
+    CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(MetricsAcc) * (size_t)B, st));
+    const int tiles = (N + kMetTile - 1) / kMetTile;
+    metrics_tile_kernel<T><<<dim3(tiles, tiles, B), 256, kMetSmemBytes, st>>>(x, ref, N, quantize, acc);
+    LAUNCH_CHECK("metrics_tile_kernel");
+    metrics_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(acc, out, B, N);
+    LAUNCH_CHECK("metrics_finalize_kernel");
+    return PNPADMM_OK;
+}
+
 // FP32 FMA throughput probe: 8 independent FMA chains per thread.
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float b, float c) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
@@ -777,6 +807,16 @@ int pnpadmm_cnc_combine_f64(const double* z, const double* x, const double* w, c
 }
 int pnpadmm_dual_update_f32(float* x, float* z, float* w, int clamp01, size_t n, pnpadmm_stream_t s) { return dual_impl<float>(x, z, w, clamp01, n, ST(s)); }
 int pnpadmm_dual_update_f64(double* x, double* z, double* w, int clamp01, size_t n, pnpadmm_stream_t s) { return dual_impl<double>(x, z, w, clamp01, n, ST(s)); }
+
+int pnpadmm_metrics_f32(const float* x, const uint8_t* ref, int B, int N, int quantize, double* out, void* scratch,
+                        size_t scratch_bytes, pnpadmm_stream_t s) {
+    return metrics_impl<float>(x, ref, B, N, quantize, out, scratch, scratch_bytes, ST(s));
+}
+int pnpadmm_metrics_f64(const double* x, const uint8_t* ref, int B, int N, int quantize, double* out, void* scratch,
+                        size_t scratch_bytes, pnpadmm_stream_t s) {
+    return metrics_impl<double>(x, ref, B, N, quantize, out, scratch, scratch_bytes, ST(s));
+}
+size_t pnpadmm_metrics_scratch_bytes(int B) { return B > 0 ? sizeof(MetricsAcc) * (size_t)B : 0; }
 
 int pnpadmm_measure_fp32_peak(double* flops, pnpadmm_stream_t s) {
     if (!flops) return fail(PNPADMM_ERR_BAD_ARG, "measure_fp32_peak: NULL pointer");

@@ -251,3 +251,27 @@ def dual_update_(x, z, w, clamp01: bool) -> None:
     with torch.cuda.device(x.device):
         _abi.check(getattr(_abi.load(), 'pnpadmm_dual_update_' + sfx)(x.data_ptr(), z.data_ptr(), w.data_ptr(), int(clamp01),
                                                                       x.numel(), _stream_ptr()))
+
+
+def image_metrics(x: torch.Tensor, ref_u8: torch.Tensor, quantize: bool = False) -> torch.Tensor:
+    """Per-image (PSNR dB, SSIM, RE) on the device: ``x`` (B,N,N) float32/float64 reconstructions on unit scale,
+    ``ref_u8`` (B,N,N) uint8 ground truth.  Same definitions as the reference's ``calculate_psnr`` /
+    ``calculate_ssim`` / ``calculate_re`` (utils/utils_image.py:543-636, border 0), double precision.
+    ``quantize=False`` scores ``255 x`` (S1:133), ``True`` scores ``uint8(round(255 clip(x)))`` (S6:315).
+    Returns a (B,3) float64 CUDA tensor; nothing is copied to the host."""
+    dev = _require_cuda(x.device)
+    if x.dim() == 2:
+        x, ref_u8 = x[None], ref_u8[None]
+    if x.dtype not in (torch.float32, torch.float64) or ref_u8.dtype != torch.uint8 or x.shape != ref_u8.shape \
+            or x.dim() != 3 or x.shape[1] != x.shape[2]:
+        raise ValueError('image_metrics: x (B,N,N) float32/float64 and ref_u8 (B,N,N) uint8 of the same shape')
+    x, ref_u8 = x.contiguous(), ref_u8.to(dev).contiguous()
+    B, N = int(x.shape[0]), int(x.shape[1])
+    lib = _abi.load()
+    out = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    scratch = torch.empty(lib.pnpadmm_metrics_scratch_bytes(B), dtype=torch.uint8, device=dev)
+    sfx = 'f64' if x.dtype == torch.float64 else 'f32'
+    with torch.cuda.device(dev):
+        _abi.check(getattr(lib, 'pnpadmm_metrics_' + sfx)(x.data_ptr(), ref_u8.data_ptr(), B, N, int(bool(quantize)),
+                                                          out.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream_ptr()))
+    return out

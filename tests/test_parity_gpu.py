@@ -279,3 +279,40 @@ def test_error_codes(pk):
         pk.admm_solve(np.zeros((2, 64, 64), np.float32), np.ones((64, 64)), np.zeros((64, 64), complex), kernel='cluster')
     with pytest.raises(ValueError):
         pk.admm_solve(np.zeros((2, 64, 64), np.float32), np.ones((64, 64)), np.zeros((64, 64), complex), reo=0.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# 8f rank 1: PSNR / SSIM / RE on the device against the reference's definitions (oracle restatement)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dt', ['float32', 'float64'])
+def test_device_metrics_match_reference_definitions(pk, cs_inputs, dt):
+    idx = [0, 4, 9]
+    H = cs_inputs['images'][idx]
+    imgs = _imgs(cs_inputs, idx)
+    x = np.stack([orc.admm_cnc(im, cs_inputs['masks'][0].astype(np.float64), cs_inputs['noises'], **kat.CNC_DEFAULTS)
+                  for im in imgs]).astype(dt)                      # unclipped, may exceed 1
+    for quantize in (False, True):
+        got = pk.image_metrics(torch.as_tensor(x).cuda(), torch.as_tensor(H).cuda(), quantize=quantize).cpu().numpy()
+        for k in range(len(idx)):
+            E = orc.single2uint(x[k].astype(np.float32)) if quantize else x[k].astype(np.float64) * 255
+            want = (orc.calculate_psnr(E, H[k]), orc.calculate_ssim(E, H[k]), orc.calculate_re(E, H[k]))
+            assert abs(got[k, 0] - want[0]) < 1e-9 and abs(got[k, 1] - want[1]) < 1e-11 and abs(got[k, 2] - want[2]) < 1e-12, \
+                (quantize, k, got[k], want)
+    # the KAT table row of image 01, Q_Random30, CNC (results/Set_dn_ADMM_CNC.log: 24.7868 / 0.4528 / 0.1486)
+    x64 = orc.admm_cnc(imgs[0], cs_inputs['masks'][0].astype(np.float64), cs_inputs['noises'], **kat.CNC_DEFAULTS)
+    m = pk.image_metrics(torch.as_tensor(x64[None]).cuda(), torch.as_tensor(H[:1]).cuda()).cpu().numpy()[0]
+    assert (round(m[0], 4), round(m[1], 4), round(m[2], 4)) == (24.7868, 0.4528, 0.1486)
+
+
+def test_device_metrics_sizes_and_errors(pk):
+    rng = np.random.default_rng(5)
+    for N in (16, 64, 512):
+        x = rng.random((2, N, N)).astype(np.float32)
+        H = rng.integers(0, 256, (2, N, N), dtype=np.uint8)
+        got = pk.image_metrics(torch.as_tensor(x).cuda(), torch.as_tensor(H).cuda()).cpu().numpy()
+        for k in range(2):
+            E = x[k].astype(np.float64) * 255
+            want = (orc.calculate_psnr(E, H[k]), orc.calculate_ssim(E, H[k]), orc.calculate_re(E, H[k]))
+            np.testing.assert_allclose(got[k], want, rtol=1e-10, atol=1e-12)
+    with pytest.raises(ValueError):
+        pk.image_metrics(torch.zeros((2, 8, 8), device='cuda'), torch.zeros((2, 8, 8), dtype=torch.uint8, device='cuda'))
