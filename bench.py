@@ -36,6 +36,8 @@ N = 256
 B_PER_GPU = 64
 CNC = dict(alpha=0.45, iter_num=50, lambda1=0.5, reo=0.05, b=64)      # S4:176
 MASK_KINDS = ('cartesian', 'radial', 'random')
+WORKLOAD = ('BASELINE config 2: ADMM-CNC 256x256, batch 64 per GPU, 30% cartesian/radial/random masks cycling per step, '
+            'reference defaults (alpha .45, 50 it, lambda .5, reo .05, b 64)')
 FLOP_PER_IMAGE_ITER = 10 * N * N * math.log2(N * N)                   # 10 485 760
 FP32_LANES_PER_SM = 128
 
@@ -95,8 +97,8 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'admm_cnc_iterations_per_s', 'value': value, 'unit': 'iterations/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'ADMM-CNC 256x256, 30% cartesian/radial/random masks, reference defaults (S4:176)',
-                   'images_per_step': n_img, 'iter_num': CNC['iter_num']},
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B_PER_GPU, 'iter_num': CNC['iter_num'],
+                   'sample': f'{n_img} images of that workload per step (bounded CPU sample), one process per core'},
         'cpu_baseline': {'value': value, 'unit': 'iterations/s', 'cores': cores, 'kind': 'port',
                          'sample': f'{n_img} images x 50 iterations per step, one process per core (NumPy fp64, '
                                    f'oracle restatement bit-identical to the unmodified reference script)'},
@@ -248,6 +250,34 @@ def run_ours(args):
         if r >= args.warmup:
             k1_ms.append(e0.elapsed_time(e1))
     k1_ms = float(np.mean(k1_ms))
+
+    # K2 (streaming kernels) against the HBM roofline: ADMM-CNC at N = 1024, 64 images per GPU, 10 iterations
+    # per launch sequence (state + workspace = 2.3 GB >> L2, so every pass streams from HBM)
+    k2 = None
+    if rank == 0:
+        from pnp_admm_cnc_mri_b200 import data as pdata
+        N2, B2, IT2 = 1024, 64, 10
+        s2 = pk.AdmmSolver(B2, N2)
+        im2 = np.stack([pdata.phantom(N2, i) for i in range(4)] * (B2 // 4)).astype(np.float32)
+        m2 = pdata.make_mask('random', N2, seed=0)
+        y2 = s2.acquire(im2, m2, pdata.make_noise(N2, seed=7))
+        z20 = s2.zero_filled(y2)
+        s2.prepare(y2, m2, CNC['reo'])
+        x2 = torch.empty_like(z20)
+        t2 = []
+        for r in range(5):
+            z2, w2 = z20.clone(), torch.zeros_like(z20)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            s2.iterate(x2, z2, w2, 'cnc', IT2, CNC['lambda1'], CNC['reo'], CNC['alpha'], CNC['b'], kernel='streaming')
+            e1.record()
+            torch.cuda.synchronize()
+            if r >= 2:
+                t2.append(e0.elapsed_time(e1))
+        k2 = dict(N=N2, B=B2, iters=IT2, ms=float(np.mean(t2)))
+        del s2, y2, z20, x2, z2, w2
+        torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None
 
     fl = ctypes.c_double()
@@ -274,17 +304,15 @@ def run_ours(args):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'images_per_s': value / CNC['iter_num'],
-            'config': {'workload': 'BASELINE config 2: ADMM-CNC 256x256, batch 64 per GPU, 30% cartesian/radial/random '
-                                   'masks cycling per step, reference defaults (alpha .45, 50 it, lambda .5, reo .05, b 64)',
-                       'batch_per_gpu': B, 'iter_num': CNC['iter_num'], 'kernel': 'cluster256 (K1, 16-CTA clusters, 2 CTAs/SM)',
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'iter_num': CNC['iter_num'], 'kernel': 'cluster256 (K1, 16-CTA clusters, 2 CTAs/SM); acquisition / zero-fill: K2 rows2/cols2',
                        'l2': 'flushed (256 MiB fill) between timed steps', 'sharding': f'batch x{world}, no collective'},
             'e2e': {'value': e2e, 'unit': 'iterations/s', 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(h_img.numel() + h_masks[0].numel() + h_noise.numel() * 4),
                     'd2h_bytes_per_step': int(h_x.numel() * 4), 'api': 'pnpadmm_reconstruct_host_f32 (pinned host buffers)'},
             'gpu_launches': 9 * args.steps,
             'launches_per_step': {'device': 9, 'e2e': 10,
-                                  'kernels': 'rows<FWD_IMG>, cols<FWD_ACQ>, cols<INV>, rows<INV_ABS>, copy_zero, write_cf, '
-                                             'prepare, pack_mcode_k1, cluster256 (+ u8_to_unit in e2e)'},
+                                  'kernels': 'rows2<FWD_IMG>, cols2<FWD_ACQ>, cols2<INV>, rows2<INV_ABS>, copy_zero, write_cf, '
+                                             'prepare, pack_mcode, cluster256 (+ u8_to_unit in e2e)'},
             'roofline': {'bound': 'fp32', 'kernel': 'cluster256_kernel', 'achieved': achieved, 'peak': nominal_peak,
                          'unit': 'TFLOP/s', 'frac': achieved / nominal_peak, 'traffic': None,
                          'peak_source': f'nominal non-tensor FP32: {sm.value} SMs x 128 lanes x 2 x {sm_max:.0f} MHz '
@@ -295,6 +323,24 @@ def run_ours(args):
                                        'complex 2-D FFTs; executed flops are lower: pair-packing + radix-16)',
                          'launch_ms': k1_ms, 'resident_clusters': ncl.value},
             'clocks': clocks,
+        }
+        hbm_peak = peaks.get('hbm_gbs', 6450.0)
+        its2 = k2['B'] * k2['iters'] / (k2['ms'] * 1e-3)
+        moved = its2 * 36.5 * k2['N'] ** 2 / 1e9
+        line['roofline_streaming'] = {
+            'bound': 'hbm', 'kernel': 'rows2_kernel<1024> + cols2_kernel<1024> (K2, one pair per iteration)',
+            'achieved': moved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': moved / hbm_peak,
+            'traffic': 2319e6 * k2['B'] / 64,
+            'traffic_source': 'profiles/r1_k2v2_ncu_summary.txt: dram read+write of one rows2 + one cols2 launch at N=1024, '
+                              'B=64 (1554 MB + 765 MB), scaled by B/64',
+            'bytes_model': '73 N^2 per packed plane-iteration = 36.5 N^2 per image-iteration (rows pass 48 B/px: K 8+8, '
+                           'z,w of two images 16+16; cols pass 25 B/px: K 8+8, G 8, codes 1/4): DESIGN.md 5',
+            'achieved_survey_q57': its2 * 57 * k2['N'] ** 2 / 1e9,
+            'survey_model': 'SURVEY 8d counts 57 N^2 per image-iteration for an unpaired implementation; pairing two '
+                            'real images per complex plane moves 36.5 N^2, so the survey-model figure can exceed the peak',
+            'workload': f"ADMM-CNC N={k2['N']}, B={k2['B']}, {k2['iters']} iterations per timed call", 'call_ms': k2['ms'],
+            'iterations_per_s': its2,
+            'peak_source': 'MEASURED_PEAKS.json hbm_gbs (copy bandwidth)' if 'hbm_gbs' in peaks else 'fallback 6450 GB/s',
         }
         if cpu_v is not None:
             line['cpu_baseline'] = {'value': cpu_v, 'unit': 'iterations/s', 'cores': 1, 'kind': 'port',

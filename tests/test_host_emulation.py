@@ -86,3 +86,39 @@ def test_k1_emulated_solve_matches_oracle(emu, cs_inputs, prox, P, cluster):
         assert np.linalg.norm(z[k] - zr) / np.linalg.norm(zr) < 1e-4
         p = orc.calculate_psnr(x[k].astype(np.float64) * 255, cs_inputs['images'][i])
         assert abs(p - kat.PSNR[('Q_Radial30', prox)][i]) < 0.01
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 streaming kernels: the per-thread FFT stages (stream2_core.cuh) against a naive double DFT
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def s2emu():
+    so = os.path.join(EMU_DIR, 's2_emu.so')
+    src = os.path.join(EMU_DIR, 's2_emu.cpp')
+    deps = [src] + [os.path.join(ROOT, 'pnp_admm_cnc_mri_b200', 'csrc', f)
+                    for f in ('stream2_core.cuh', 'cluster256_core.cuh', 'common.cuh')]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', so, src])
+    lib = ctypes.CDLL(so)
+    lib.s2_fft_check.restype = ctypes.c_double
+    lib.s2_fft_check.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
+    return lib
+
+
+@pytest.mark.parametrize('N', [256, 512, 1024])
+@pytest.mark.parametrize('inv', [0, 1])
+@pytest.mark.parametrize('layout', [0, 1], ids=['rows', 'cols'])
+def test_k2_fft_stages(s2emu, N, inv, layout):
+    # radix 16 x 16 [x 2 | x 4] Stockham stages, row (padded) and column ([N][C]) shared-memory layouts
+    for seed in (1, 2):
+        assert 0 <= s2emu.s2_fft_check(N, inv, layout, seed) < 3e-7
+
+
+def test_k2_packed_codes(s2emu):
+    rng = np.random.default_rng(0)
+    for N in (256, 512, 1024):
+        mc = rng.integers(0, 3, (N, N), dtype=np.uint8)
+        T = N // 16
+        for t, kc in ((0, 0), (T - 1, N - 1), (3, 17)):
+            w = s2emu.s2_pack_codes(mc.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), N, t, kc)
+            assert [(w >> (2 * m)) & 3 for m in range(16)] == [int(mc[t + T * m, kc]) for m in range(16)]
