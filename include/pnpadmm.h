@@ -152,6 +152,22 @@ int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, co
                                  int kernel, void* d_scratch, size_t scratch_bytes,
                                  void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
 
+/* Pipelined form of the same call for back-to-back batches: the H2D copies run on `h2d`, the kernels
+ * on `compute`, the D2H copy on `d2h` (three distinct streams), with two device slots so that the
+ * copies of batch i-1 / i+1 overlap the kernels of batch i.  Alternate slot = 0, 1, 0, ... between
+ * calls; ordering between the streams uses library-owned events (created once per device).  Returns
+ * after everything is enqueued; pnpadmm_reconstruct_host_wait(slot) blocks the host until the h_x
+ * passed with that slot has been written.  The host buffers of a slot must stay untouched until then.
+ * d_scratch: pnpadmm_host_pipeline_scratch_bytes(B, N) bytes. */
+size_t pnpadmm_host_pipeline_scratch_bytes(int B, int N);
+int pnpadmm_reconstruct_host_pipelined_f32(const uint8_t* h_img, const uint8_t* h_mask, const float* h_noise,
+                                           float* h_x, int B, int N,
+                                           int prox, int iters, double lambda1, double reo, double alpha, double b,
+                                           int kernel, void* d_scratch, size_t scratch_bytes,
+                                           void* ws, size_t ws_bytes, int slot,
+                                           pnpadmm_stream_t compute, pnpadmm_stream_t h2d, pnpadmm_stream_t d2h);
+int pnpadmm_reconstruct_host_wait(int slot);
+
 /* ---------------------------------------------------------------------------------------
  * Pointwise pieces used by the PnP variants (denoiser runs outside this library).
  * ------------------------------------------------------------------------------------- */

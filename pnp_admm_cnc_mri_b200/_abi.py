@@ -21,6 +21,7 @@ SYMBOLS = [
     'pnpadmm_prepare_f32', 'pnpadmm_prepare_f64', 'pnpadmm_xupdate_f32', 'pnpadmm_xupdate_f64',
     'pnpadmm_iterate_f32', 'pnpadmm_iterate_f64', 'pnpadmm_solve_f32', 'pnpadmm_solve_f64',
     'pnpadmm_host_scratch_bytes', 'pnpadmm_reconstruct_host_f32',
+    'pnpadmm_host_pipeline_scratch_bytes', 'pnpadmm_reconstruct_host_pipelined_f32', 'pnpadmm_reconstruct_host_wait',
     'pnpadmm_soft_f32', 'pnpadmm_soft_f64', 'pnpadmm_cnc_combine_f32', 'pnpadmm_cnc_combine_f64',
     'pnpadmm_dual_update_f32', 'pnpadmm_dual_update_f64', 'pnpadmm_measure_fp32_peak',
     'pnpadmm_metrics_scratch_bytes', 'pnpadmm_metrics_f32', 'pnpadmm_metrics_f64',
@@ -80,6 +81,12 @@ def load() -> ctypes.CDLL:
     for sfx in ('f32', 'f64'):
         f = getattr(lib, 'pnpadmm_metrics_' + sfx); f.restype = i
         f.argtypes = [p, p, i, i, i, p, p, z, p]
+    lib.pnpadmm_host_pipeline_scratch_bytes.restype = z
+    lib.pnpadmm_host_pipeline_scratch_bytes.argtypes = [i, i]
+    lib.pnpadmm_reconstruct_host_pipelined_f32.restype = i
+    lib.pnpadmm_reconstruct_host_pipelined_f32.argtypes = [p, p, p, p, i, i, i, i, d, d, d, d, i, p, z, p, z, i, p, p, p]
+    lib.pnpadmm_reconstruct_host_wait.restype = i
+    lib.pnpadmm_reconstruct_host_wait.argtypes = [i]
     lib.pnpadmm_measure_fp32_peak.restype = i
     lib.pnpadmm_measure_fp32_peak.argtypes = [POINTER(c_double), p]
     if lib.pnpadmm_abi_version() != ABI_VERSION:

@@ -795,6 +795,87 @@ int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, co
     return PNPADMM_OK;
 }
 
+// Pipelined variant: copies on their own streams, double-buffered device slots, ordering by library-owned events.
+size_t pnpadmm_host_pipeline_scratch_bytes(int B, int N) {
+    if (B <= 0 || N <= 0) return 0;
+    const size_t nn = (size_t)N * N, n = (size_t)B * nn;
+    // per slot: img u8, mask u8, noise c64, x f32;  shared by both slots (compute stream only): img f32, y c64, z, w
+    return 2 * (align_up(n) + align_up(nn) + align_up(nn * 8) + align_up(n * 4)) + align_up(n * 4) + align_up(n * 8) +
+           2 * align_up(n * 4);
+}
+
+namespace {
+struct PipeEvents { bool ready = false; cudaEvent_t in_ready[2], done[2], out_done[2]; };
+PipeEvents g_pipe[kMaxDevices];
+}  // namespace
+
+int pnpadmm_reconstruct_host_pipelined_f32(const uint8_t* h_img, const uint8_t* h_mask, const float* h_noise, float* h_x,
+                                           int B, int N, int prox, int iters, double lambda1, double reo, double alpha,
+                                           double b, int kernel, void* d_scratch, size_t scratch_bytes, void* ws, size_t wsb,
+                                           int slot, pnpadmm_stream_t compute, pnpadmm_stream_t h2d, pnpadmm_stream_t d2h) {
+    if (!h_img || !h_mask || !h_noise || !h_x || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: NULL pointer or B <= 0");
+    if (slot != 0 && slot != 1) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: slot must be 0 or 1");
+    int rc = check_n(N, false); if (rc) return rc;
+    if (!d_scratch || ((uintptr_t)d_scratch) % kAlign || scratch_bytes < pnpadmm_host_pipeline_scratch_bytes(B, N))
+        return fail(PNPADMM_ERR_WORKSPACE, "reconstruct_host_pipelined: d_scratch NULL, misaligned or smaller than %zu bytes",
+                    pnpadmm_host_pipeline_scratch_bytes(B, N));
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    PipeEvents& ev = g_pipe[dev];
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!ev.ready) {
+            for (int i = 0; i < 2; ++i) {
+                CUDA_TRY(cudaEventCreateWithFlags(&ev.in_ready[i], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&ev.done[i], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&ev.out_done[i], cudaEventDisableTiming));
+            }
+            ev.ready = true;
+        }
+    }
+    cudaStream_t sc = ST(compute), si = ST(h2d), so = ST(d2h);
+    const size_t nn = (size_t)N * N, n = (size_t)B * nn;
+    unsigned char* p = (unsigned char*)d_scratch;
+    uint8_t* d_img8[2]; uint8_t* d_mask[2]; float* d_noise[2]; float* d_x[2];
+    for (int i = 0; i < 2; ++i) {
+        d_img8[i] = p; p += align_up(n);
+        d_mask[i] = p; p += align_up(nn);
+        d_noise[i] = (float*)p; p += align_up(nn * 8);
+        d_x[i] = (float*)p; p += align_up(n * 4);
+    }
+    float* d_img = (float*)p; p += align_up(n * 4);
+    float* d_y = (float*)p; p += align_up(n * 8);
+    float* d_z = (float*)p; p += align_up(n * 4);
+    float* d_w = (float*)p;
+    // inputs of this slot: free once the compute of the previous call on the slot has finished (done[slot])
+    CUDA_TRY(cudaStreamWaitEvent(si, ev.done[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(d_img8[slot], h_img, n, cudaMemcpyHostToDevice, si));
+    CUDA_TRY(cudaMemcpyAsync(d_mask[slot], h_mask, nn, cudaMemcpyHostToDevice, si));
+    CUDA_TRY(cudaMemcpyAsync(d_noise[slot], h_noise, nn * 8, cudaMemcpyHostToDevice, si));
+    CUDA_TRY(cudaEventRecord(ev.in_ready[slot], si));
+    // compute: needs the inputs, and the slot's output buffer drained by the previous D2H
+    CUDA_TRY(cudaStreamWaitEvent(sc, ev.in_ready[slot], 0));
+    CUDA_TRY(cudaStreamWaitEvent(sc, ev.out_done[slot], 0));
+    u8_to_unit_kernel<float><<<grid_1d(n, d->sm_count), 256, 0, sc>>>(d_img8[slot], d_img, n);
+    LAUNCH_CHECK("u8_to_unit_kernel");
+    rc = acquire_impl<float>(d_img, d_mask[slot], d_noise[slot], d_y, B, N, 0, 0, 0, ws, wsb, sc); if (rc) return rc;
+    rc = solve_impl<float>(d_y, d_mask[slot], d_x[slot], d_z, d_w, B, N, 0, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, sc);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev.done[slot], sc));
+    CUDA_TRY(cudaStreamWaitEvent(so, ev.done[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(h_x, d_x[slot], n * 4, cudaMemcpyDeviceToHost, so));
+    CUDA_TRY(cudaEventRecord(ev.out_done[slot], so));
+    return PNPADMM_OK;
+}
+
+int pnpadmm_reconstruct_host_wait(int slot) {
+    if (slot != 0 && slot != 1) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_wait: slot must be 0 or 1");
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    if (!g_pipe[dev].ready) return PNPADMM_OK;   // nothing was ever enqueued
+    CUDA_TRY(cudaEventSynchronize(g_pipe[dev].out_done[slot]));
+    return PNPADMM_OK;
+}
+
 int pnpadmm_soft_f32(const float* x, float* out, double c, size_t n, pnpadmm_stream_t s) { return soft_impl<float>(x, out, c, n, ST(s)); }
 int pnpadmm_soft_f64(const double* x, double* out, double c, size_t n, pnpadmm_stream_t s) { return soft_impl<double>(x, out, c, n, ST(s)); }
 int pnpadmm_cnc_combine_f32(const float* z, const float* x, const float* w, const float* sd, float* t, double alpha,

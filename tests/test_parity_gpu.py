@@ -316,3 +316,49 @@ def test_device_metrics_sizes_and_errors(pk):
             np.testing.assert_allclose(got[k], want, rtol=1e-10, atol=1e-12)
     with pytest.raises(ValueError):
         pk.image_metrics(torch.zeros((2, 8, 8), device='cuda'), torch.zeros((2, 8, 8), dtype=torch.uint8, device='cuda'))
+
+
+def test_pipelined_host_call_matches_sync_call(pk, cs_inputs):
+    """pnpadmm_reconstruct_host_pipelined_f32 (copies on their own streams, two slots) returns the same
+    reconstructions as the single-stream host call, step after step."""
+    from pnp_admm_cnc_mri_b200 import _abi
+    lib = _abi.load()
+    B, N = 6, 256
+    P = kat.CNC_DEFAULTS
+    imgs = [torch.as_tensor(cs_inputs['images'][k:k + B].copy()).pin_memory() for k in (0, 3, 6, 9)]
+    masks = [torch.as_tensor(cs_inputs['masks'][k].copy()).pin_memory() for k in range(3)]
+    noise = torch.view_as_real(torch.as_tensor(cs_inputs['noises']).to(torch.complex64)).contiguous().pin_memory()
+    solver = pk.AdmmSolver(B, N)
+    st = torch.cuda.current_stream().cuda_stream
+    scratch = torch.empty(lib.pnpadmm_host_scratch_bytes(B, N), dtype=torch.uint8, device='cuda')
+    want = []
+    for i in range(4):
+        hx = torch.empty((B, N, N), dtype=torch.float32).pin_memory()
+        _abi.check(lib.pnpadmm_reconstruct_host_f32(imgs[i].data_ptr(), masks[i % 3].data_ptr(), noise.data_ptr(), hx.data_ptr(),
+                                                    B, N, _abi.PROX_CNC, P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'],
+                                                    _abi.KERNEL_AUTO, scratch.data_ptr(), scratch.numel(), solver.ws.data_ptr(),
+                                                    solver.ws_bytes, st))
+        torch.cuda.synchronize()
+        want.append(hx.clone())
+    ps = torch.empty(lib.pnpadmm_host_pipeline_scratch_bytes(B, N), dtype=torch.uint8, device='cuda')
+    sc, si, so = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    hx2 = [torch.empty((B, N, N), dtype=torch.float32).pin_memory() for _ in range(2)]
+    got = {}
+    for i in range(4):
+        if i >= 2:
+            _abi.check(lib.pnpadmm_reconstruct_host_wait(i & 1))
+            got[i - 2] = hx2[i & 1].clone()
+        _abi.check(lib.pnpadmm_reconstruct_host_pipelined_f32(
+            imgs[i].data_ptr(), masks[i % 3].data_ptr(), noise.data_ptr(), hx2[i & 1].data_ptr(), B, N, _abi.PROX_CNC,
+            P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'], _abi.KERNEL_AUTO, ps.data_ptr(), ps.numel(),
+            solver.ws.data_ptr(), solver.ws_bytes, i & 1, sc.cuda_stream, si.cuda_stream, so.cuda_stream))
+    for i in (2, 3):
+        _abi.check(lib.pnpadmm_reconstruct_host_wait(i & 1))
+        got[i] = hx2[i & 1].clone()
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert torch.equal(got[i], want[i]), i
+    # and against the oracle for one image of the last step
+    xr = orc.admm_cnc(orc.preprocess_uint8(cs_inputs['images'][9]), cs_inputs['masks'][0].astype(np.float64), cs_inputs['noises'], **P)
+    assert rel(got[3][0].numpy(), xr) < TOL32
