@@ -100,12 +100,16 @@ struct ClusterParams {
     int mcode_batched;
     const float* cf;       // [3] device: residual coefficients (written by prepare)
     ProxParams<float> prox;
-    // Chunked static schedule: when P is not a multiple of the resident clusters, each plane's `iters`
-    // are cut into n_chunks pieces of `chunk` iterations; task = chunk * P + plane, cluster k runs tasks
-    // k, k + nclusters, ...  A plane's z, w state is handed from one cluster to the next through global
-    // memory (L2), guarded by progress[plane][rank] (chunks completed, release/acquire at gpu scope).
+    // Chunked schedule: when P is not a multiple of the resident clusters, each plane's `iters` are cut
+    // into n_chunks pieces of `chunk` iterations; task = chunk * P + plane.  Clusters claim tasks in
+    // increasing order from an atomic queue, so the task a chunk depends on (same plane, previous chunk)
+    // was always claimed earlier by a cluster that is running: no deadlock however few clusters are
+    // resident (e.g. when another kernel shares the GPU).  A plane's z, w state is handed from one cluster
+    // to the next through global memory (L2), guarded by progress[plane][rank] (chunks completed,
+    // release/acquire at gpu scope).
     int chunk, n_chunks;
-    int* progress;         // [P][CL], zeroed before the launch (unused when n_chunks == 1)
+    int* progress;         // [P][16], zeroed before the launch
+    int* queue;            // next unclaimed task, zeroed before the launch
     int dbg;               // timing experiments only (results invalid): 1 = no transposes, 2 = no G staging
 };
 
@@ -127,8 +131,6 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x;
     c.smem = smem;
-    const int cluster_id = blockIdx.x / kCluster;
-    const int nclusters = gridDim.x / kCluster;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t bar0 = smem0 + G::kOffBar;
@@ -161,7 +163,18 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
 
     const int mode = (p.prox.prox == PROX_NONE) ? PROX_NONE : prox_mode(p.prox);
     const int ntasks = p.P * p.n_chunks;
-    for (int task = cluster_id; task < ntasks; task += nclusters) {
+    const uint32_t sTask = bar0 + 48;                     // task slot of this CTA (rank 0's is the cluster's)
+    const uint32_t sTask0 = mapa(sTask, 0);
+    for (;;) {
+        if (c.rank == 0 && threadIdx.x == 0) {
+            const int t = atomicAdd(p.queue, 1);
+            asm volatile("st.shared.s32 [%0], %1;" ::"r"(sTask), "r"(t) : "memory");
+        }
+        cluster_sync_all();
+        int task;
+        asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(task) : "r"(sTask0) : "memory");
+        cluster_sync_all();                               // everyone has the task before rank 0 claims the next
+        if (task >= ntasks) break;
         const int plane = task % p.P, chunk = task / p.P;
         const int it0 = chunk * p.chunk;
         const int it1 = (it0 + p.chunk < p.iters) ? it0 + p.chunk : p.iters;

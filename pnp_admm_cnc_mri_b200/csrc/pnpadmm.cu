@@ -54,6 +54,7 @@ struct DeviceState {
     int max_clusters_256 = 0;     // best of the two geometries below
     int max_cl8 = 0, max_cl16 = 0;  // co-resident clusters of the 8-CTA / 16-CTA variants of K1
     int k1_cluster = 8;           // geometry used by default
+    cudaStream_t side = nullptr;  // hybrid schedule: the K2 share of a batch runs here, beside K1
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
@@ -246,6 +247,7 @@ int ensure_device(DeviceState** out) {
             if (n > 0) { d.max_cl8 = n; d.max_cl16 = n; }
         }
         d.max_clusters_256 = d.k1_cluster == 16 ? d.max_cl16 : d.max_cl8;
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
         d.ready = true;
     }
     *out = &d;
@@ -277,7 +279,7 @@ size_t ws_bytes_impl(int B, int N, size_t elt, int mask_batched) {
     s += align_up(P * nn * 2 * elt);         // G
     s += align_up((mask_batched ? P : 1) * nn);
     s += align_up((mask_batched ? P : 1) * nn / 4);   // packed codes (2 bits per bin, 32-bit words)
-    s += align_up(P * 16 * sizeof(int));              // progress counters [P][<=16 ranks]
+    s += align_up((P * 16 + 16) * sizeof(int));       // progress counters [P][<=16 ranks] + task queue
     if (N == 256 && elt == 4) s += align_up(P * nn * 2 * elt);   // Gt (cluster kernel)
     return s;
 }
@@ -300,7 +302,7 @@ int carve(void* ws, size_t ws_bytes, int B, int N, int mask_batched, Workspace<T
     out->G = (cx<T>*)p; p += align_up(P * nn * 2 * sizeof(T));
     out->mcode = p; p += align_up((mask_batched ? P : 1) * nn);
     out->mpack = (uint32_t*)p; p += align_up((mask_batched ? P : 1) * nn / 4);
-    out->progress = (int*)p; p += align_up(P * 16 * sizeof(int));
+    out->progress = (int*)p; p += align_up((P * 16 + 16) * sizeof(int));
     out->Gt = (N == 256 && sizeof(T) == 4) ? (cx<T>*)p : nullptr;
     out->P = (int)P;
     out->solo = mask_batched ? 1 : 0;
@@ -471,7 +473,8 @@ int launch_cluster_t(k1::ClusterParams& cp, int max_clusters, cudaStream_t st) {
         const int n = atoi(e);
         if (n >= 1 && n <= cp.iters) { cp.chunk = (cp.iters + n - 1) / n; cp.n_chunks = (cp.iters + cp.chunk - 1) / cp.chunk; }
     }
-    if (cp.n_chunks > 1) CUDA_TRY(cudaMemsetAsync(cp.progress, 0, sizeof(int) * cp.P * 16, st));
+    CUDA_TRY(cudaMemsetAsync(cp.progress, 0, sizeof(int) * (cp.P * 16 + 16), st));   // hand-off counters + task queue
+    cp.queue = cp.progress + cp.P * 16;
     const long ntasks = (long)cp.P * cp.n_chunks;
     int ncl = ntasks < max_clusters ? (int)ntasks : max_clusters;
     cudaLaunchConfig_t cfg;
@@ -518,6 +521,53 @@ template <> struct ClusterDispatch<float> {
     }
 };
 
+// K2 iteration loop on the planes of `w` (fp32, N in {256, 512, 1024}); `sms` caps the persistent grid of the
+// columns pass (the hybrid schedule runs it on the SMs K1 leaves free).
+template <typename T>
+int stream2_iterate(const Workspace<T>& w, T* x, T* z, T* wv, int B, int N, const ProxParams<T>& pp, int iters, int sms,
+                    cudaStream_t st) {
+    StreamParams<T> p = base_params(w, B, N);
+    p.z = z; p.w = wv; p.x = x; p.prox = pp;
+    S2<T>::template rows<RM_FWD_ZW>(p, w.P, st);
+    for (int it = 0; it < iters; ++it) {
+        S2<T>::template cols<CM_FWD_BLEND_INV>(p, w.P, w.mpack, sms, st);
+        p.last = (it == iters - 1);
+        S2<T>::template rows<RM_INV_PROX_FWD>(p, w.P, st);
+    }
+    LAUNCH_CHECK("K2 iteration kernels");
+    return PNPADMM_OK;
+}
+
+// Hybrid schedule for N = 256: the cluster kernel can only use the SMs that form whole 8-SM groups inside
+// a GPC (112 or 120 of 148); the planes [P1, P) run on the K2 streaming kernels on a side stream and land
+// on the SMs K1 leaves free.  Returns P1 (== P: no split).  Model (fitted on B200, tools/k1_bench.py sweeps in
+// profiles/r1_k1_experiments.txt): K1 takes tau1 = 10.1 us per plane-iteration and cluster; K2 on the leftover
+// SMs takes 11 + 2.7 p2 us per iteration for p2 planes (one wave of `cap` planes has a 21 us latency floor).
+int plan_hybrid(const DeviceState* d, int P, int iters) {
+    static const char* off = getenv("PNPADMM_NO_HYBRID");
+    if (off && atoi(off) != 0) return P;
+    const int ncl = d->max_clusters_256;
+    const int left = d->sm_count - 8 * ncl;
+    const int cap = left / 8;                      // planes per K2 wave: 32 row-CTAs (4 per SM) / 16 col-tiles (2 per SM) per plane
+    if (ncl <= 0 || cap < 1 || iters < 4 || P <= ncl) return P;
+    if (const char* e = getenv("PNPADMM_HYBRID_P2")) {   // experiments: force the K2 share
+        const int p2 = atoi(e);
+        return (p2 >= 0 && p2 < P) ? P - p2 : P;
+    }
+    const double tau1 = 10.1, handoff = 0.35, scale = (double)cap / 4.0;   // constants measured with 36 SMs left (cap = 4)
+    double best = 1e30; int best_p2 = 0;
+    for (int p2 = 0; p2 <= P - ncl && p2 <= P / 3; ++p2) {
+        const int p1 = P - p2;
+        int chunk, nch; plan_chunks(p1, iters, ncl, &chunk, &nch);
+        const long steps = ((long)p1 * nch + ncl - 1) / ncl;
+        const double t1 = steps * (chunk + (nch > 1 ? handoff : 0.0)) * tau1;
+        const double t2 = p2 ? (double)iters * (11.0 + 2.7 * p2 / scale) : 0.0;
+        const double t = t1 > t2 ? t1 : t2;
+        if (t < best - 1e-9) { best = t; best_p2 = p2; }
+    }
+    return P - best_p2;
+}
+
 template <typename T>
 int xupdate_impl(const T* z, const T* wv, T* x, T* xpw, int B, int N, int mask_batched, int kernel, void* ws,
                  size_t ws_bytes, cudaStream_t st) {
@@ -562,20 +612,38 @@ int iterate_impl(T* x, T* z, T* wv, int B, int N, int mask_batched, int prox, in
     bool use_cluster; rc = pick_kernel(kernel, N, sizeof(T) == 8, d, &use_cluster); if (rc) return rc;
     if (iters == 0) return PNPADMM_OK;
     ProxParams<T> pp = make_prox<T>(prox, lambda1, reo, alpha, b);
-    if (use_cluster) return ClusterDispatch<T>::run(w, z, wv, x, z, wv, nullptr, B, iters, pp, d, st);
+    if (use_cluster) {
+        const int P1 = (kernel == PNPADMM_KERNEL_AUTO && S2<T>::ok(N) && aligned16(z) && aligned16(wv) && aligned16(x))
+                           ? plan_hybrid(d, w.P, iters) : w.P;
+        if (P1 == w.P) return ClusterDispatch<T>::run(w, z, wv, x, z, wv, nullptr, B, iters, pp, d, st);
+        // K1 on planes [0, P1) in `st`; K2 on planes [P1, P) in the side stream, joined back into `st`
+        const size_t nn = (size_t)N * N;
+        const int B1 = w.solo ? P1 : 2 * P1;
+        Workspace<T> w1 = w, w2 = w;
+        w1.P = P1;
+        w2.P = w.P - P1;
+        w2.K = w.K + (size_t)P1 * nn; w2.G = w.G + (size_t)P1 * nn;
+        if (w.solo) { w2.mcode = w.mcode + (size_t)P1 * nn; w2.mpack = w.mpack + (size_t)P1 * (nn / 16); }
+        cudaEvent_t fork, join;
+        CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(d->side, fork, 0));
+        rc = ClusterDispatch<T>::run(w1, z, wv, x, z, wv, nullptr, B1, iters, pp, d, st);
+        if (rc == PNPADMM_OK)
+            rc = stream2_iterate<T>(w2, x + (size_t)B1 * nn, z + (size_t)B1 * nn, wv + (size_t)B1 * nn, B - B1, N, pp, iters,
+                                    d->sm_count - 8 * d->max_clusters_256, d->side);
+        CUDA_TRY(cudaEventRecord(join, d->side));
+        CUDA_TRY(cudaStreamWaitEvent(st, join, 0));
+        CUDA_TRY(cudaEventDestroy(fork));
+        CUDA_TRY(cudaEventDestroy(join));
+        return rc;
+    }
 
     StreamParams<T> p = base_params(w, B, N);
     p.z = z; p.w = wv; p.x = x; p.prox = pp;
-    if (S2<T>::ok(N) && aligned16(z) && aligned16(wv) && aligned16(x)) {
-        S2<T>::template rows<RM_FWD_ZW>(p, w.P, st);
-        for (int it = 0; it < iters; ++it) {
-            S2<T>::template cols<CM_FWD_BLEND_INV>(p, w.P, w.mpack, d->sm_count, st);
-            p.last = (it == iters - 1);
-            S2<T>::template rows<RM_INV_PROX_FWD>(p, w.P, st);
-        }
-        LAUNCH_CHECK("K2 iteration kernels");
-        return PNPADMM_OK;
-    }
+    if (S2<T>::ok(N) && aligned16(z) && aligned16(wv) && aligned16(x))
+        return stream2_iterate<T>(w, x, z, wv, B, N, pp, iters, d->sm_count, st);
     const int rl = rows_lines<T>(N), cl = cols_lines<T>(N);
     const size_t rs = rows_smem<T>(N), cs = cols_smem<T>(N);
     p.lines = rl;

@@ -362,3 +362,28 @@ def test_pipelined_host_call_matches_sync_call(pk, cs_inputs):
     # and against the oracle for one image of the last step
     xr = orc.admm_cnc(orc.preprocess_uint8(cs_inputs['images'][9]), cs_inputs['masks'][0].astype(np.float64), cs_inputs['noises'], **P)
     assert rel(got[3][0].numpy(), xr) < TOL32
+
+
+def test_hybrid_schedule_parity(pk, cs_inputs, monkeypatch):
+    """kernel='auto' at N = 256 splits a large batch: most packed planes on the cluster kernel, the rest on the
+    K2 streaming kernels on a side stream (the SMs the clusters cannot use).  Both shares must meet the gate,
+    including the odd tail image, and the forced splits must agree with the pure cluster run."""
+    B = 45                                               # 23 packed planes, last one half empty
+    idx = [i % 15 for i in range(B)]
+    imgs = _imgs(cs_inputs, idx)
+    m = cs_inputs['masks'][1]
+    P = kat.CNC_DEFAULTS
+    ref = {i: orc.admm_cnc(imgs[i], m.astype(np.float64), cs_inputs['noises'], **P) for i in range(15)}
+    pure = pk.admm_solve(imgs, m, cs_inputs['noises'], prox='cnc', kernel='cluster', **P)
+    for p2 in ('3', '7', None):                          # forced K2 shares, then the planner's own choice
+        if p2 is None:
+            monkeypatch.delenv('PNPADMM_HYBRID_P2', raising=False)
+        else:
+            monkeypatch.setenv('PNPADMM_HYBRID_P2', p2)
+        x = pk.admm_solve(imgs, m, cs_inputs['noises'], prox='cnc', kernel='auto', **P)
+        for k in range(B):
+            assert rel(x[k], ref[idx[k]]) < TOL32, (p2, k)
+        assert rel(x, pure) < 2e-5
+        if p2 is not None:                               # the K1 share is bit-identical to the pure cluster run
+            n1 = 2 * (23 - int(p2))
+            assert np.array_equal(x[:n1], pure[:n1])

@@ -24,7 +24,7 @@ for B in Bs:
             z = z0.clone(); w = torch.zeros_like(z0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(); e0.record()
-            s.iterate(x, z, w, prox, 50, 0.5, 0.05, 0.45, 64, kernel='cluster')
+            s.iterate(x, z, w, prox, 50, 0.5, 0.05, 0.45, 64, kernel=os.environ.get('K1B_KERNEL', 'cluster'))
             e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         t = float(np.median(ts[2:]))
         its = B * 50 / (t * 1e-3)
