@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
 
     const int mode = (p.prox.prox == PROX_NONE) ? PROX_NONE : prox_mode(p.prox);
     const int ntasks = p.P * p.n_chunks;
+    if ((p.dbg >> 8) && ((blockIdx.x / kCluster) & 1)) {   // experiment: stagger odd clusters by (dbg >> 8) us
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)(p.dbg >> 8) * 1965) {}
+    }
     const uint32_t sTask = bar0 + 48;                     // task slot of this CTA (rank 0's is the cluster's)
     const uint32_t sTask0 = mapa(sTask, 0);
     for (;;) {

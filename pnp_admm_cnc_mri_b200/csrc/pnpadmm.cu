@@ -483,13 +483,20 @@ int launch_cluster_t(k1::ClusterParams& cp, int max_clusters, cudaStream_t st) {
     cfg.blockDim = dim3(G::kThreads);
     cfg.dynamicSmemBytes = G::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (const char* e = getenv("PNPADMM_K1_POLICY")) {   // experiments: 1 = spread, 2 = load balancing
+        attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+        attr[1].val.clusterSchedulingPolicyPreference =
+            atoi(e) == 2 ? cudaClusterSchedulingPolicyLoadBalancing : cudaClusterSchedulingPolicySpread;
+        cfg.numAttrs = 2;
+    }
+    if (const char* e = getenv("PNPADMM_K1_STAGGER")) cp.dbg = atoi(e) << 8;   // experiments: start delay of odd clusters (us)
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_kernel<CL>, (const k1::ClusterParams)cp));
     return PNPADMM_OK;
 }
