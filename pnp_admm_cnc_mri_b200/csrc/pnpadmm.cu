@@ -229,6 +229,9 @@ int ensure_device(DeviceState** out) {
         }
         CUDA_TRY(cudaMemcpyToSymbol(g_tw_f32, tf.data(), sizeof(float2) * kTwMax));
         CUDA_TRY(cudaMemcpyToSymbol(g_tw_f64, td.data(), sizeof(double2) * kTwMax));
+        std::vector<float2> t256(256);
+        for (int i = 0; i < 256; ++i) t256[i] = tf[((i >> 4) * (i & 15) * 16) & (kTwMax - 1)];   // = k1::fill_tw
+        CUDA_TRY(cudaMemcpyToSymbol(s2::g_tw256, t256.data(), sizeof(float2) * 256));
         CUDA_TRY(set_stream_attrs<float>());
         CUDA_TRY(set_stream_attrs<double>());
         CUDA_TRY(S2<float>::set_attrs());

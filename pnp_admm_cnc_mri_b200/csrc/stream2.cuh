@@ -62,10 +62,8 @@ template <int T, bool COLS> PNP_D void line_sync() {
     if (!COLS && T <= 32) __syncwarp(); else __syncthreads();
 }
 
-PNP_D void fill_tw256(cf32* TW, int tid, int nthreads) {
-    const cf32* m = reinterpret_cast<const cf32*>(g_tw_f32);
-    for (int i = tid; i < 256; i += nthreads) k1::fill_tw(TW, m, i);
-}
+// TW256[i * 16 + k] = W_256^(i k), contiguous in global memory so that it is staged with the tile copies
+__device__ __align__(128) float2 g_tw256[256];
 
 // one 1-D transform of my line, registers -> registers (n = t + T m layout on both sides)
 template <bool INV, int N, bool COLS, class Line>
@@ -117,7 +115,9 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
         if (kLoadK) bytes += L * kRowBytes;
         if (kLoadZW) bytes += (has_b ? 4 : 2) * kRealBytes;
         if (MODE == RM_FWD_IMG) bytes += kRealBytes;
+        bytes += 256 * 8;
         k1::mbar_arm_tx(bar, bytes);
+        bulk_g2s(smem0 + G::kOffTW, g_tw256, 256 * 8, bar);
         if (kLoadK) {
             const cf32* src = (MODE == RM_INV_ABS ? p.cin : p.K) + tile_off;
 #pragma unroll
@@ -133,8 +133,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
         }
         if (MODE == RM_FWD_IMG) bulk_g2s(smem0 + G::kOffZW, p.img + tile_off, kRealBytes, bar);
     }
-    fill_tw256(TW, tid, kRowsThreads);
-    __syncthreads();
+    __syncthreads();                        // barrier initialised before anyone waits on it
     k1::mbar_wait(bar, 0);
 
     RowLine ln;
@@ -257,7 +256,7 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
         }
     };
 
-    fill_tw256(TW, tid, NT);
+    if (tid < 128) cp_async16(smem0 + 3 * TE * 8 + tid * 16, reinterpret_cast<const unsigned char*>(g_tw256) + tid * 16);
     int tile = blockIdx.x;
     if (tile < ntiles) issue_tile(in, tile, smem0, true);
     cp_async_commit();

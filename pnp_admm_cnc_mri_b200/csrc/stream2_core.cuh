@@ -29,6 +29,13 @@ namespace s2 {
 
 using k1::cf32;
 
+// read-only twiddle load (non-coherent path on the device)
+#if defined(__CUDA_ARCH__)
+PNP_D cf32 ld_tw(const cf32* p) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return mk<float>(v.x, v.y); }
+#else
+inline cf32 ld_tw(const cf32* p) { return *p; }
+#endif
+
 template <int N>
 struct Plan {
     static_assert(N == 256 || N == 512 || N == 1024, "K2 register-FFT kernels: N in {256, 512, 1024}");
@@ -91,7 +98,7 @@ PNP_HD void stage3(cf32 (&a)[16], int t, const Line& ln, const cf32* twN, int tw
 #pragma unroll
         for (int u = 0; u < NB3; ++u) {
             const int j = t + T * u;
-            const cf32 v1 = twmul<INV>(a[u + NB3], twN[j * tw_stride]);
+            const cf32 v1 = twmul<INV>(a[u + NB3], ld_tw(twN + j * tw_stride));
             const cf32 v0 = a[u];
             a[u] = v0 + v1;
             a[u + NB3] = v0 - v1;
@@ -100,9 +107,9 @@ PNP_HD void stage3(cf32 (&a)[16], int t, const Line& ln, const cf32* twN, int tw
 #pragma unroll
         for (int u = 0; u < NB3; ++u) {
             const int j = t + T * u;
-            const cf32 v1 = twmul<INV>(a[u + NB3], twN[j * tw_stride]);
-            const cf32 v2 = twmul<INV>(a[u + 2 * NB3], twN[2 * j * tw_stride]);
-            const cf32 v3 = twmul<INV>(a[u + 3 * NB3], twN[3 * j * tw_stride]);
+            const cf32 v1 = twmul<INV>(a[u + NB3], ld_tw(twN + j * tw_stride));
+            const cf32 v2 = twmul<INV>(a[u + 2 * NB3], ld_tw(twN + 2 * j * tw_stride));
+            const cf32 v3 = twmul<INV>(a[u + 3 * NB3], ld_tw(twN + 3 * j * tw_stride));
             k1::dft4<INV>(a[u], v1, v2, v3, a[u], a[u + NB3], a[u + 2 * NB3], a[u + 3 * NB3]);
         }
     }
