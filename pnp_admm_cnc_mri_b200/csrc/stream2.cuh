@@ -29,9 +29,12 @@ namespace s2 {
 constexpr int kRowsThreads = 128;
 
 template <int N> struct ColsGeo {
-    static constexpr int C = (N == 1024) ? 8 : 16;          // columns per tile
+#ifndef PNP_COLS512_C
+#define PNP_COLS512_C 8
+#endif
+    static constexpr int C = (N == 1024) ? 8 : (N == 512 ? PNP_COLS512_C : 16);   // columns per tile
     static constexpr int kThreads = C * Plan<N>::T;          // 256 (N = 256) or 512
-    static constexpr int kCtasPerSm = (N == 256) ? 2 : 1;
+    static constexpr int kCtasPerSm = (N == 256 || kThreads == 256) ? 2 : 1;
     static constexpr int kTileElems = N * C;
     static constexpr int kSmemBytes = 3 * kTileElems * 8 + 256 * 8;   // 2 K slots + G slot + TW256
 };
@@ -42,7 +45,7 @@ template <int N> struct RowsGeo {
     static constexpr int kOffZW = L * kPitch * 8;
     static constexpr int kOffTW = kOffZW + 4 * L * N * 4;
     static constexpr int kOffBar = kOffTW + 256 * 8;
-    static constexpr int kSmemBytes = kOffBar + 16;
+    static constexpr int kSmemBytes = kOffBar + 16;   // two mbarriers: K rows + twiddles, z / w (or img) rows
 };
 
 PNP_D void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -108,15 +111,17 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
 
     constexpr bool kLoadK = (MODE == RM_INV_PROX_FWD || MODE == RM_INV_X || MODE == RM_INV_ABS);
     constexpr bool kLoadZW = (MODE == RM_INV_PROX_FWD || MODE == RM_INV_X || MODE == RM_FWD_ZW);
+    const uint32_t bar2 = bar + 8;          // z / w / img rows: needed only after the inverse transform
     if (tid == 0) {
         k1::mbar_init(bar, 1);
+        k1::mbar_init(bar2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        uint32_t bytes = 0;
+        uint32_t bytes = 256 * 8, bytes2 = 0;
         if (kLoadK) bytes += L * kRowBytes;
-        if (kLoadZW) bytes += (has_b ? 4 : 2) * kRealBytes;
-        if (MODE == RM_FWD_IMG) bytes += kRealBytes;
-        bytes += 256 * 8;
+        if (kLoadZW) bytes2 += (has_b ? 4 : 2) * kRealBytes;
+        if (MODE == RM_FWD_IMG) bytes2 += kRealBytes;
         k1::mbar_arm_tx(bar, bytes);
+        if (bytes2) k1::mbar_arm_tx(bar2, bytes2);
         bulk_g2s(smem0 + G::kOffTW, g_tw256, 256 * 8, bar);
         if (kLoadK) {
             const cf32* src = (MODE == RM_INV_ABS ? p.cin : p.K) + tile_off;
@@ -124,14 +129,14 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
             for (int l = 0; l < L; ++l) bulk_g2s(smem0 + l * G::kPitch * 8, src + (size_t)l * N, kRowBytes, bar);
         }
         if (kLoadZW) {
-            bulk_g2s(smem0 + G::kOffZW, p.z + offa, kRealBytes, bar);
-            bulk_g2s(smem0 + G::kOffZW + kRealBytes, p.w + offa, kRealBytes, bar);
+            bulk_g2s(smem0 + G::kOffZW, p.z + offa, kRealBytes, bar2);
+            bulk_g2s(smem0 + G::kOffZW + kRealBytes, p.w + offa, kRealBytes, bar2);
             if (has_b) {
-                bulk_g2s(smem0 + G::kOffZW + 2 * kRealBytes, p.z + offb, kRealBytes, bar);
-                bulk_g2s(smem0 + G::kOffZW + 3 * kRealBytes, p.w + offb, kRealBytes, bar);
+                bulk_g2s(smem0 + G::kOffZW + 2 * kRealBytes, p.z + offb, kRealBytes, bar2);
+                bulk_g2s(smem0 + G::kOffZW + 3 * kRealBytes, p.w + offb, kRealBytes, bar2);
             }
         }
-        if (MODE == RM_FWD_IMG) bulk_g2s(smem0 + G::kOffZW, p.img + tile_off, kRealBytes, bar);
+        if (MODE == RM_FWD_IMG) bulk_g2s(smem0 + G::kOffZW, p.img + tile_off, kRealBytes, bar2);
     }
     __syncthreads();                        // barrier initialised before anyone waits on it
     k1::mbar_wait(bar, 0);
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
         line_sync<T, false>();                     // landing layout fully read before the padded layout is written
         fft_regs<true, N, false>(a, t, ln, TW);
     }
+    if (kLoadZW || MODE == RM_FWD_IMG) k1::mbar_wait(bar2, 0);
 
     if (MODE == RM_INV_ABS) {               // zero-filled reconstruction |ifft2(y)|          (S1:100)
 #pragma unroll
@@ -245,28 +251,30 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
     const float cf1 = (MODE == CM_FWD_BLEND_INV) ? p.cf[1] : 0.f, cf2 = (MODE == CM_FWD_BLEND_INV) ? p.cf[2] : 0.f;
 
     // tile copy: N rows x (C * 8) bytes = N * C / 2 pieces of 16 bytes, 8 per thread
-    auto issue_tile = [&](const cf32* base, int tile, uint32_t dst, bool batched) {
+    // `permute`: land the rows in the ColLine order (K tiles); the G / noise tile is read in natural order
+    auto issue_tile = [&](const cf32* base, int tile, uint32_t dst, bool batched, bool permute) {
         const int plane = tile / tiles_per_plane, c0 = (tile - plane * tiles_per_plane) * C;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(base + (batched ? (size_t)plane * nn : 0) + c0);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int q = tid + NT * e;
             const int row = q / (C / 2), part = q % (C / 2);
-            cp_async16(dst + (uint32_t)(row * C * 8 + part * 16), src + (size_t)row * N * 8 + part * 16);
+            const int prow = permute ? col_phys_row<C>(row) : row;
+            cp_async16(dst + (uint32_t)(prow * C * 8 + part * 16), src + (size_t)row * N * 8 + part * 16);
         }
     };
 
     if (tid < 128) cp_async16(smem0 + 3 * TE * 8 + tid * 16, reinterpret_cast<const unsigned char*>(g_tw256) + tid * 16);
     int tile = blockIdx.x;
-    if (tile < ntiles) issue_tile(in, tile, smem0, true);
+    if (tile < ntiles) issue_tile(in, tile, smem0, true, true);
     cp_async_commit();
     for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it & 1;
         const int plane = tile / tiles_per_plane, c0 = (tile - plane * tiles_per_plane) * C;
-        if (MODE != CM_INV) issue_tile(aux, tile, smem0 + 2 * TE * 8, aux_batched);
+        if (MODE != CM_INV) issue_tile(aux, tile, smem0 + 2 * TE * 8, aux_batched, false);
         cp_async_commit();
         const int next = tile + gridDim.x;
-        if (next < ntiles) issue_tile(in, next, smem0 + (uint32_t)((s ^ 1) * TE * 8), true);
+        if (next < ntiles) issue_tile(in, next, smem0 + (uint32_t)((s ^ 1) * TE * 8), true, true);
         cp_async_commit();
         uint32_t codes = 0;
         if (MODE == CM_FWD_BLEND_INV) codes = mpack[(p.mcode_batched ? (size_t)plane * (nn / 16) : 0) + (size_t)t * N + c0 + c];

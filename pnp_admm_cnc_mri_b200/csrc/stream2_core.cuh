@@ -51,11 +51,16 @@ struct RowLine {
     PNP_HD cf32& raw(int idx) const { return line[idx]; }
 };
 
+// With C = 8 a row is 64 B = half of the banks, and the stage-1 stores of a warp (rows 16 t + i for four
+// consecutive t) would all land on the same half: rows are stored at row ^ ((row >> 4) & 1), which alternates
+// the half with t and keeps every group of four consecutive rows contiguous (all other accesses).
+template <int C> PNP_HD int col_phys_row(int row) { return C == 8 ? (row ^ ((row >> 4) & 1)) : row; }
+
 template <int C>
 struct ColLine {
     cf32* col;   // tile + c
-    PNP_HD cf32& at(int idx) const { return col[idx * C]; }
-    PNP_HD cf32& raw(int idx) const { return col[idx * C]; }
+    PNP_HD cf32& at(int idx) const { return col[col_phys_row<C>(idx) * C]; }
+    PNP_HD cf32& raw(int idx) const { return col[col_phys_row<C>(idx) * C]; }
 };
 
 // stage 1: registers (n = t + T i) -> fft16 -> shared
