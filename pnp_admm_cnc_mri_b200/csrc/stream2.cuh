@@ -32,7 +32,10 @@ template <int N> struct ColsGeo {
 #ifndef PNP_COLS512_C
 #define PNP_COLS512_C 8
 #endif
-    static constexpr int C = (N == 1024) ? 8 : (N == 512 ? PNP_COLS512_C : 16);   // columns per tile
+#ifndef PNP_COLS1024_C
+#define PNP_COLS1024_C 8
+#endif
+    static constexpr int C = (N == 1024) ? PNP_COLS1024_C : (N == 512 ? PNP_COLS512_C : 16);   // columns per tile
     static constexpr int kThreads = C * Plan<N>::T;          // 256 (N = 256) or 512
     static constexpr int kCtasPerSm = (N == 256 || kThreads == 256) ? 2 : 1;
     static constexpr int kTileElems = N * C;

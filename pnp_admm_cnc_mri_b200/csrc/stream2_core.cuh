@@ -54,7 +54,7 @@ struct RowLine {
 // With C = 8 a row is 64 B = half of the banks, and the stage-1 stores of a warp (rows 16 t + i for four
 // consecutive t) would all land on the same half: rows are stored at row ^ ((row >> 4) & 1), which alternates
 // the half with t and keeps every group of four consecutive rows contiguous (all other accesses).
-template <int C> PNP_HD int col_phys_row(int row) { return C == 8 ? (row ^ ((row >> 4) & 1)) : row; }
+template <int C> PNP_HD int col_phys_row(int row) { return C == 8 ? (row ^ ((row >> 4) & 1)) : (C == 4 ? (row ^ ((row >> 4) & 3)) : row); }
 
 template <int C>
 struct ColLine {
