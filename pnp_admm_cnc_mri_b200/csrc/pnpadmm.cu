@@ -551,7 +551,7 @@ int stream2_iterate(const Workspace<T>& w, T* x, T* z, T* wv, int B, int N, cons
 // Hybrid schedule for N = 256: the cluster kernel can only use the SMs that form whole 8-SM groups inside
 // a GPC (112 or 120 of 148); the planes [P1, P) run on the K2 streaming kernels on a side stream and land
 // on the SMs K1 leaves free.  Returns P1 (== P: no split).  Model (fitted on B200, tools/k1_bench.py sweeps in
-// profiles/r1_k1_experiments.txt): K1 takes tau1 = 10.1 us per plane-iteration and cluster; K2 on the leftover
+// profiles/r1_experiments.txt): K1 takes tau1 = 10.1 us per plane-iteration and cluster; K2 on the leftover
 // SMs takes 11 + 2.7 p2 us per iteration for p2 planes (one wave of `cap` planes has a 21 us latency floor).
 int plan_hybrid(const DeviceState* d, int P, int iters) {
     static const char* off = getenv("PNPADMM_NO_HYBRID");
