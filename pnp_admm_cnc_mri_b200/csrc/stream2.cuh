@@ -39,7 +39,8 @@ template <int N> struct ColsGeo {
     static constexpr int kThreads = C * Plan<N>::T;          // 256 (N = 256) or 512
     static constexpr int kCtasPerSm = (N == 256 || kThreads == 256) ? 2 : 1;
     static constexpr int kTileElems = N * C;
-    static constexpr int kSmemBytes = 3 * kTileElems * 8 + 256 * 8;   // 2 K slots + G slot + TW256
+    static constexpr int kTw3Bytes = (Plan<N>::R3 - 1) * 256 * 8;                  // stage-3 twiddle table
+    static constexpr int kSmemBytes = 3 * kTileElems * 8 + 256 * 8 + kTw3Bytes;   // 2 K slots + G slot + TW256 + TW3
 };
 template <int N> struct RowsGeo {
     static constexpr int T = Plan<N>::T;
@@ -72,8 +73,8 @@ template <int T, bool COLS> PNP_D void line_sync() {
 __device__ __align__(128) float2 g_tw256[256];
 
 // one 1-D transform of my line, registers -> registers (n = t + T m layout on both sides)
-template <bool INV, int N, bool COLS, class Line>
-PNP_D void fft_regs(cf32 (&a)[16], int t, const Line& ln, const cf32* TW) {
+template <bool INV, int N, bool COLS, class Line, class Tw3>
+PNP_D void fft_regs(cf32 (&a)[16], int t, const Line& ln, const cf32* TW, const Tw3& tw3) {
     constexpr int T = Plan<N>::T;
     stage1_store<INV, N>(a, t, ln);
     line_sync<T, COLS>();
@@ -82,7 +83,7 @@ PNP_D void fft_regs(cf32 (&a)[16], int t, const Line& ln, const cf32* TW) {
         line_sync<T, COLS>();
         stage2_store<N>(a, t, ln);
         line_sync<T, COLS>();
-        stage3<INV, N>(a, t, ln, reinterpret_cast<const cf32*>(g_tw_f32), kTwMax / N);
+        stage3<INV, N>(a, t, ln, tw3);
     }
 }
 
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
 
     RowLine ln;
     ln.line = Ks + line * G::kPitch;
+    const Tw3Master tw3{reinterpret_cast<const cf32*>(g_tw_f32), kTwMax / N};
     const float* za_s = zw + line * N;
     const float* wa_s = za_s + L * N;
     const float* zb_s = wa_s + L * N;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
 #pragma unroll
         for (int m = 0; m < 16; ++m) a[m] = ln.raw(t + T * m);
         line_sync<T, false>();                     // landing layout fully read before the padded layout is written
-        fft_regs<true, N, false>(a, t, ln, TW);
+        fft_regs<true, N, false>(a, t, ln, TW, tw3);
     }
     if (kLoadZW || MODE == RM_FWD_IMG) k1::mbar_wait(bar2, 0);
 
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
 #pragma unroll
         for (int m = 0; m < 16; ++m) a[m] = mk<float>(za_s[t + T * m], 0.f);
     }
-    fft_regs<false, N, false>(a, t, ln, TW);
+    fft_regs<false, N, false>(a, t, ln, TW, tw3);
     cf32* out = (MODE == RM_FWD_IMG ? p.cout : p.K) + gk;
 #pragma unroll
     for (int m = 0; m < 16; ++m) out[t + T * m] = a[m];
@@ -268,6 +270,11 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
     };
 
     if (tid < 128) cp_async16(smem0 + 3 * TE * 8 + tid * 16, reinterpret_cast<const unsigned char*>(g_tw256) + tid * 16);
+    // stage-3 twiddles W_N^(i j) (N > 256) into shared memory once per CTA (visible after the first tile barrier)
+    cf32* TW3 = TW + 256;
+    for (int q = tid; q < (Plan<N>::R3 - 1) * 256; q += NT)
+        TW3[q] = ld_tw(reinterpret_cast<const cf32*>(g_tw_f32) + ((q >> 8) + 1) * (q & 255) * (kTwMax / N));
+    const Tw3Table tw3{TW3};
     int tile = blockIdx.x;
     if (tile < ntiles) issue_tile(in, tile, smem0, true, true);
     cp_async_commit();
@@ -291,9 +298,9 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
         for (int m = 0; m < 16; ++m) a[m] = ln.raw(t + T * m);
         __syncthreads();                     // tile fully read before it is reused as exchange scratch
         if (MODE == CM_INV) {
-            fft_regs<true, N, true>(a, t, ln, TW);
+            fft_regs<true, N, true>(a, t, ln, TW, tw3);
         } else {
-            fft_regs<false, N, true>(a, t, ln, TW);
+            fft_regs<false, N, true>(a, t, ln, TW, tw3);
             cp_async_wait<1>();
             __syncthreads();                 // G / noise tile landed; forward-transform scratch reads done
             const cf32* g = Gs + c;
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
                     const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
                     a[m] = mk<float>(gg.re - cf * a[m].re, gg.im - cf * a[m].im);
                 }
-                fft_regs<true, N, true>(a, t, ln, TW);
+                fft_regs<true, N, true>(a, t, ln, TW, tw3);
             } else {   // CM_FWD_ACQ: y = fft2(img) * mask + noises                         (S1:99)
                 const uint8_t* mk8 = p.mask + (p.mask_batched ? (size_t)plane * nn : 0) + c0 + c;
 #pragma unroll

@@ -93,9 +93,19 @@ PNP_HD void stage2_store(const cf32 (&a)[16], int t, const Line& ln) {
     for (int i = 0; i < 16; ++i) ln.at(base + 16 * i) = a[i];
 }
 
-// N > 256 only: stage 3.  twN[m * tw_stride] = W_N^m (the master table W_4096 with stride 4096 / N).
-template <bool INV, int N, class Line>
-PNP_HD void stage3(cf32 (&a)[16], int t, const Line& ln, const cf32* twN, int tw_stride) {
+// stage-3 twiddle sources: W_N^(i j), j < 256, i < R3
+struct Tw3Master {          // the master table W_4096^m in global memory (stride 4096 / N), read-only path
+    const cf32* m; int stride;
+    PNP_HD cf32 get(int i, int j) const { return ld_tw(m + i * j * stride); }
+};
+struct Tw3Table {           // a [R3 - 1][256] table in shared memory: tab[(i - 1) * 256 + j]
+    const cf32* tab;
+    PNP_HD cf32 get(int i, int j) const { return tab[(i - 1) * 256 + j]; }
+};
+
+// N > 256 only: stage 3.
+template <bool INV, int N, class Line, class Tw3>
+PNP_HD void stage3(cf32 (&a)[16], int t, const Line& ln, const Tw3& tw) {
     constexpr int T = Plan<N>::T, R3 = Plan<N>::R3, NB3 = Plan<N>::NB3;
 #pragma unroll
     for (int m = 0; m < 16; ++m) a[m] = ln.at(t + T * m);
@@ -103,7 +113,7 @@ PNP_HD void stage3(cf32 (&a)[16], int t, const Line& ln, const cf32* twN, int tw
 #pragma unroll
         for (int u = 0; u < NB3; ++u) {
             const int j = t + T * u;
-            const cf32 v1 = twmul<INV>(a[u + NB3], ld_tw(twN + j * tw_stride));
+            const cf32 v1 = twmul<INV>(a[u + NB3], tw.get(1, j));
             const cf32 v0 = a[u];
             a[u] = v0 + v1;
             a[u + NB3] = v0 - v1;
@@ -112,9 +122,9 @@ PNP_HD void stage3(cf32 (&a)[16], int t, const Line& ln, const cf32* twN, int tw
 #pragma unroll
         for (int u = 0; u < NB3; ++u) {
             const int j = t + T * u;
-            const cf32 v1 = twmul<INV>(a[u + NB3], ld_tw(twN + j * tw_stride));
-            const cf32 v2 = twmul<INV>(a[u + 2 * NB3], ld_tw(twN + 2 * j * tw_stride));
-            const cf32 v3 = twmul<INV>(a[u + 3 * NB3], ld_tw(twN + 3 * j * tw_stride));
+            const cf32 v1 = twmul<INV>(a[u + NB3], tw.get(1, j));
+            const cf32 v2 = twmul<INV>(a[u + 2 * NB3], tw.get(2, j));
+            const cf32 v3 = twmul<INV>(a[u + 3 * NB3], tw.get(3, j));
             k1::dft4<INV>(a[u], v1, v2, v3, a[u], a[u + NB3], a[u + 2 * NB3], a[u + 3 * NB3]);
         }
     }

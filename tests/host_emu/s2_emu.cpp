@@ -37,7 +37,7 @@ double run(MakeLine make, unsigned seed) {
     for (int t = 0; t < T; ++t) stage2_load<INV, N>(R(t), t, make(), tw256.data());
     if (PL::R3 > 1) {
         for (int t = 0; t < T; ++t) stage2_store<N>(R(t), t, make());
-        for (int t = 0; t < T; ++t) stage3<INV, N>(R(t), t, make(), tw4096.data(), 4096 / N);
+        for (int t = 0; t < T; ++t) stage3<INV, N>(R(t), t, make(), Tw3Master{tw4096.data(), 4096 / N});
     }
     double num = 0, den = 0;
     for (int t = 0; t < T; ++t)
