@@ -534,18 +534,102 @@ template <> struct ClusterDispatch<float> {
 // K2 iteration loop on the planes of `w` (fp32, N in {256, 512, 1024}); `sms` caps the persistent grid of the
 // columns pass (the hybrid schedule runs it on the SMs K1 leaves free).
 template <typename T>
+int stream2_launch_sequence(const StreamParams<T>& p0, int planes, const uint32_t* mpack, int iters, int sms, cudaStream_t st) {
+    StreamParams<T> p = p0;
+    S2<T>::template rows<RM_FWD_ZW>(p, planes, st);
+    for (int it = 0; it < iters; ++it) {
+        S2<T>::template cols<CM_FWD_BLEND_INV>(p, planes, mpack, sms, st);
+        p.last = (it == iters - 1);
+        S2<T>::template rows<RM_INV_PROX_FWD>(p, planes, st);
+    }
+    LAUNCH_CHECK("K2 iteration kernels");
+    return PNPADMM_OK;
+}
+
+// The sequence is 2 * iters + 1 launches with fixed arguments: it is captured once per configuration into a
+// CUDA graph (small per-device cache keyed by every kernel argument) and replayed with one launch, so a caller
+// that reconstructs batch after batch through the same buffers spends ~10 us of host time per call instead of
+// ~0.4 ms.  Skipped when the caller is itself capturing the stream, or with PNPADMM_NO_GRAPH=1.
+struct K2GraphKey {
+    StreamParams<float> p;
+    const uint32_t* mpack;
+    int planes, iters, sms, pad;
+};
+struct K2GraphEntry {
+    bool valid = false;
+    K2GraphKey key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long stamp = 0;
+};
+constexpr int kGraphSlots = 6;
+K2GraphEntry g_k2graphs[kMaxDevices][kGraphSlots];
+unsigned long long g_graph_clock = 0;
+
+template <typename T>
+int stream2_replay(const StreamParams<T>& p, int planes, const uint32_t* mpack, int iters, int sms, cudaStream_t st) {
+    return stream2_launch_sequence<T>(p, planes, mpack, iters, sms, st);
+}
+template <>
+int stream2_replay<float>(const StreamParams<float>& p, int planes, const uint32_t* mpack, int iters, int sms, cudaStream_t st) {
+    static const char* off = getenv("PNPADMM_NO_GRAPH");
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if ((off && atoi(off) != 0) || iters < 4 || cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return stream2_launch_sequence<float>(p, planes, mpack, iters, sms, st);
+    }
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    K2GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.p = p; key.mpack = mpack; key.planes = planes; key.iters = iters; key.sms = sms;
+    std::lock_guard<std::mutex> lk(g_mu);
+    K2GraphEntry* slot = nullptr;
+    K2GraphEntry* victim = nullptr;
+    for (int i = 0; i < kGraphSlots; ++i) {
+        K2GraphEntry& e = g_k2graphs[dev][i];
+        if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) { slot = &e; break; }
+        if (!victim || (victim->valid && (!e.valid || e.stamp < victim->stamp))) victim = &e;
+    }
+    if (!slot) {
+        // the legacy default stream cannot be captured: launch directly there
+        if (st == nullptr || st == cudaStreamLegacy) return stream2_launch_sequence<float>(p, planes, mpack, iters, sms, st);
+        slot = victim;
+        if (slot->valid) {   // evict before the capture starts (graph destruction is not a capture-safe call)
+            (void)cudaGraphExecDestroy(slot->exec);
+            (void)cudaGraphDestroy(slot->graph);
+            slot->valid = false;
+        }
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return stream2_launch_sequence<float>(p, planes, mpack, iters, sms, st);
+        }
+        const int rc = stream2_launch_sequence<float>(p, planes, mpack, iters, sms, st);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e_end = cudaStreamEndCapture(st, &g);
+        if (rc != PNPADMM_OK || e_end != cudaSuccess || !g) {
+            if (g) (void)cudaGraphDestroy(g);
+            (void)cudaGetLastError();
+            return rc != PNPADMM_OK ? rc : fail(PNPADMM_ERR_CUDA, "capturing the K2 launch sequence failed: %s", cudaGetErrorString(e_end));
+        }
+        cudaGraphExec_t ex = nullptr;
+        const cudaError_t e_inst = cudaGraphInstantiate(&ex, g, 0);
+        if (e_inst != cudaSuccess) {
+            (void)cudaGraphDestroy(g);
+            return fail(PNPADMM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e_inst));
+        }
+        slot->key = key; slot->graph = g; slot->exec = ex; slot->valid = true;
+    }
+    slot->stamp = ++g_graph_clock;
+    CUDA_TRY(cudaGraphLaunch(slot->exec, st));
+    return PNPADMM_OK;
+}
+
+template <typename T>
 int stream2_iterate(const Workspace<T>& w, T* x, T* z, T* wv, int B, int N, const ProxParams<T>& pp, int iters, int sms,
                     cudaStream_t st) {
     StreamParams<T> p = base_params(w, B, N);
     p.z = z; p.w = wv; p.x = x; p.prox = pp;
-    S2<T>::template rows<RM_FWD_ZW>(p, w.P, st);
-    for (int it = 0; it < iters; ++it) {
-        S2<T>::template cols<CM_FWD_BLEND_INV>(p, w.P, w.mpack, sms, st);
-        p.last = (it == iters - 1);
-        S2<T>::template rows<RM_INV_PROX_FWD>(p, w.P, st);
-    }
-    LAUNCH_CHECK("K2 iteration kernels");
-    return PNPADMM_OK;
+    return stream2_replay<T>(p, w.P, w.mpack, iters, sms, st);
 }
 
 // Hybrid schedule for N = 256: the cluster kernel can only use the SMs that form whole 8-SM groups inside
