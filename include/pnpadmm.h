@@ -204,6 +204,30 @@ int pnpadmm_metrics_f64(const double* x, const uint8_t* ref, int B, int N, int q
                         size_t scratch_bytes, pnpadmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * a9  DnCNN / FDnCNN denoiser forward on the tensor cores (reference
+ * models/network_dncnn.py:36-67 DnCNN.forward = x - model(x), :120-141 FDnCNN.forward = model(x);
+ * called from denoising_step S6:353-359, denoising_step1 S3:20-35, denoising_step2 S6:19-34):
+ *     conv3x3 cin->64 + ReLU,  n_mid x [conv3x3 64->64 + ReLU],  conv3x3 64->1      (nb = n_mid + 2)
+ * bf16 operands, fp32 accumulation (tcgen05 / TMEM), bf16 NHWC activations between layers,
+ * zero padding 1, bias in every layer (act_mode 'R': no batch norm).
+ *   x      [B][cin][H][W] f32 (cin = 1 DnCNN, 2 FDnCNN: noise-level map in channel 1)
+ *   out    [B][H][W] f32:  residual != 0 ? x[:, 0] - n(x) : n(x)
+ *   w_head [64][cin][3][3] f32 (values already rounded to bf16), b_head [64] f32
+ *   w_mid  n_mid x [tap = ky*3+kx][c_in / 8][c_out 64][c_in % 8] bf16 (73 728 B per layer), b_mid [n_mid][64] f32
+ *   w_tail [tap][c_in / 8][16][c_in % 8] bf16, rows 1..15 zero;  b_tail [1] f32
+ *   act0, act1: two device buffers of pnpadmm_dncnn_activation_bytes(B, H, W) bytes, 16-byte aligned.
+ * pnpadmm_conv64_bf16 runs ONE 64->64 layer (in / out [B][H][W][64] bf16 NHWC, w / bias as one w_mid
+ * layer) and exists for the parity tests.
+ * ------------------------------------------------------------------------------------- */
+size_t pnpadmm_dncnn_activation_bytes(int B, int H, int W);
+int pnpadmm_conv64_bf16(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu,
+                        pnpadmm_stream_t stream);
+int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H, int W, int n_mid,
+                               const float* w_head, const float* b_head, const void* w_mid, const float* b_mid,
+                               const void* w_tail, const float* b_tail, int residual, void* act0, void* act1,
+                               pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helper: runs `iters` dependent-FMA loops on every SM and returns the achieved
  * non-tensor FP32 FLOP/s in *flops (device-timed with CUDA events, synchronous).  Used by
  * bench.py as the measured denominator of the FP32 FFT roofline.

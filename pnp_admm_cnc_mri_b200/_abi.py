@@ -25,6 +25,7 @@ SYMBOLS = [
     'pnpadmm_soft_f32', 'pnpadmm_soft_f64', 'pnpadmm_cnc_combine_f32', 'pnpadmm_cnc_combine_f64',
     'pnpadmm_dual_update_f32', 'pnpadmm_dual_update_f64', 'pnpadmm_measure_fp32_peak',
     'pnpadmm_metrics_scratch_bytes', 'pnpadmm_metrics_f32', 'pnpadmm_metrics_f64',
+    'pnpadmm_dncnn_activation_bytes', 'pnpadmm_conv64_bf16', 'pnpadmm_dncnn_forward_bf16',
 ]
 
 _lib = None
@@ -89,6 +90,12 @@ def load() -> ctypes.CDLL:
     lib.pnpadmm_reconstruct_host_wait.argtypes = [i]
     lib.pnpadmm_measure_fp32_peak.restype = i
     lib.pnpadmm_measure_fp32_peak.argtypes = [POINTER(c_double), p]
+    lib.pnpadmm_dncnn_activation_bytes.restype = z
+    lib.pnpadmm_dncnn_activation_bytes.argtypes = [i, i, i]
+    lib.pnpadmm_conv64_bf16.restype = i
+    lib.pnpadmm_conv64_bf16.argtypes = [p, p, p, p, i, i, i, i, p]
+    lib.pnpadmm_dncnn_forward_bf16.restype = i
+    lib.pnpadmm_dncnn_forward_bf16.argtypes = [p, p, i, i, i, i, i, p, p, p, p, p, p, i, p, p, p]
     if lib.pnpadmm_abi_version() != ABI_VERSION:
         raise PnpAdmmError(f'ABI version mismatch: library {lib.pnpadmm_abi_version()} != binding {ABI_VERSION}; rebuild')
     _lib = lib

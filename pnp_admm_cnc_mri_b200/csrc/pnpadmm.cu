@@ -15,6 +15,7 @@
 #include "streaming.cuh"
 #include "stream2.cuh"
 #include "metrics.cuh"
+#include "dncnn_tc.cuh"
 
 using namespace pnp;
 
@@ -235,6 +236,8 @@ int ensure_device(DeviceState** out) {
         CUDA_TRY(set_stream_attrs<float>());
         CUDA_TRY(set_stream_attrs<double>());
         CUDA_TRY(S2<float>::set_attrs());
+        CUDA_TRY(cudaFuncSetAttribute(tc::conv64_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(tc::conv64_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         d.max_cl8 = probe_clusters<8>(d.sm_count);
         d.max_cl16 = probe_clusters<16>(d.sm_count);
         // Default geometry: 16 half-size CTAs (two planes share an SM, so one computes while the other
@@ -841,6 +844,70 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, fl
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// ------------------------------------------------------------------------------------------
+// K5: DnCNN / FDnCNN forward on the tensor cores (dncnn_tc.cuh)
+// ------------------------------------------------------------------------------------------
+int conv_geometry(tc::ConvParams& p, int B, int H, int W, const char* who) {
+    if (B <= 0 || H <= 0 || W <= 0) return fail(PNPADMM_ERR_BAD_ARG, "%s: B=%d H=%d W=%d must be positive", who, B, H, W);
+    if ((long long)B * H * W >= (1ll << 31)) return fail(PNPADMM_ERR_BAD_SIZE, "%s: B*H*W = %lld pixels exceeds 2^31", who, (long long)B * H * W);
+    p.B = B; p.H = H; p.W = W;
+    p.strip = H < 64 ? H : 64;
+    p.xtiles = (W + tc::kTileM - 1) / tc::kTileM;
+    p.ystrips = (H + p.strip - 1) / p.strip;
+    p.items = B * p.xtiles * p.ystrips;
+    return PNPADMM_OK;
+}
+
+int conv64_impl(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu, cudaStream_t st) {
+    if (!in || !out || !w || !bias) return fail(PNPADMM_ERR_BAD_ARG, "conv64: NULL pointer");
+    if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)w)) & 15) return fail(PNPADMM_ERR_BAD_ARG, "conv64: pointers must be 16-byte aligned");
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    tc::ConvParams p{};
+    rc = conv_geometry(p, B, H, W, "conv64"); if (rc) return rc;
+    p.in = static_cast<const __nv_bfloat16*>(in); p.out = static_cast<__nv_bfloat16*>(out);
+    p.w = w; p.bias = bias; p.relu = relu;
+    const int grid = p.items < d->sm_count ? p.items : d->sm_count;
+    tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    LAUNCH_CHECK("conv64_tc_kernel<64>");
+    return PNPADMM_OK;
+}
+
+int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W, int n_mid, const float* w_head,
+                       const float* b_head, const void* w_mid, const float* b_mid, const void* w_tail, const float* b_tail,
+                       int residual, void* act0, void* act1, cudaStream_t st) {
+    if (!x || !out || !w_head || !b_head || !w_tail || !b_tail || !act0 || !act1 || (n_mid > 0 && (!w_mid || !b_mid)))
+        return fail(PNPADMM_ERR_BAD_ARG, "dncnn_forward: NULL pointer");
+    if (cin != 1 && cin != 2) return fail(PNPADMM_ERR_UNSUPPORTED, "dncnn_forward: %d input channels (1 = DnCNN, 2 = FDnCNN)", cin);
+    if (n_mid < 0) return fail(PNPADMM_ERR_BAD_ARG, "dncnn_forward: n_mid=%d", n_mid);
+    if ((((uintptr_t)act0) | ((uintptr_t)act1) | ((uintptr_t)w_mid) | ((uintptr_t)w_tail)) & 15)
+        return fail(PNPADMM_ERR_BAD_ARG, "dncnn_forward: activation / weight pointers must be 16-byte aligned");
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    tc::ConvParams p{};
+    rc = conv_geometry(p, B, H, W, "dncnn_forward"); if (rc) return rc;
+    __nv_bfloat16* act[2] = {static_cast<__nv_bfloat16*>(act0), static_cast<__nv_bfloat16*>(act1)};
+    const size_t nthreads = (size_t)B * H * W * 8;
+    const unsigned hgrid = (unsigned)((nthreads + 255) / 256);
+    if (cin == 1) tc::dncnn_head_kernel<1><<<hgrid, 256, 0, st>>>(x, act[0], w_head, b_head, B, H, W);
+    else tc::dncnn_head_kernel<2><<<hgrid, 256, 0, st>>>(x, act[0], w_head, b_head, B, H, W);
+    LAUNCH_CHECK("dncnn_head_kernel");
+    const int grid = p.items < d->sm_count ? p.items : d->sm_count;
+    p.relu = 1;
+    for (int l = 0; l < n_mid; ++l) {
+        p.in = act[l & 1]; p.out = act[(l + 1) & 1];
+        p.w = static_cast<const unsigned char*>(w_mid) + (size_t)l * tc::kWBytesMax;
+        p.bias = b_mid + 64 * l;
+        tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    }
+    LAUNCH_CHECK("conv64_tc_kernel<64>");
+    p.in = act[n_mid & 1]; p.out = nullptr; p.out_f32 = out;
+    p.w = w_tail; p.bias = b_tail; p.relu = 0;
+    p.resid = residual ? x : nullptr;          // channel 0 of x
+    p.resid_bstride = (long long)cin * H * W;
+    tc::conv64_tc_kernel<16><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    LAUNCH_CHECK("conv64_tc_kernel<16>");
+    return PNPADMM_OK;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -1086,6 +1153,20 @@ int pnpadmm_measure_fp32_peak(double* flops, pnpadmm_stream_t s) {
     LAUNCH_CHECK("fma_peak_kernel");
     *flops = 2.0 * 64.0 * iters * (double)blocks * threads / (best * 1e-3);
     return PNPADMM_OK;
+}
+
+size_t pnpadmm_dncnn_activation_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return align_up((size_t)B * H * W * 64 * 2);
+}
+int pnpadmm_conv64_bf16(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu,
+                        pnpadmm_stream_t s) {
+    return conv64_impl(in, out, w, bias, B, H, W, relu, ST(s));
+}
+int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H, int W, int n_mid, const float* w_head,
+                               const float* b_head, const void* w_mid, const float* b_mid, const void* w_tail,
+                               const float* b_tail, int residual, void* act0, void* act1, pnpadmm_stream_t s) {
+    return dncnn_forward_impl(x, out, B, cin, H, W, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, residual, act0, act1, ST(s));
 }
 
 }  // extern "C"

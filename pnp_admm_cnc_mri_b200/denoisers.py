@@ -239,13 +239,23 @@ class Denoiser:
     """
 
     def __init__(self, model_name: str, iter_num: int = 50, x8: bool = False, noises=None, dtype=torch.bfloat16,
-                 device='cuda', seed: int = 0, weights=None, ircnn_weights: Optional[Sequence] = None, model: Optional[nn.Module] = None):
+                 device='cuda', seed: int = 0, weights=None, ircnn_weights: Optional[Sequence] = None, model: Optional[nn.Module] = None,
+                 fused: Optional[bool] = None):
         self.name = model_name
         self.arch = _arch(model_name)
         self.dtype = dtype
         self.device = torch.device(device)
         self.x8 = bool(x8) and self.arch in ('drunet', 'ircnn')       # only these branches look at x8 (S3:39-62)
         net = model if model is not None else build_model(model_name, seed, weights)
+        # DnCNN / FDnCNN in bf16 on a GPU run on the hand-written tensor-core kernels (csrc/dncnn_tc.cuh) unless
+        # fused=False asks for the stock PyTorch module (the A/B baseline); other architectures stay in PyTorch.
+        can_fuse = self.arch in ('dncnn', 'fdncnn') and dtype == torch.bfloat16 and self.device.type == 'cuda'
+        if fused and not can_fuse:
+            raise ValueError('fused=True needs a DnCNN / FDnCNN in bf16 on a CUDA device')
+        self.fused = None
+        if can_fuse and fused is not False:
+            from .dncnn_fused import FusedDnCNN
+            self.fused = FusedDnCNN(net, residual=(self.arch == 'dncnn'), device=self.device)
         self.net = net.to(self.device, dtype).to(memory_format=torch.channels_last)
         self.sigmas = None
         self.noise_map = None
@@ -273,10 +283,11 @@ class Denoiser:
     @torch.no_grad()
     def __call__(self, x: torch.Tensor, i: int = 0) -> torch.Tensor:
         if self.arch == 'dncnn':
-            return self._run(x)                                                                     # S3:20-22
+            return self.fused(x) if self.fused is not None else self._run(x)                        # S3:20-22
         if self.arch == 'fdncnn':
             nm = self.noise_map.expand(x.shape[0], 1, *x.shape[-2:])
-            return self._run(torch.cat((x, nm), 1))                                                 # S3:26-35
+            xin = torch.cat((x, nm), 1)
+            return self.fused(xin) if self.fused is not None else self._run(xin)                    # S3:26-35
         if self.arch == 'ffdnet':
             return self._run(x, self.ffdnet_sigma.to(self.dtype))                                   # S3:64-66
         mode = i % 8 if self.x8 else 0

@@ -1,0 +1,119 @@
+"""DnCNN / FDnCNN forward through the tensor-core kernels of the C ABI (``pnpadmm_dncnn_forward_bf16``).
+
+The reference runs its denoisers as stock ``torch.nn`` modules (models/network_dncnn.py:36-67, 120-141, called
+from S6:353-359 / S3:20-35).  On B200 the 64->64 layers are hand-written tcgen05 implicit GEMMs
+(csrc/dncnn_tc.cuh); this module only packs the weights of an ``nn.Module`` into the layouts the kernels read
+and owns the two bf16 activation buffers.  Host logic only: there is no fallback when the library is missing.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+
+
+def conv_layers(net: nn.Module) -> List[nn.Conv2d]:
+    """The convolutions of a DnCNN / FDnCNN in forward order (``net.model`` is conv, ReLU, conv, ...)."""
+    convs = [m for m in net.model if isinstance(m, nn.Conv2d)]
+    if len(convs) < 2:
+        raise ValueError('need at least a first and a last convolution')
+    for k, c in enumerate(convs):
+        if c.kernel_size != (3, 3) or c.padding != (1, 1) or c.dilation != (1, 1) or c.stride != (1, 1) or c.bias is None:
+            raise ValueError(f'layer {k}: only conv3x3, stride 1, padding 1, dilation 1, with bias is supported')
+    if convs[0].out_channels != 64 or convs[-1].in_channels != 64 or convs[-1].out_channels != 1:
+        raise ValueError('expected 64 feature channels and one output channel')
+    for c in convs[1:-1]:
+        if c.in_channels != 64 or c.out_channels != 64:
+            raise ValueError('middle layers must be 64 -> 64')
+    return convs
+
+
+def pack_conv64(weight: torch.Tensor, n_out: int = 64) -> torch.Tensor:
+    """[c_out][64][3][3] float -> [tap = ky*3+kx][c_in // 8][n_out][c_in % 8] bf16 (rows c_out.. n_out-1 zero):
+    the shared-memory image of the B operand (no-swizzle K-major core matrices of 8 c_out x 8 c_in)."""
+    co = weight.shape[0]
+    if weight.shape[1:] != (64, 3, 3) or co > n_out:
+        raise ValueError(f'bad weight shape {tuple(weight.shape)}')
+    w = torch.zeros((n_out, 64, 3, 3), dtype=torch.float32, device=weight.device)
+    w[:co] = weight.float()
+    w = w.permute(2, 3, 1, 0).reshape(9, 8, 8, n_out)          # tap, c_in // 8, c_in % 8, c_out
+    return w.permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
+
+
+def pack_dncnn(net: nn.Module, device) -> Tuple[dict, int, int]:
+    convs = conv_layers(net)
+    head, mids, tail = convs[0], convs[1:-1], convs[-1]
+    dev = torch.device(device)
+    bf = lambda t: t.detach().to(dev, torch.float32).to(torch.bfloat16)      # noqa: E731  (weights live in bf16, like net.to(bf16))
+    packed = {
+        'w_head': bf(head.weight).float().contiguous(),
+        'b_head': bf(head.bias).float().contiguous(),
+        'w_mid': (torch.stack([pack_conv64(bf(c.weight)) for c in mids]).contiguous() if mids
+                  else torch.zeros(0, dtype=torch.bfloat16, device=dev)),
+        'b_mid': (torch.stack([bf(c.bias).float() for c in mids]).contiguous() if mids
+                  else torch.zeros(0, dtype=torch.float32, device=dev)),
+        'w_tail': pack_conv64(bf(tail.weight), 16),
+        'b_tail': bf(tail.bias).float().contiguous(),
+    }
+    return packed, head.in_channels, len(mids)
+
+
+class FusedDnCNN:
+    """``y = D(x)`` for a DnCNN (residual, 1 input channel) or FDnCNN (non-residual, 2 input channels).
+
+    x: (B, cin, H, W) float32 CUDA tensor -> (B, 1, H, W) float32.  Work is enqueued on the current stream.
+    """
+
+    def __init__(self, net: nn.Module, residual: bool, device='cuda'):
+        if not torch.cuda.is_available():
+            raise _abi.PnpAdmmError('no CUDA device visible: the tensor-core denoiser has no CPU path')
+        self.lib = _abi.load()
+        self.device = torch.device(device)
+        self.residual = bool(residual)
+        self.w, self.cin, self.n_mid = pack_dncnn(net, self.device)
+        if self.cin not in (1, 2):
+            raise ValueError(f'{self.cin} input channels: only DnCNN (1) and FDnCNN (2) are on the path')
+        self._act = None
+        self._act_key = None
+
+    def _buffers(self, B, H, W):
+        key = (B, H, W)
+        if self._act_key != key:
+            n = self.lib.pnpadmm_dncnn_activation_bytes(B, H, W)
+            self._act = (torch.empty(n, dtype=torch.uint8, device=self.device), torch.empty(n, dtype=torch.uint8, device=self.device))
+            self._act_key = key
+        return self._act
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if x.ndim != 4 or x.shape[1] != self.cin or not x.is_cuda:
+            raise ValueError(f'expected a CUDA tensor of shape (B, {self.cin}, H, W), got {tuple(x.shape)} on {x.device}')
+        x = x.float().contiguous()
+        B, _, H, W = (int(v) for v in x.shape)
+        a0, a1 = self._buffers(B, H, W)
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+        w = self.w
+        _abi.check(self.lib.pnpadmm_dncnn_forward_bf16(
+            x.data_ptr(), out.data_ptr(), B, self.cin, H, W, self.n_mid, w['w_head'].data_ptr(), w['b_head'].data_ptr(),
+            w['w_mid'].data_ptr() if self.n_mid else None, w['b_mid'].data_ptr() if self.n_mid else None,
+            w['w_tail'].data_ptr(), w['b_tail'].data_ptr(), int(self.residual), a0.data_ptr(), a1.data_ptr(),
+            torch.cuda.current_stream().cuda_stream))
+        return out
+
+
+def conv64(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.Tensor:
+    """One 64 -> 64 layer through ``pnpadmm_conv64_bf16``: x (B, H, W, 64) bf16 CUDA -> same shape (parity tests)."""
+    lib = _abi.load()
+    if x_nhwc.dtype != torch.bfloat16 or x_nhwc.ndim != 4 or x_nhwc.shape[-1] != 64 or not x_nhwc.is_cuda:
+        raise ValueError('expected a (B, H, W, 64) bf16 CUDA tensor')
+    x = x_nhwc.contiguous()
+    B, H, W, _ = (int(v) for v in x.shape)
+    wp = pack_conv64(weight.to(x.device))
+    bs = bias.to(x.device, torch.float32).contiguous()
+    out = torch.empty_like(x)
+    _abi.check(lib.pnpadmm_conv64_bf16(x.data_ptr(), out.data_ptr(), wp.data_ptr(), bs.data_ptr(), B, H, W, int(relu),
+                                       torch.cuda.current_stream().cuda_stream))
+    return out

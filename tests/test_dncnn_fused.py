@@ -1,0 +1,128 @@
+"""K5: DnCNN / FDnCNN forward on the tensor cores (csrc/dncnn_tc.cuh) against PyTorch.
+
+CPU part: the weight packing (the shared-memory image of the B operand) and the tap convention, by evaluating
+the implicit GEMM exactly as the kernel indexes it.  GPU part: one 64->64 layer and whole networks through the
+C ABI against float32 PyTorch convolutions of the same bf16-rounded weights.
+Tolerances: a layer's output is rounded to bf16 (relative 2^-9 per value); a 17-layer network accumulates those
+roundings exactly like a bf16 PyTorch module does, so the gate is the error of PyTorch's own bf16 forward.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pnp_admm_cnc_mri_b200 import denoisers
+from pnp_admm_cnc_mri_b200 import dncnn_fused as df
+
+
+def _emulate_packed_conv(x_nhwc, wp, bias, relu):
+    """out[y, x, co] = sum_{tap, kc, c8} in[y+ky-1, x+kx-1, 8 kc + c8] * wp[tap][kc][co][c8]  (zero padding)."""
+    B, H, W, _ = x_nhwc.shape
+    n_out = wp.shape[2]
+    xp = F.pad(x_nhwc.float(), (0, 0, 1, 1, 1, 1))
+    out = torch.zeros(B, H, W, n_out)
+    for ky in range(3):
+        for kx in range(3):
+            a = xp[:, ky:ky + H, kx:kx + W, :].reshape(B, H, W, 8, 8)              # ..., kc, c8
+            out += torch.einsum('bhwkc,knc->bhwn', a, wp[ky * 3 + kx].float())
+    out += bias.float()
+    return out.clamp_min(0) if relu else out
+
+
+def test_pack_conv64_matches_conv2d():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(64, 64, 3, 3, generator=g).to(torch.bfloat16).float()
+    b = torch.randn(64, generator=g)
+    x = torch.randn(2, 5, 7, 64, generator=g).to(torch.bfloat16)
+    wp = df.pack_conv64(w)
+    assert wp.shape == (9, 8, 64, 8) and wp.dtype == torch.bfloat16
+    got = _emulate_packed_conv(x, wp, b, relu=True)
+    want = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1)).permute(0, 2, 3, 1)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-4)
+    # last layer: one real output row, padded to N = 16
+    wt = torch.randn(1, 64, 3, 3, generator=g)
+    wpt = df.pack_conv64(wt, 16)
+    assert wpt.shape == (9, 8, 16, 8) and float(wpt[:, :, 1:].abs().max()) == 0.0
+    got = _emulate_packed_conv(x, wpt, torch.zeros(16), relu=False)[..., 0]
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), None, padding=1)[:, 0]
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-4)
+
+
+def test_pack_dncnn_layer_split():
+    net = denoisers.build_model('dncnn_25')
+    packed, cin, n_mid = df.pack_dncnn(net, 'cpu')
+    assert (cin, n_mid) == (1, 15)
+    assert packed['w_mid'].shape == (15, 9, 8, 64, 8) and packed['b_mid'].shape == (15, 64)
+    assert packed['w_head'].shape == (64, 1, 3, 3) and packed['w_tail'].shape == (9, 8, 16, 8)
+    net2 = denoisers.build_model('fdncnn_gray')
+    _, cin2, n_mid2 = df.pack_dncnn(net2, 'cpu')
+    assert (cin2, n_mid2) == (2, 18)
+    with pytest.raises(ValueError):
+        df.conv_layers(denoisers.build_model('ircnn_gray'))      # dilated convolutions are not on this kernel
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(1, 8, 128), (2, 64, 256), (3, 70, 200), (1, 3, 40), (2, 130, 129), (1, 256, 256)])
+@pytest.mark.parametrize('relu', [True, False])
+def test_conv64_layer_gpu(shape, relu):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + H + W)
+    x = torch.randn(B, H, W, 64, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24.0).to(torch.bfloat16).float().cuda()
+    b = torch.randn(64, generator=g).cuda()
+    got = df.conv64(x, w, b, relu=relu).float()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        want = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)
+    if relu:
+        want = want.clamp_min(0)
+    # fp32 accumulation of exact bf16 products, output rounded once to bf16: |err| <= 2^-9 |want| + accumulation-order noise
+    err = (got - want).abs()
+    assert float((err - (2.0 ** -8) * want.abs()).max()) < 2e-3, float(err.max())
+    assert _rel(got, want) < 3e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,shape', [('dncnn_25', (4, 256, 256)), ('dncnn_25', (2, 96, 160)), ('dncnn3', (1, 64, 64)),
+                                        ('fdncnn_gray', (2, 128, 128))])
+def test_dncnn_forward_gpu(name, shape):
+    B, H, W = shape
+    net = denoisers.build_model(name, seed=3)
+    # random-init weights scaled up so that n(x) is not vanishingly small after 17-20 layers
+    with torch.no_grad():
+        for c in df.conv_layers(net):
+            c.weight.mul_(1.6)
+            c.weight.copy_(c.weight.to(torch.bfloat16).float())
+            c.bias.copy_(c.bias.to(torch.bfloat16).float())
+    net = net.cuda()
+    g = torch.Generator().manual_seed(11)
+    cin = df.conv_layers(net)[0].in_channels
+    x = torch.rand(B, cin, H, W, generator=g).cuda()
+    x = x.to(torch.bfloat16).float()             # the kernels round the network input to bf16, like net.to(bf16)(x.to(bf16))
+    fused = df.FusedDnCNN(net, residual=(cin == 1))
+    got = fused(x)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        want = net(x)                                                      # fp32 PyTorch, same (bf16-representable) weights
+        ref16 = net.to(torch.bfloat16)(x.to(torch.bfloat16)).float()       # PyTorch's own bf16 forward
+    assert got.shape == want.shape == (B, 1, H, W)
+    n_got = (x[:, :1] - got) if cin == 1 else got                          # the network part n(x)
+    n_want = (x[:, :1] - want) if cin == 1 else want
+    n_ref16 = (x[:, :1] - ref16) if cin == 1 else ref16
+    e_ours, e_torch = _rel(n_got, n_want), _rel(n_ref16, n_want)
+    assert e_ours < max(2.0 * e_torch, 2e-2), (e_ours, e_torch)
+    assert _rel(got, want) < 1e-2
+
+
+@pytest.mark.gpu
+def test_denoiser_dispatch_uses_fused_gpu():
+    d = denoisers.build_denoiser('dncnn_25', seed=1)
+    assert d.fused is not None
+    x = torch.rand(2, 1, 64, 64, device='cuda')
+    y = d(x, 0)
+    d_ref = denoisers.build_denoiser('dncnn_25', seed=1, fused=False)
+    y_ref = d_ref(x, 0)
+    assert _rel(y, y_ref) < 1e-2
