@@ -64,6 +64,7 @@ struct ConvParams {
     const float* bias;          // [64] (tail: [1])
     int B, H, W, strip, xtiles, ystrips, items;
     int relu;
+    int dbg;                    // timing experiments only (results invalid): 1 = no input copies, 2 = no output stores, 4 = no MMAs
 };
 
 PNP_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,6 +107,23 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1
           "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]),      \
           "=r"(v[o + 30]), "=r"(v[o + 31])                                                                           \
         : "r"(taddr))
+
+PNP_D void st_global_v8(void* p, const uint32_t (&o)[8]) {      // one 256-bit store (SASS STG.256)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                 : "memory");
+}
+
+// one lane of the (converged) warp
+PNP_D bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 
 PNP_D uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -181,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     const int x = it.x0 - 1 + s;
                     const bool ok = yok && (x >= 0) && (x < p.W);
                     const __nv_bfloat16* src = ok ? rowp + (size_t)x * 64 + ch * 8 : p.in;
-                    cp_async16(dst0 + ch * kChunkBytes + s * 16, src, ok ? 16u : 0u);
+                    if (!(p.dbg & 1)) cp_async16(dst0 + ch * kChunkBytes + s * 16, src, ok ? 16u : 0u);
                 }
                 cp_async_commit();
                 if (e >= (uint32_t)kLag) {
@@ -195,36 +213,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         k1::fence_proxy_async();
         for (uint32_t k = (e >= (uint32_t)kLag ? e - kLag : 0u); k < e; ++k) mbar_arrive(bFull(k % kStages));
     } else if (warp == 4) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            uint32_t e_base = 0, waited = 0, t = 0;
-            const uint32_t wsm = s0 + kOffW;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-                const Item it = decode_item(p, item);
-                for (int j = 0; j < it.rows; ++j, ++t) {
-                    const uint32_t as = t & 1u;
-                    k1::mbar_wait(bTEmpty(as), ((t >> 1) & 1u) ^ 1u);
-                    while (waited <= e_base + j + 2) {
-                        k1::mbar_wait(bFull(waited % kStages), (waited / kStages) & 1u);
-                        ++waited;
-                    }
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * 64;
-                    uint32_t acc = 0;
+        // ------------------------------------------------------------------ MMA issuer
+        // The whole warp runs the loop (warp-uniform control and address math stay on the uniform datapath); one
+        // elected lane issues the tensor-core instructions.
+        uint32_t e_base = 0, waited = 0, t = 0;
+        const uint64_t desc_hi_a = ((uint64_t)(kChunkBytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+        const uint64_t b_desc0 = make_desc(s0 + kOffW, NOUT * 16, 128);
+        const bool leader = elect_one();
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const Item it = decode_item(p, item);
+            for (int j = 0; j < it.rows; ++j, ++t) {
+                const uint32_t as = t & 1u;
+                k1::mbar_wait(bTEmpty(as), ((t >> 1) & 1u) ^ 1u);
+                while (waited <= e_base + j + 2) {
+                    k1::mbar_wait(bFull(waited % kStages), (waited / kStages) & 1u);
+                    ++waited;
+                }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 64;
+                if (leader && !(p.dbg & 4)) {
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         const uint32_t a_row = ring + ((e_base + j + dy) % kStages) * kRowBytes;
+                        const uint64_t a_desc0 = desc_hi_a | (uint64_t)((a_row & 0x3FFFFu) >> 4);
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = make_desc(a_row + dx * 16 + ks * 2 * kChunkBytes, kChunkBytes, 128);
-                                const uint64_t bd = make_desc(wsm + ((dy * 3 + dx) * 8 + ks * 2) * (NOUT * 16), NOUT * 16, 128);
-                                tc_mma_bf16(d_tmem, ad, bd, kIdesc, acc);
-                                acc = 1;
+                                // start-address field += byte offset / 16 (never carries out of its 14 bits: smem < 256 KB)
+                                const uint64_t ad = a_desc0 + (uint64_t)((dx * 16 + ks * 2 * kChunkBytes) >> 4);
+                                const uint64_t bd = b_desc0 + (uint64_t)((((dy * 3 + dx) * 8 + ks * 2) * (NOUT * 16)) >> 4);
+                                tc_mma_bf16(d_tmem, ad, bd, kIdesc, (dy | dx | ks) != 0);
                             }
                         }
                     }
+                }
+                __syncwarp();
+                if (leader) {
                     tc_commit(bEmpty((e_base + j) % kStages));           // input row j is not needed by later output rows
                     if (j == it.rows - 1) {
                         tc_commit(bEmpty((e_base + j + 1) % kStages));
@@ -232,10 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     }
                     tc_commit(bTFull(as));
                 }
-                e_base += it.rows + 2;
+                __syncwarp();
             }
+            e_base += it.rows + 2;
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps
         uint32_t t = 0;
@@ -256,20 +281,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bTEmpty(as));
-                    if (x < p.W) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * 64);
+                    if (x < p.W && !(p.dbg & 2)) {
+                        __nv_bfloat16* dst = p.out + pix * 64;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float f[8];
+                        for (int q = 0; q < 4; ++q) {           // 16 channels = one 32-byte sector per store
+                            float f[16];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                f[k] = __uint_as_float(v[8 * q + k]) + bias_s[8 * q + k];
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const float4 bb = reinterpret_cast<const float4*>(bias_s)[4 * q + k4];
+                                f[4 * k4 + 0] = bb.x; f[4 * k4 + 1] = bb.y; f[4 * k4 + 2] = bb.z; f[4 * k4 + 3] = bb.w;
+                            }
+                            uint32_t o[8];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                f[k] += __uint_as_float(v[16 * q + k]);
                                 if (p.relu) f[k] = fmaxf(f[k], 0.f);
                             }
-                            uint4 o;
-                            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-                            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                            dst[q] = o;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) o[k] = pack_bf16x2(f[2 * k], f[2 * k + 1]);
+                            st_global_v8(dst + 16 * q, o);
                         }
                     }
                 } else {
@@ -296,53 +326,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
 
 // First layer: conv3x3 CIN -> 64 + bias + ReLU on the CUDA cores (K = 9 CIN is too thin for the tensor cores and the
 // layer is bound by its 128 B/pixel NHWC write).  x: [B][CIN][H][W] fp32 (rounded to bf16 like a bf16 PyTorch module
-// would), w: [64][CIN][3][3] fp32 (bf16-representable values), out: [B][H][W][64] bf16.  Thread = (pixel, 8 channels).
+// would), w: [64][CIN][3][3] fp32 (bf16-representable values), out: [B][H][W][64] bf16.
+// Thread = (8 output channels, pixel lane): its 72 CIN weights live in registers for the whole kernel and it walks over
+// kHeadPix pixels; the 8 threads of a pixel write its 128 bytes as one contiguous segment.
+constexpr int kHeadPix = 16;     // pixels per thread
 template <int CIN>
 __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                          const float* __restrict__ w, const float* __restrict__ bias, int B,
                                                          int H, int W) {
-    __shared__ float ws[64 * CIN * 9];
-    __shared__ float bs[64];
-    for (int i = threadIdx.x; i < 64 * CIN * 9; i += blockDim.x) ws[i] = w[i];
-    if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
-    __syncthreads();
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t npix = (size_t)B * H * W;
-    const size_t pix = idx >> 3;
-    const int ch = (int)(idx & 7);
-    if (pix >= npix) return;
-    const int xx = (int)(pix % W);
-    const int yy = (int)((pix / W) % H);
-    const size_t b = pix / ((size_t)W * H);
-    float in[CIN][9];
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) {
-        const float* img = x + (b * CIN + ci) * (size_t)H * W;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int y2 = yy + ky - 1, x2 = xx + kx - 1;
-                float v = 0.f;
-                if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) v = __ldg(img + (size_t)y2 * W + x2);
-                in[ci][ky * 3 + kx] = __bfloat162float(__float2bfloat16(v));
-            }
-    }
-    float f[8];
+    const int ch = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    float wr[CIN][8][9], br[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const int co = ch * 8 + c;
-        float acc = bs[co];
+        br[c] = __ldg(bias + ch * 8 + c);
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) acc = fmaf(ws[(co * CIN + ci) * 9 + t], in[ci][t], acc);
-        f[c] = fmaxf(acc, 0.f);
+            for (int t = 0; t < 9; ++t) wr[ci][c][t] = __ldg(w + ((ch * 8 + c) * CIN + ci) * 9 + t);
     }
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(out + pix * 64 + ch * 8) = o;
+    const uint32_t npix = (uint32_t)B * H * W;          // < 2^31 (checked by the host)
+    uint32_t pix = blockIdx.x * (32u * kHeadPix) + pl;
+    if (pix >= npix) return;
+    int xx = (int)(pix % (uint32_t)W);
+    int yy = (int)((pix / (uint32_t)W) % (uint32_t)H);
+    uint32_t b = pix / ((uint32_t)W * H);
+    for (int it = 0; it < kHeadPix; ++it, pix += 32, xx += 32) {
+        if (pix >= npix) return;
+        while (xx >= W) { xx -= W; if (++yy == H) { yy = 0; ++b; } }
+        float f[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[c] = br[c];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* img = x + ((size_t)b * CIN + ci) * (size_t)H * W;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int y2 = yy + ky - 1, x2 = xx + kx - 1;
+                    float v = 0.f;
+                    if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) v = __ldg(img + (size_t)y2 * W + x2);
+                    v = __bfloat162float(__float2bfloat16(v));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) f[c] = fmaf(wr[ci][c][ky * 3 + kx], v, f[c]);
+                }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)); o.y = pack_bf16x2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
+        o.z = pack_bf16x2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)); o.w = pack_bf16x2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
+        *reinterpret_cast<uint4*>(out + (size_t)pix * 64 + ch * 8) = o;
+    }
 }
 
 }  // namespace tc

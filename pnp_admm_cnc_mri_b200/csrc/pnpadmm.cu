@@ -866,6 +866,7 @@ int conv64_impl(const void* in, void* out, const void* w, const float* bias, int
     rc = conv_geometry(p, B, H, W, "conv64"); if (rc) return rc;
     p.in = static_cast<const __nv_bfloat16*>(in); p.out = static_cast<__nv_bfloat16*>(out);
     p.w = w; p.bias = bias; p.relu = relu;
+    if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);
     const int grid = p.items < d->sm_count ? p.items : d->sm_count;
     tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
     LAUNCH_CHECK("conv64_tc_kernel<64>");
@@ -885,8 +886,8 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
     tc::ConvParams p{};
     rc = conv_geometry(p, B, H, W, "dncnn_forward"); if (rc) return rc;
     __nv_bfloat16* act[2] = {static_cast<__nv_bfloat16*>(act0), static_cast<__nv_bfloat16*>(act1)};
-    const size_t nthreads = (size_t)B * H * W * 8;
-    const unsigned hgrid = (unsigned)((nthreads + 255) / 256);
+    const size_t per_block = 32 * (size_t)tc::kHeadPix;
+    const unsigned hgrid = (unsigned)(((size_t)B * H * W + per_block - 1) / per_block);
     if (cin == 1) tc::dncnn_head_kernel<1><<<hgrid, 256, 0, st>>>(x, act[0], w_head, b_head, B, H, W);
     else tc::dncnn_head_kernel<2><<<hgrid, 256, 0, st>>>(x, act[0], w_head, b_head, B, H, W);
     LAUNCH_CHECK("dncnn_head_kernel");

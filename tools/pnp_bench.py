@@ -8,6 +8,7 @@ import pnp_admm_cnc_mri_b200 as pk
 from pnp_admm_cnc_mri_b200 import data, pnp, denoisers
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'c3'
+FUSED = os.environ.get('PNP_FUSED', '1') != '0'      # PNP_FUSED=0: stock PyTorch bf16 (cuDNN) denoiser, the A/B baseline
 dev = torch.device('cuda', 0)
 
 
@@ -28,12 +29,13 @@ if which == 'c3':
     imgs = torch.as_tensor(np.stack([data.phantom(N, i) for i in range(8)] * (B // 8)).astype(np.float32)).to(dev)
     m = data.make_mask('random', N, seed=0)
     nz = data.make_noise(N, seed=3)
-    D = denoisers.build_denoiser('dncnn_25', iter_num=iters, device=dev)          # DnCNN-17, nc=64, random init, bf16
+    D = denoisers.build_denoiser('dncnn_25', iter_num=iters, device=dev, fused=None if FUSED else False)   # DnCNN-17, nc=64, random init, bf16
     t_all = timed(lambda: pnp.pnp_admm_cnc(imgs, m, nz, D, D, alpha=1.2, iter_num=iters, lambda1=4, reo=0.45, b=0.3))
     x = torch.rand(B, 1, N, N, device=dev)
     t_den = timed(lambda: D(x, 0))
     flops = 2 * 555137 * N * N * B          # per forward (2 x params x pixels)
     print(json.dumps({'config': 3, 'workload': f'PnP-ADMM-CNC DnCNN-17 bf16, B={B}, 256x256', 'iters_timed': iters,
+                      'denoiser': 'tcgen05 kernels (csrc/dncnn_tc.cuh)' if D.fused is not None else 'PyTorch bf16 channels_last (cuDNN)',
                       'ms_per_iteration': t_all / iters, 'image_iterations_per_s': B * iters / (t_all * 1e-3),
                       'denoiser_forward_ms': t_den, 'denoiser_share': 2 * t_den * iters / t_all,
                       'denoiser_tflops': flops / (t_den * 1e-3) / 1e12}))
