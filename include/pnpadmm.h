@@ -213,11 +213,12 @@ int pnpadmm_metrics_f64(const double* x, const uint8_t* ref, int B, int N, int q
  *   x      [B][cin][H][W] f32 (cin = 1 DnCNN, 2 FDnCNN: noise-level map in channel 1)
  *   out    [B][H][W] f32:  residual != 0 ? x[:, 0] - n(x) : n(x)
  *   w_head [64][cin][3][3] f32 (values already rounded to bf16), b_head [64] f32
- *   w_mid  n_mid x [tap = ky*3+kx][c_in / 8][c_out 64][c_in % 8] bf16 (73 728 B per layer), b_mid [n_mid][64] f32
- *   w_tail [tap][c_in / 8][16][c_in % 8] bf16, rows 1..15 zero;  b_tail [1] f32
+ *   w_mid  n_mid x [kx][c_in / 8][ky][c_out 64][c_in % 8] bf16 (73 728 B per layer), b_mid [n_mid][64] f32
+ *   w_tail [kx][c_in / 8][ky][16][c_in % 8] bf16, rows 1..15 of every ky zero;  b_tail [1] f32
  *   act0, act1: two device buffers of pnpadmm_dncnn_activation_bytes(B, H, W) bytes, 16-byte aligned.
- * pnpadmm_conv64_bf16 runs ONE 64->64 layer (in / out [B][H][W][64] bf16 NHWC, w / bias as one w_mid
- * layer) and exists for the parity tests.
+ * pnpadmm_conv64_bf16 runs ONE 64->64 layer (w / bias as one w_mid layer) and exists for the parity tests;
+ * in / out are [B][H][W][64] bf16 in the kernels' inter-layer layout: NHWC with the 16-byte chunk c (8 channels)
+ * of pixel x stored at position c ^ (x & 7) of the pixel's 128 bytes.
  * ------------------------------------------------------------------------------------- */
 size_t pnpadmm_dncnn_activation_bytes(int B, int H, int W);
 int pnpadmm_conv64_bf16(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu,

@@ -8,20 +8,22 @@
 //         act[y + ky - 1][x0 + m + kx - 1][c_in] * w[c_out][c_in][ky][kx]            M = 128, N = 64, K = 576
 //
 // issued as 36 `tcgen05.mma.cta_group::1.kind::f16` (128 x 64 x 16, bf16 in, fp32 accumulate in TMEM) by one
-// thread.  Activations are NHWC bf16 (128 B per pixel).  Shared memory uses the NO-SWIZZLE K-major canonical
+// thread.  Activations are NHWC bf16 (128 B per pixel; between layers the 16-byte channel chunk c of pixel x is stored
+// at position c ^ (x & 7), which makes the epilogue's staging tile bank-conflict free and bulk-copyable as is).  Shared memory uses the NO-SWIZZLE K-major canonical
 // layout (core matrix = 8 rows x 16 B, contiguous 128 B):
 //     A row buffer : [k-chunk 0..7][slot 0..130][8 c_in]   slot s <-> pixel x0 - 1 + s (1-pixel halo each side)
 // so the tap shift kx is a 16-byte shift of the descriptor start address and the tap shift ky selects another
 // row buffer: the im2col matrix is never materialised and every input row is loaded ONCE per strip and reused by
 // the 9 taps of three output rows.  The row buffers form a 6-deep ring filled by four producer warps with 16-byte
 // `cp.async` (zero-fill outside the image = the convolution's zero padding); the 72 KB of weights of the layer
-//     B            : [tap 0..8][k-chunk 0..7][c_out 0..N)[8 c_in]
+//     B            : [kx 0..2][k-chunk 0..7][ky 0..2][c_out 0..N)[8 c_in]   (the three ky taps stacked along N)
 // stay resident for the persistent CTA's whole life.  Accumulators are double-buffered in TMEM so the epilogue
 // warps (tcgen05.ld -> bias -> ReLU -> bf16 -> 128 B per pixel) overlap the next row's MMAs.
 //
-//   warps 0-3 : epilogue (TMEM lane quadrant = warp)          mbarriers: full[6] / empty[6]  (producer <-> MMA)
-//   warp  4   : TMEM alloc, one lane issues the MMAs                      tfull[2] / tempty[2] (MMA <-> epilogue)
-//   warps 5-8 : producers
+//   warps 0-3  : epilogue (TMEM lane quadrant = warp & 3)
+//   warp  4    : TMEM alloc, one elected lane issues the MMAs
+//   warps 5-8  : producers
+//   mbarriers  : full[6] / empty[6] (producers <-> MMA), tfull[8] / tempty[8] (MMA <-> epilogue, one pair per block)
 //
 // The first layer (c_in = 1 or 2) and nothing else runs on the CUDA cores (it is a 0.3 ms NHWC write); the last
 // layer (c_out = 1) reuses the tensor-core kernel with N = 16 (rows 1..15 of B are zero) and an fp32 epilogue
@@ -41,18 +43,20 @@ constexpr int kPPad = 131;                     // slot pitch of a k-chunk plane,
 constexpr int kChunkBytes = kPPad * 16;        // = LBO of the A descriptor
 constexpr int kRowBytes = 8 * kChunkBytes;     // 16768
 constexpr int kStages = 6;
-constexpr int kLag = 2;                        // producer signals a row two rows after issuing it (copies stay in flight)
 constexpr int kThreads = 288;
 constexpr int kProducers = 128;
+constexpr int kEpiGroups = 1;                  // epilogue groups of four warps; group g takes the output rows t = g (mod kEpiGroups)
+constexpr int kMmaWarp = 4 * kEpiGroups;       // warps [0, 4 g): epilogue, then one MMA warp, then four producer warps
 constexpr int kOffW = 0;
 constexpr int kWBytesMax = 9 * 8 * 64 * 16;    // 73728
 constexpr int kOffRing = kWBytesMax;
 constexpr int kOffBar = kOffRing + kStages * kRowBytes;
-constexpr int kNumBars = 2 * kStages + 4;
+constexpr int kBlocks = 8;                     // accumulator blocks (output rows in flight) in TMEM
+constexpr int kNumBars = 2 * kStages + 2 * kBlocks;
 constexpr int kOffTmemPtr = kOffBar + 8 * kNumBars;
 constexpr int kOffBias = kOffTmemPtr + 16;
-constexpr int kSmemBytes = kOffBias + 64 * 4;
-constexpr int kTmemCols = 128;                 // two accumulator stages of 64 columns
+constexpr int kOffOut = kOffBias + 64 * 4;     // two staging tiles [128 pixels][128 B] (global layout, see below)
+constexpr int kSmemBytes = kOffOut + 2 * kTileM * 128;
 
 struct ConvParams {
     const __nv_bfloat16* in;    // [B][H][W][64]
@@ -74,6 +78,18 @@ PNP_D void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
 PNP_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> PNP_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 PNP_D void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// Waits sleep in hardware (k1::mbar_wait: try_wait with a suspend-time hint, clock-bounded so that a protocol bug traps):
+// the kernel runs power-capped (~1.45 GHz under load), so a spinning waiter costs clock for the warps that work.
+PNP_D void mbar_wait(uint32_t bar, uint32_t parity) { k1::mbar_wait(bar, parity); }
+// Optional wait-time attribution (PNPADMM_TC_DEBUG bit 256): cycles each role spent blocked on each barrier kind, summed
+// over CTAs: [0] producer/empty [1] MMA/tempty [2] MMA/full [3] epilogue/tfull [4] MMA loop total [5] producer total [6] epilogue total
+__device__ unsigned long long g_tc_prof[8];
+PNP_D void mbar_wait_t(uint32_t bar, uint32_t parity, unsigned long long& acc, bool on) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+}
 PNP_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 PNP_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 PNP_D void tc_commit(uint32_t bar) {
@@ -125,6 +141,18 @@ PNP_D bool elect_one() {
     return pred != 0;
 }
 
+#define PNP_TMEM_ST32(taddr, v, o)                                                                                   \
+    asm volatile(                                                                                                    \
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "  \
+        "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"                 \
+        ::"r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]),      \
+          "r"(v[o + 6]), "r"(v[o + 7]), "r"(v[o + 8]), "r"(v[o + 9]), "r"(v[o + 10]), "r"(v[o + 11]),                \
+          "r"(v[o + 12]), "r"(v[o + 13]), "r"(v[o + 14]), "r"(v[o + 15]), "r"(v[o + 16]), "r"(v[o + 17]),            \
+          "r"(v[o + 18]), "r"(v[o + 19]), "r"(v[o + 20]), "r"(v[o + 21]), "r"(v[o + 22]), "r"(v[o + 23]),            \
+          "r"(v[o + 24]), "r"(v[o + 25]), "r"(v[o + 26]), "r"(v[o + 27]), "r"(v[o + 28]), "r"(v[o + 29]),            \
+          "r"(v[o + 30]), "r"(v[o + 31])                                                                             \
+        : "memory")
+
 PNP_D uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -146,24 +174,35 @@ PNP_D Item decode_item(const ConvParams& p, int item) {
 
 // NOUT = 64: bf16 NHWC output with bias (+ ReLU).  NOUT = 16: last layer, only c_out 0 is real; fp32 output,
 // out = resid - (conv + bias) when resid != null, else conv + bias.
+//
+// Input-stationary schedule.  Input row i of a strip contributes to the output rows j = i - dy (dy = 0, 1, 2), and
+// the weights of the three dy taps are stacked along N in shared memory, so ONE instruction of N = 3 NOUT per
+// (dx, k-step) feeds all three output rows from one fetch of the A slab:  12 instructions of 128 x 192 x 16 per row
+// instead of 36 of 128 x 64 x 16 (shared-memory operand traffic 120 KB instead of 216 KB per row).  The accumulators
+// of consecutive output rows therefore sit in consecutive TMEM column blocks, in DESCENDING row order: output row t
+// (running count) lives in block (-t) mod 8, so the window of input row i is blocks [blk(j = i), blk(i - 1),
+// blk(i - 2)] = b, b + 1, b + 2 (split in two instructions where it wraps).  A block is complete after its third
+// input row; the epilogue drains it and re-initialises it with the BIAS (tcgen05.st), so every MMA accumulates.
 template <int NOUT>
 __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int kWBytes = 9 * 8 * NOUT * 16;
-    constexpr uint32_t kIdesc = make_idesc(NOUT);
+    constexpr uint32_t kTmemColsK = kBlocks * NOUT;          // 512 (all of TMEM) or 128
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool prof = (p.dbg & 256) != 0;
     const uint32_t s0 = smem_u32(smem);
     const uint32_t ring = s0 + kOffRing, bars = s0 + kOffBar;
     auto bFull = [&](uint32_t i) { return bars + 8 * i; };
     auto bEmpty = [&](uint32_t i) { return bars + 8 * (kStages + i); };
     auto bTFull = [&](uint32_t i) { return bars + 8 * (2 * kStages + i); };
-    auto bTEmpty = [&](uint32_t i) { return bars + 8 * (2 * kStages + 2 + i); };
+    auto bTEmpty = [&](uint32_t i) { return bars + 8 * (2 * kStages + kBlocks + i); };
+    auto blk = [](uint32_t t) { return (kBlocks - (t & (kBlocks - 1))) & (kBlocks - 1); };
     float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { k1::mbar_init(bFull(i), kProducers); k1::mbar_init(bEmpty(i), 1); }
-        for (int i = 0; i < 2; ++i) { k1::mbar_init(bTFull(i), 1); k1::mbar_init(bTEmpty(i), 4); }
+        for (int i = 0; i < kBlocks; ++i) { k1::mbar_init(bTFull(i), 1); k1::mbar_init(bTEmpty(i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < kWBytes / 16; i += kThreads)
@@ -172,8 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
     if (threadIdx.x < 64) bias_s[threadIdx.x] = (threadIdx.x < (NOUT == 64 ? 64 : 1)) ? p.bias[threadIdx.x] : 0.f;
     cp_async_wait<0>();
     k1::fence_proxy_async();                   // weights (generic-proxy writes) visible to the tensor core's async proxy
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s0 + kOffTmemPtr), "r"(kTmemCols) : "memory");
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s0 + kOffTmemPtr), "r"(kTmemColsK) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -181,147 +220,226 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 5) {
+    // epilogue warps: the bias is the accumulators' initial value (this thread's TMEM lane, all columns of a block)
+    auto init_block = [&](uint32_t taddr) {
+        if (NOUT == 64) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {          // 16 columns at a time keeps the register peak low
+                uint32_t br[16];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 b4 = reinterpret_cast<const uint4*>(bias_s)[4 * h + k];
+                    br[4 * k] = b4.x; br[4 * k + 1] = b4.y; br[4 * k + 2] = b4.z; br[4 * k + 3] = b4.w;
+                }
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                    ::"r"(taddr + 16 * h), "r"(br[0]), "r"(br[1]), "r"(br[2]), "r"(br[3]), "r"(br[4]), "r"(br[5]), "r"(br[6]), "r"(br[7]),
+                      "r"(br[8]), "r"(br[9]), "r"(br[10]), "r"(br[11]), "r"(br[12]), "r"(br[13]), "r"(br[14]), "r"(br[15])
+                    : "memory");
+            }
+        } else {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(bias_s[0])) : "memory");
+        }
+    };
+    if (warp < kMmaWarp) {
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int b = (warp >> 2); b < kBlocks; b += kEpiGroups) init_block(lane_addr + b * NOUT);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp > kMmaWarp) {
         // ------------------------------------------------------------------ producers: input rows -> ring
-        const int pt = threadIdx.x - 160;
+        // Thread (ch = k-chunk, s_base) copies slots s_base + 16 k (k = 0..8) of every row: all offsets are per-thread
+        // constants, so a row costs ~3 instructions per 16-byte copy (the four producer warps sit alone on their
+        // schedulers: their own instruction latency, not bandwidth, is what a longer loop body would cost).
+        const int pt = threadIdx.x - 32 * (kMmaWarp + 1);
+        unsigned long long w0 = 0;
+        const long long tstart = clock64();
+        const int ch = pt & 7, s_base = pt >> 3;
+        const uint32_t dst_off = ch * kChunkBytes + s_base * 16;
+        const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in);
         uint32_t e = 0;
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        for (int item = blockIdx.x; item < ((p.dbg & 128) ? 0 : p.items); item += gridDim.x) {
             const Item it = decode_item(p, item);
+            uint32_t xmask = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int s = s_base + 16 * k, x = it.x0 - 1 + s;
+                if (s < kSlots && x >= 0 && x < p.W) xmask |= 1u << k;
+            }
+            // activations are stored chunk-swizzled: 16-byte chunk c of pixel x sits at position c ^ (x & 7) of its 128 bytes
+            const long long col_off = (long long)(it.x0 - 1 + s_base) * 128 + ((ch ^ ((it.x0 - 1 + s_base) & 7)) * 16);   // bytes from the row start
             for (int r = 0; r < it.rows + 2; ++r, ++e) {
                 const uint32_t st = e % kStages;
-                k1::mbar_wait(bEmpty(st), ((e / kStages) & 1u) ^ 1u);
+                mbar_wait_t(bEmpty(st), ((e / kStages) & 1u) ^ 1u, w0, prof);
                 const int y = it.y0 - 1 + r;
                 const bool yok = (y >= 0) && (y < p.H);
-                const __nv_bfloat16* rowp = p.in + ((size_t)it.b * p.H + (yok ? y : 0)) * p.W * 64;
-                const uint32_t dst0 = ring + st * kRowBytes;
-                for (int i = pt; i < kSlots * 8; i += kProducers) {
-                    const int s = i >> 3, ch = i & 7;
-                    const int x = it.x0 - 1 + s;
-                    const bool ok = yok && (x >= 0) && (x < p.W);
-                    const __nv_bfloat16* src = ok ? rowp + (size_t)x * 64 + ch * 8 : p.in;
-                    if (!(p.dbg & 1)) cp_async16(dst0 + ch * kChunkBytes + s * 16, src, ok ? 16u : 0u);
+                const uint32_t m = (yok && !(p.dbg & 1)) ? xmask : 0u;
+                const unsigned char* src0 = in_b + ((size_t)it.b * p.H + (yok ? y : 0)) * p.W * 128 + col_off;
+                const uint32_t dst0 = ring + st * kRowBytes + dst_off;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    if (k == 8 && s_base >= kSlots - 128) break;             // slots 128, 129: threads with s_base < 2
+                    const bool ok = (m >> k) & 1u;
+                    cp_async16(dst0 + k * 256, ok ? src0 + k * 2048 : in_b, ok ? 16u : 0u);
                 }
-                cp_async_commit();
-                if (e >= (uint32_t)kLag) {
-                    cp_async_wait<kLag>();
-                    k1::fence_proxy_async();
-                    mbar_arrive(bFull((e - kLag) % kStages));
-                }
+                // arrives on the row's barrier when this thread's copies above have landed (no wait in the producer)
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bFull(st)) : "memory");
             }
         }
-        cp_async_wait<0>();
-        k1::fence_proxy_async();
-        for (uint32_t k = (e >= (uint32_t)kLag ? e - kLag : 0u); k < e; ++k) mbar_arrive(bFull(k % kStages));
-    } else if (warp == 4) {
+        if (prof && pt == 0) { atomicAdd(&g_tc_prof[0], w0); atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - tstart)); }
+    } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer
         // The whole warp runs the loop (warp-uniform control and address math stay on the uniform datapath); one
         // elected lane issues the tensor-core instructions.
-        uint32_t e_base = 0, waited = 0, t = 0;
+        uint32_t e = 0, t_base = 0;
+        unsigned long long w1 = 0, w2 = 0;
+        const long long tstart = clock64();
         const uint64_t desc_hi_a = ((uint64_t)(kChunkBytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-        const uint64_t b_desc0 = make_desc(s0 + kOffW, NOUT * 16, 128);
+        const uint64_t b_desc0 = make_desc(s0 + kOffW, 3 * NOUT * 16, 128);
         const bool leader = elect_one();
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const Item it = decode_item(p, item);
-            for (int j = 0; j < it.rows; ++j, ++t) {
-                const uint32_t as = t & 1u;
-                k1::mbar_wait(bTEmpty(as), ((t >> 1) & 1u) ^ 1u);
-                while (waited <= e_base + j + 2) {
-                    k1::mbar_wait(bFull(waited % kStages), (waited / kStages) & 1u);
-                    ++waited;
+            const int R = it.rows;
+            for (int i = 0; i < R + 2; ++i, ++e) {
+                const uint32_t st = e % kStages;
+                if (i < R && !(p.dbg & 64)) {                  // block of the output row that starts with this input row
+                    const uint32_t t = t_base + i;
+                    mbar_wait_t(bTEmpty(blk(t)), ((t / kBlocks) & 1u) ^ 1u, w1, prof);
                 }
+                if (!(p.dbg & 128)) mbar_wait_t(bFull(st), (e / kStages) & 1u, w2, prof);
+                if (!(p.dbg & 32)) k1::fence_proxy_async();   // the row was written through the generic proxy (cp.async); the MMA reads it through the async proxy
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * 64;
                 if (leader && !(p.dbg & 4)) {
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const uint32_t a_row = ring + ((e_base + j + dy) % kStages) * kRowBytes;
-                        const uint64_t a_desc0 = desc_hi_a | (uint64_t)((a_row & 0x3FFFFu) >> 4);
+                    const uint32_t a_row = ring + st * kRowBytes;
+                    const uint64_t a_desc0 = desc_hi_a | (uint64_t)((a_row & 0x3FFFFu) >> 4);
+                    const int dy_hi = i < 2 ? i : 2;
+                    int dy = i - (R - 1) > 0 ? i - (R - 1) : 0;
+                    while (dy <= dy_hi) {
+                        const uint32_t b = blk(t_base + i - dy);
+                        int n = dy_hi - dy + 1;
+                        if (n > (int)(kBlocks - b)) n = kBlocks - b;
+                        const uint32_t idesc = make_idesc(n * NOUT);
+                        const uint32_t d_tmem = tmem_base + b * NOUT;
+                        const uint64_t b_dy = b_desc0 + (uint64_t)((dy * NOUT * 16) >> 4);
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 // start-address field += byte offset / 16 (never carries out of its 14 bits: smem < 256 KB)
                                 const uint64_t ad = a_desc0 + (uint64_t)((dx * 16 + ks * 2 * kChunkBytes) >> 4);
-                                const uint64_t bd = b_desc0 + (uint64_t)((((dy * 3 + dx) * 8 + ks * 2) * (NOUT * 16)) >> 4);
-                                tc_mma_bf16(d_tmem, ad, bd, kIdesc, (dy | dx | ks) != 0);
+                                const uint64_t bd = b_dy + (uint64_t)(((dx * 8 + ks * 2) * (3 * NOUT * 16)) >> 4);
+                                tc_mma_bf16(d_tmem, ad, bd, idesc, 1);
                             }
                         }
+                        dy += n;
                     }
                 }
                 __syncwarp();
                 if (leader) {
-                    tc_commit(bEmpty((e_base + j) % kStages));           // input row j is not needed by later output rows
-                    if (j == it.rows - 1) {
-                        tc_commit(bEmpty((e_base + j + 1) % kStages));
-                        tc_commit(bEmpty((e_base + j + 2) % kStages));
-                    }
-                    tc_commit(bTFull(as));
+                    if (!(p.dbg & 128)) tc_commit(bEmpty(st));                // each input row is consumed in one go
+                    if (i >= 2 && !(p.dbg & 64)) tc_commit(bTFull(blk(t_base + i - 2)));   // output row i - 2 has its three input rows
                 }
                 __syncwarp();
             }
-            e_base += it.rows + 2;
+            t_base += R;
         }
+        if (prof && lane == 0) { atomicAdd(&g_tc_prof[1], w1); atomicAdd(&g_tc_prof[2], w2); atomicAdd(&g_tc_prof[4], (unsigned long long)(clock64() - tstart)); }
     } else {
         // ------------------------------------------------------------------ epilogue warps
+        // Groups of four warps (TMEM lane quadrant = warp & 3); with kEpiGroups = 2 they take alternate output rows
+        // (measured: no gain, the epilogue is not the bottleneck, and 13 warps cap the kernel at 128 registers).
         uint32_t t = 0;
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        unsigned long long w3 = 0;
+        const long long tstart = clock64();
+        const uint32_t grp = warp >> 2, quad = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int item = blockIdx.x; item < ((p.dbg & 64) ? 0 : p.items); item += gridDim.x) {
             const Item it = decode_item(p, item);
             for (int j = 0; j < it.rows; ++j, ++t) {
-                const uint32_t as = t & 1u;
-                k1::mbar_wait(bTFull(as), (t >> 1) & 1u);
+                if (kEpiGroups > 1 && (t % kEpiGroups) != grp) continue;
+                const uint32_t b = blk(t);
+                mbar_wait_t(bTFull(b), (t / kBlocks) & 1u, w3, prof);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * 64;
-                const int x = it.x0 + warp * 32 + lane, y = it.y0 + j;
+                const uint32_t taddr = lane_addr + b * NOUT;
+                const int x = it.x0 + quad * 32 + lane, y = it.y0 + j;
                 const size_t pix = ((size_t)it.b * p.H + y) * p.W + x;
                 if (NOUT == 64) {
                     uint32_t v[64];
+                    if (!(p.dbg & 8)) {
                     PNP_TMEM_LD32(taddr, v, 0);
                     PNP_TMEM_LD32(taddr + 32, v, 32);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+                    if (!(p.dbg & 16)) {
+                    init_block(taddr);                           // next use of the block starts from the bias again
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bTEmpty(as));
-                    if (x < p.W && !(p.dbg & 2)) {
-                        __nv_bfloat16* dst = p.out + pix * 64;
+                    if (lane == 0) mbar_arrive(bTEmpty(b));
+                    // bf16 row of this pixel -> staging tile in the global (chunk-swizzled) layout -> one 4 KB bulk copy per
+                    // warp (async proxy; the LSU never sees the global stores).  A warp only touches its own 32 staging
+                    // rows, so the only ordering needed is its own: its previous copy (two rows ago) must have read them.
+                    if (lane == 0) {                           // the copy that last read this staging tile has finished reading
+                        if (kEpiGroups == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                    const uint32_t sbuf = (kEpiGroups == 1) ? (t & 1u) : grp;      // two staging tiles in all
+                    const uint32_t swarp = s0 + kOffOut + sbuf * (kTileM * 128) + quad * (32 * 128);
+                    const uint32_t srow = swarp + lane * 128;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {           // 16 channels = one 32-byte sector per store
-                            float f[16];
+                    for (int q = 0; q < 8; ++q) {
+                        uint32_t o[4];
 #pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                const float4 bb = reinterpret_cast<const float4*>(bias_s)[4 * q + k4];
-                                f[4 * k4 + 0] = bb.x; f[4 * k4 + 1] = bb.y; f[4 * k4 + 2] = bb.z; f[4 * k4 + 3] = bb.w;
-                            }
-                            uint32_t o[8];
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) {
-                                f[k] += __uint_as_float(v[16 * q + k]);
-                                if (p.relu) f[k] = fmaxf(f[k], 0.f);
-                            }
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) o[k] = pack_bf16x2(f[2 * k], f[2 * k + 1]);
-                            st_global_v8(dst + 16 * q, o);
+                        for (int k = 0; k < 4; ++k) {
+                            float f0 = __uint_as_float(v[8 * q + 2 * k]), f1 = __uint_as_float(v[8 * q + 2 * k + 1]);
+                            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                            o[k] = pack_bf16x2(f0, f1);
                         }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + 16 * (q ^ (lane & 7))), "r"(o[0]), "r"(o[1]),
+                                     "r"(o[2]), "r"(o[3])
+                                     : "memory");
+                    }
+                    k1::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int xw = it.x0 + quad * 32;                       // first pixel of this warp
+                        const int npx = p.W - xw < 32 ? p.W - xw : 32;
+                        if (npx > 0 && !(p.dbg & 2))
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out + (pix - lane) * 64),
+                                         "r"(swarp), "r"(npx * 128)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 } else {
                     uint32_t v0;
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v0) : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    init_block(taddr);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bTEmpty(as));
-                    if (x < p.W) {
-                        const float n = __uint_as_float(v0) + bias_s[0];
+                    if (lane == 0) mbar_arrive(bTEmpty(b));
+                    if (x < p.W && !(p.dbg & 2)) {
+                        const float n = __uint_as_float(v0);
                         p.out_f32[pix] = p.resid ? p.resid[(size_t)it.b * p.resid_bstride + (size_t)y * p.W + x] - n : n;
                     }
                 }
             }
         }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all staged rows have been written out
+        if (prof && warp == 0 && lane == 0) { atomicAdd(&g_tc_prof[3], w3); atomicAdd(&g_tc_prof[6], (unsigned long long)(clock64() - tstart)); }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 4)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (warp == kMmaWarp)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsK) : "memory");
 }
 
 // First layer: conv3x3 CIN -> 64 + bias + ReLU on the CUDA cores (K = 9 CIN is too thin for the tensor cores and the
@@ -350,31 +468,53 @@ __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict
     int xx = (int)(pix % (uint32_t)W);
     int yy = (int)((pix / (uint32_t)W) % (uint32_t)H);
     uint32_t b = pix / ((uint32_t)W * H);
-    for (int it = 0; it < kHeadPix; ++it, pix += 32, xx += 32) {
-        if (pix >= npix) return;
-        while (xx >= W) { xx -= W; if (++yy == H) { yy = 0; ++b; } }
-        float f[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) f[c] = br[c];
+    // the 3x3 neighbourhood of pixel (b, yy, xx), all CIN channels, rounded to bf16
+    auto load_nb = [&](float (&v)[CIN][9], int xq, int yq, uint32_t bq) {
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-            const float* img = x + ((size_t)b * CIN + ci) * (size_t)H * W;
+            const float* img = x + ((size_t)bq * CIN + ci) * (size_t)H * W;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const int y2 = yy + ky - 1, x2 = xx + kx - 1;
-                    float v = 0.f;
-                    if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) v = __ldg(img + (size_t)y2 * W + x2);
-                    v = __bfloat162float(__float2bfloat16(v));
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) f[c] = fmaf(wr[ci][c][ky * 3 + kx], v, f[c]);
+                    const int y2 = yq + ky - 1, x2 = xq + kx - 1;
+                    float t = 0.f;
+                    if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) t = __ldg(img + (size_t)y2 * W + x2);
+                    v[ci][ky * 3 + kx] = t;
                 }
         }
+    };
+    float cur[CIN][9], nxt[CIN][9];
+    load_nb(cur, xx, yy, b);
+    for (int it = 0; it < kHeadPix; ++it) {
+        // prefetch the next pixel's neighbourhood before the arithmetic of this one (the loop is latency-bound otherwise)
+        const uint32_t pix_n = pix + 32;
+        int xn = xx + 32, yn = yy;
+        uint32_t bn = b;
+        while (xn >= W) { xn -= W; if (++yn == H) { yn = 0; ++bn; } }
+        const bool more = (it + 1 < kHeadPix) && (pix_n < npix);
+        if (more) load_nb(nxt, xn, yn, bn);
+        float f[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[c] = br[c];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float v = __bfloat162float(__float2bfloat16(cur[ci][t]));
+#pragma unroll
+                for (int c = 0; c < 8; ++c) f[c] = fmaf(wr[ci][c][t], v, f[c]);
+            }
         uint4 o;
         o.x = pack_bf16x2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)); o.y = pack_bf16x2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
         o.z = pack_bf16x2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)); o.w = pack_bf16x2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
-        *reinterpret_cast<uint4*>(out + (size_t)pix * 64 + ch * 8) = o;
+        *reinterpret_cast<uint4*>(out + (size_t)pix * 64 + (ch ^ (xx & 7)) * 8) = o;      // chunk-swizzled activation layout
+        if (!more) return;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) cur[ci][t] = nxt[ci][t];
+        pix = pix_n; xx = xn; yy = yn; b = bn;
     }
 }
 

@@ -1170,4 +1170,13 @@ int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H
     return dncnn_forward_impl(x, out, B, cin, H, W, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, residual, act0, act1, ST(s));
 }
 
+// debug only (not part of include/pnpadmm.h): read and clear the wait-time counters of conv64_tc_kernel (PNPADMM_TC_DEBUG bit 256)
+int pnpadmm_debug_tc_prof(unsigned long long* h_out8) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(h_out8, tc::g_tc_prof, sizeof(unsigned long long) * 8));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyToSymbol(tc::g_tc_prof, z, sizeof(z)));
+    return PNPADMM_OK;
+}
+
 }  // extern "C"

@@ -32,15 +32,17 @@ def conv_layers(net: nn.Module) -> List[nn.Conv2d]:
 
 
 def pack_conv64(weight: torch.Tensor, n_out: int = 64) -> torch.Tensor:
-    """[c_out][64][3][3] float -> [tap = ky*3+kx][c_in // 8][n_out][c_in % 8] bf16 (rows c_out.. n_out-1 zero):
-    the shared-memory image of the B operand (no-swizzle K-major core matrices of 8 c_out x 8 c_in)."""
+    """[c_out][64][3][3] float -> [kx][c_in // 8][ky][n_out][c_in % 8] bf16 (rows c_out.. n_out-1 zero): the
+    shared-memory image of the B operand (no-swizzle K-major core matrices of 8 rows x 8 c_in).  For one (kx, k-chunk)
+    the three ky taps are stacked along N (row = ky * n_out + c_out), so one N = 3 n_out instruction feeds the three
+    output rows an input row contributes to (csrc/dncnn_tc.cuh)."""
     co = weight.shape[0]
     if weight.shape[1:] != (64, 3, 3) or co > n_out:
         raise ValueError(f'bad weight shape {tuple(weight.shape)}')
     w = torch.zeros((n_out, 64, 3, 3), dtype=torch.float32, device=weight.device)
     w[:co] = weight.float()
-    w = w.permute(2, 3, 1, 0).reshape(9, 8, 8, n_out)          # tap, c_in // 8, c_in % 8, c_out
-    return w.permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
+    w = w.permute(3, 1, 2, 0).reshape(3, 8, 8, 3, n_out)       # kx, c_in // 8, c_in % 8, ky, c_out
+    return w.permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
 
 
 def pack_dncnn(net: nn.Module, device) -> Tuple[dict, int, int]:
@@ -104,16 +106,27 @@ class FusedDnCNN:
         return out
 
 
+def swizzle_chunks(x_nhwc: torch.Tensor) -> torch.Tensor:
+    """Dense (B, H, W, 64) <-> the kernels' inter-layer layout: the 16-byte chunk c (8 channels) of pixel x sits at
+    position c ^ (x & 7).  The permutation is an involution, so the same call converts both ways."""
+    B, H, W, C = x_nhwc.shape
+    v = x_nhwc.reshape(B, H, W, 8, 8)
+    xs = torch.arange(W, device=x_nhwc.device) & 7
+    pos = torch.arange(8, device=x_nhwc.device)[None, :] ^ xs[:, None]          # [W][8]: source chunk of each position
+    idx = pos[None, None, :, :, None].expand(B, H, W, 8, 8)
+    return torch.gather(v, 3, idx).reshape(B, H, W, C).contiguous()
+
+
 def conv64(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.Tensor:
     """One 64 -> 64 layer through ``pnpadmm_conv64_bf16``: x (B, H, W, 64) bf16 CUDA -> same shape (parity tests)."""
     lib = _abi.load()
     if x_nhwc.dtype != torch.bfloat16 or x_nhwc.ndim != 4 or x_nhwc.shape[-1] != 64 or not x_nhwc.is_cuda:
         raise ValueError('expected a (B, H, W, 64) bf16 CUDA tensor')
-    x = x_nhwc.contiguous()
+    x = swizzle_chunks(x_nhwc)
     B, H, W, _ = (int(v) for v in x.shape)
     wp = pack_conv64(weight.to(x.device))
     bs = bias.to(x.device, torch.float32).contiguous()
     out = torch.empty_like(x)
     _abi.check(lib.pnpadmm_conv64_bf16(x.data_ptr(), out.data_ptr(), wp.data_ptr(), bs.data_ptr(), B, H, W, int(relu),
                                        torch.cuda.current_stream().cuda_stream))
-    return out
+    return swizzle_chunks(out)

@@ -16,15 +16,15 @@ from pnp_admm_cnc_mri_b200 import dncnn_fused as df
 
 
 def _emulate_packed_conv(x_nhwc, wp, bias, relu):
-    """out[y, x, co] = sum_{tap, kc, c8} in[y+ky-1, x+kx-1, 8 kc + c8] * wp[tap][kc][co][c8]  (zero padding)."""
+    """out[y, x, co] = sum_{kx, kc, ky, c8} in[y+ky-1, x+kx-1, 8 kc + c8] * wp[kx][kc][ky][co][c8]  (zero padding)."""
     B, H, W, _ = x_nhwc.shape
-    n_out = wp.shape[2]
+    n_out = wp.shape[3]
     xp = F.pad(x_nhwc.float(), (0, 0, 1, 1, 1, 1))
     out = torch.zeros(B, H, W, n_out)
     for ky in range(3):
         for kx in range(3):
             a = xp[:, ky:ky + H, kx:kx + W, :].reshape(B, H, W, 8, 8)              # ..., kc, c8
-            out += torch.einsum('bhwkc,knc->bhwn', a, wp[ky * 3 + kx].float())
+            out += torch.einsum('bhwkc,knc->bhwn', a, wp[kx, :, ky].float())
     out += bias.float()
     return out.clamp_min(0) if relu else out
 
@@ -35,14 +35,14 @@ def test_pack_conv64_matches_conv2d():
     b = torch.randn(64, generator=g)
     x = torch.randn(2, 5, 7, 64, generator=g).to(torch.bfloat16)
     wp = df.pack_conv64(w)
-    assert wp.shape == (9, 8, 64, 8) and wp.dtype == torch.bfloat16
+    assert wp.shape == (3, 8, 3, 64, 8) and wp.dtype == torch.bfloat16
     got = _emulate_packed_conv(x, wp, b, relu=True)
     want = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1)).permute(0, 2, 3, 1)
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-4)
     # last layer: one real output row, padded to N = 16
     wt = torch.randn(1, 64, 3, 3, generator=g)
     wpt = df.pack_conv64(wt, 16)
-    assert wpt.shape == (9, 8, 16, 8) and float(wpt[:, :, 1:].abs().max()) == 0.0
+    assert wpt.shape == (3, 8, 3, 16, 8) and float(wpt[:, :, :, 1:].abs().max()) == 0.0
     got = _emulate_packed_conv(x, wpt, torch.zeros(16), relu=False)[..., 0]
     want = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), None, padding=1)[:, 0]
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-4)
@@ -52,8 +52,8 @@ def test_pack_dncnn_layer_split():
     net = denoisers.build_model('dncnn_25')
     packed, cin, n_mid = df.pack_dncnn(net, 'cpu')
     assert (cin, n_mid) == (1, 15)
-    assert packed['w_mid'].shape == (15, 9, 8, 64, 8) and packed['b_mid'].shape == (15, 64)
-    assert packed['w_head'].shape == (64, 1, 3, 3) and packed['w_tail'].shape == (9, 8, 16, 8)
+    assert packed['w_mid'].shape == (15, 3, 8, 3, 64, 8) and packed['b_mid'].shape == (15, 64)
+    assert packed['w_head'].shape == (64, 1, 3, 3) and packed['w_tail'].shape == (3, 8, 3, 16, 8)
     net2 = denoisers.build_model('fdncnn_gray')
     _, cin2, n_mid2 = df.pack_dncnn(net2, 'cpu')
     assert (cin2, n_mid2) == (2, 18)

@@ -25,3 +25,11 @@ for r in range(reps + 2):
 t = min(ts)
 fl = 2.0 * 64 * 64 * 9 * H * W * B
 print(f'dbg={os.environ.get("PNPADMM_TC_DEBUG", "0")} B={B}: {t * 1e3:.1f} us  {fl / t / 1e9:.0f} TFLOP/s  {2 * a.numel() * 2 / t / 1e6:.0f} GB/s', flush=True)
+
+if int(os.environ.get('PNPADMM_TC_DEBUG', '0')) & 256:
+    import ctypes
+    buf = (ctypes.c_ulonglong * 8)()
+    lib.pnpadmm_debug_tc_prof(buf)
+    n = (reps + 2) * 148
+    names = ['producer wait empty', 'mma wait tempty', 'mma wait full', 'epilogue wait tfull', 'mma total', 'producer total', 'epilogue total']
+    print('  per CTA and launch, kcycles: ' + ', '.join(f'{nm} {buf[i] / n / 1e3:.0f}' for i, nm in enumerate(names)))
