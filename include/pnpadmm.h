@@ -208,7 +208,7 @@ int pnpadmm_metrics_f64(const double* x, const uint8_t* ref, int B, int N, int q
  * models/network_dncnn.py:36-67 DnCNN.forward = x - model(x), :120-141 FDnCNN.forward = model(x);
  * called from denoising_step S6:353-359, denoising_step1 S3:20-35, denoising_step2 S6:19-34):
  *     conv3x3 cin->64 + ReLU,  n_mid x [conv3x3 64->64 + ReLU],  conv3x3 64->1      (nb = n_mid + 2)
- * bf16 operands, fp32 accumulation (tcgen05 / TMEM), bf16 NHWC activations between layers,
+ * bf16 operands, fp32 accumulation (tcgen05 / TMEM), bf16 activations between layers,
  * zero padding 1, bias in every layer (act_mode 'R': no batch norm).
  *   x      [B][cin][H][W] f32 (cin = 1 DnCNN, 2 FDnCNN: noise-level map in channel 1)
  *   out    [B][H][W] f32:  residual != 0 ? x[:, 0] - n(x) : n(x)
@@ -217,8 +217,8 @@ int pnpadmm_metrics_f64(const double* x, const uint8_t* ref, int B, int N, int q
  *   w_tail [kx][c_in / 8][ky][16][c_in % 8] bf16, rows 1..15 of every ky zero;  b_tail [1] f32
  *   act0, act1: two device buffers of pnpadmm_dncnn_activation_bytes(B, H, W) bytes, 16-byte aligned.
  * pnpadmm_conv64_bf16 runs ONE 64->64 layer (w / bias as one w_mid layer) and exists for the parity tests;
- * in / out are [B][H][W][64] bf16 in the kernels' inter-layer layout: NHWC with the 16-byte chunk c (8 channels)
- * of pixel x stored at position c ^ (x & 7) of the pixel's 128 bytes.
+ * in / out are bf16 in the kernels' inter-layer layout [B][H][8][W][8] ("chunk-planar rows": channel c of pixel
+ * (y, x) at [y][c / 8][x][c % 8]), which makes every tile transfer a contiguous 1-D bulk copy.
  * ------------------------------------------------------------------------------------- */
 size_t pnpadmm_dncnn_activation_bytes(int B, int H, int W);
 int pnpadmm_conv64_bf16(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu,

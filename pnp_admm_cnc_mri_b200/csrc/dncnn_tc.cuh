@@ -8,21 +8,21 @@
 //         act[y + ky - 1][x0 + m + kx - 1][c_in] * w[c_out][c_in][ky][kx]            M = 128, N = 64, K = 576
 //
 // issued as 36 `tcgen05.mma.cta_group::1.kind::f16` (128 x 64 x 16, bf16 in, fp32 accumulate in TMEM) by one
-// thread.  Activations are NHWC bf16 (128 B per pixel; between layers the 16-byte channel chunk c of pixel x is stored
-// at position c ^ (x & 7), which makes the epilogue's staging tile bank-conflict free and bulk-copyable as is).  Shared memory uses the NO-SWIZZLE K-major canonical
-// layout (core matrix = 8 rows x 16 B, contiguous 128 B):
+// thread.  Activations are bf16 in CHUNK-PLANAR ROWS, [B][H][8 chunks][W][8 channels]: a row of the image is 8 planes of
+// W x 16 bytes.  Shared memory uses the NO-SWIZZLE K-major canonical layout (core matrix = 8 rows x 16 B = 128 B):
 //     A row buffer : [k-chunk 0..7][slot 0..130][8 c_in]   slot s <-> pixel x0 - 1 + s (1-pixel halo each side)
-// so the tap shift kx is a 16-byte shift of the descriptor start address and the tap shift ky selects another
-// row buffer: the im2col matrix is never materialised and every input row is loaded ONCE per strip and reused by
-// the 9 taps of three output rows.  The row buffers form a 6-deep ring filled by four producer warps with 16-byte
-// `cp.async` (zero-fill outside the image = the convolution's zero padding); the 72 KB of weights of the layer
+// so the tap shift kx is a 16-byte shift of the descriptor start address and the tap shift ky selects another row
+// buffer: the im2col matrix is never materialised, every input row is loaded ONCE per strip, and a k-chunk plane of a
+// row buffer is 2080 CONTIGUOUS bytes of global memory: one 1-D bulk copy (cp.async.bulk, TMA engine) per plane, no
+// tensor map and no LSU instruction on the load path; zero padding comes from a zero buffer.  The row buffers form a
+// 6-deep ring; the 72 KB of weights of the layer
 //     B            : [kx 0..2][k-chunk 0..7][ky 0..2][c_out 0..N)[8 c_in]   (the three ky taps stacked along N)
-// stay resident for the persistent CTA's whole life.  Accumulators are double-buffered in TMEM so the epilogue
-// warps (tcgen05.ld -> bias -> ReLU -> bf16 -> 128 B per pixel) overlap the next row's MMAs.
+// stay resident for the persistent CTA's whole life.  Accumulators live in an 8-block ring in TMEM (see the kernel)
+// so the epilogue warps (tcgen05.ld -> ReLU -> bf16 -> staging tile -> 8 bulk stores of 2 KB) overlap the MMAs.
 //
 //   warps 0-3  : epilogue (TMEM lane quadrant = warp & 3)
 //   warp  4    : TMEM alloc, one elected lane issues the MMAs
-//   warps 5-8  : producers
+//   warp  5    : producer (one lane issues the bulk copies)
 //   mbarriers  : full[6] / empty[6] (producers <-> MMA), tfull[8] / tempty[8] (MMA <-> epilogue, one pair per block)
 //
 // The first layer (c_in = 1 or 2) and nothing else runs on the CUDA cores (it is a 0.3 ms NHWC write); the last
@@ -43,10 +43,9 @@ constexpr int kPPad = 131;                     // slot pitch of a k-chunk plane,
 constexpr int kChunkBytes = kPPad * 16;        // = LBO of the A descriptor
 constexpr int kRowBytes = 8 * kChunkBytes;     // 16768
 constexpr int kStages = 6;
-constexpr int kThreads = 288;
-constexpr int kProducers = 128;
+constexpr int kThreads = 192;                  // warps 0-3 epilogue, 4 MMA, 5 producer (one lane issues the bulk copies)
 constexpr int kEpiGroups = 1;                  // epilogue groups of four warps; group g takes the output rows t = g (mod kEpiGroups)
-constexpr int kMmaWarp = 4 * kEpiGroups;       // warps [0, 4 g): epilogue, then one MMA warp, then four producer warps
+constexpr int kMmaWarp = 4 * kEpiGroups;       // warps [0, 4 g): epilogue, then the MMA warp, then the producer warp
 constexpr int kOffW = 0;
 constexpr int kWBytesMax = 9 * 8 * 64 * 16;    // 73728
 constexpr int kOffRing = kWBytesMax;
@@ -55,12 +54,16 @@ constexpr int kBlocks = 8;                     // accumulator blocks (output row
 constexpr int kNumBars = 2 * kStages + 2 * kBlocks;
 constexpr int kOffTmemPtr = kOffBar + 8 * kNumBars;
 constexpr int kOffBias = kOffTmemPtr + 16;
-constexpr int kOffOut = kOffBias + 64 * 4;     // two staging tiles [128 pixels][128 B] (global layout, see below)
+constexpr int kOffOut = kOffBias + 64 * 4;     // two staging tiles [8 chunks][128 pixels][16 B]
 constexpr int kSmemBytes = kOffOut + 2 * kTileM * 128;
+constexpr int kRowTxBytes = 8 * kSlots * 16;   // bytes a staged input row receives (data + zero padding)
+
+// source of the zero padding (rows above / below the image, the pixel left / right of it)
+__device__ __align__(128) unsigned char g_zero[kSlots * 16];
 
 struct ConvParams {
-    const __nv_bfloat16* in;    // [B][H][W][64]
-    __nv_bfloat16* out;         // [B][H][W][64]           (N = 64 layers)
+    const __nv_bfloat16* in;    // [B][H][8 chunks][W][8 channels]   (chunk-planar rows, see the file header)
+    __nv_bfloat16* out;         // same layout                       (N = 64 layers)
     const float* resid;         // tail: residual source, pixel (b, y, x) at resid[b * resid_bstride + y * W + x] (may be null)
     float* out_f32;             // tail: [B][H][W]
     long long resid_bstride;
@@ -89,6 +92,14 @@ PNP_D void mbar_wait_t(uint32_t bar, uint32_t parity, unsigned long long& acc, b
     const long long t0 = clock64();
     mbar_wait(bar, parity);
     acc += (unsigned long long)(clock64() - t0);
+}
+PNP_D void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {      // global -> shared, counts on `bar`
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+PNP_D void bulk_store(void* dst, uint32_t src, uint32_t bytes) {                          // shared -> global, bulk async-group
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 PNP_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 PNP_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -201,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { k1::mbar_init(bFull(i), kProducers); k1::mbar_init(bEmpty(i), 1); }
+        for (int i = 0; i < kStages; ++i) { k1::mbar_init(bFull(i), 1); k1::mbar_init(bEmpty(i), 1); }
         for (int i = 0; i < kBlocks; ++i) { k1::mbar_init(bTFull(i), 1); k1::mbar_init(bTEmpty(i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -251,46 +262,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
     tc_fence_after();
 
     if (warp > kMmaWarp) {
-        // ------------------------------------------------------------------ producers: input rows -> ring
-        // Thread (ch = k-chunk, s_base) copies slots s_base + 16 k (k = 0..8) of every row: all offsets are per-thread
-        // constants, so a row costs ~3 instructions per 16-byte copy (the four producer warps sit alone on their
-        // schedulers: their own instruction latency, not bandwidth, is what a longer loop body would cost).
-        const int pt = threadIdx.x - 32 * (kMmaWarp + 1);
+        // ------------------------------------------------------------------ producer: input rows -> ring
+        // One lane streams the input rows with 1-D bulk copies (TMA engine, no LSU): in the chunk-planar layout the
+        // 130 pixels a row buffer needs from one 8-channel chunk are 2080 contiguous bytes of global memory and of the
+        // A operand's plane, so a row is 8 copies (+ 16-byte zero copies for the pixel left / right of the image and
+        // whole zero planes for the rows above / below it: the convolution's padding).
         unsigned long long w0 = 0;
         const long long tstart = clock64();
-        const int ch = pt & 7, s_base = pt >> 3;
-        const uint32_t dst_off = ch * kChunkBytes + s_base * 16;
-        const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in);
-        uint32_t e = 0;
-        for (int item = blockIdx.x; item < ((p.dbg & 128) ? 0 : p.items); item += gridDim.x) {
-            const Item it = decode_item(p, item);
-            uint32_t xmask = 0;
+        if (lane == 0) {
+            const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in);
+            const size_t plane = (size_t)p.W * 16, rowb = 8 * plane;
+            uint32_t e = 0;
+            for (int item = blockIdx.x; item < ((p.dbg & 128) ? 0 : p.items); item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                const int xs = it.x0 - 1;
+                const int lo = xs < 0 ? 0 : xs;
+                const int hi = it.x0 + kTileM + 1 < p.W ? it.x0 + kTileM + 1 : p.W;
+                const uint32_t nleft = lo - xs, nvalid = hi - lo, nright = kSlots - nleft - nvalid;
+                for (int r = 0; r < it.rows + 2; ++r, ++e) {
+                    const uint32_t st = e % kStages;
+                    mbar_wait_t(bEmpty(st), ((e / kStages) & 1u) ^ 1u, w0, prof);
+                    const uint32_t bar = bFull(st), dst0 = ring + st * kRowBytes;
+                    if (p.dbg & 1) { mbar_arrive(bar); continue; }
+                    k1::mbar_arm_tx(bar, kRowTxBytes);
+                    const int y = it.y0 - 1 + r;
+                    if (y < 0 || y >= p.H) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const int s = s_base + 16 * k, x = it.x0 - 1 + s;
-                if (s < kSlots && x >= 0 && x < p.W) xmask |= 1u << k;
-            }
-            // activations are stored chunk-swizzled: 16-byte chunk c of pixel x sits at position c ^ (x & 7) of its 128 bytes
-            const long long col_off = (long long)(it.x0 - 1 + s_base) * 128 + ((ch ^ ((it.x0 - 1 + s_base) & 7)) * 16);   // bytes from the row start
-            for (int r = 0; r < it.rows + 2; ++r, ++e) {
-                const uint32_t st = e % kStages;
-                mbar_wait_t(bEmpty(st), ((e / kStages) & 1u) ^ 1u, w0, prof);
-                const int y = it.y0 - 1 + r;
-                const bool yok = (y >= 0) && (y < p.H);
-                const uint32_t m = (yok && !(p.dbg & 1)) ? xmask : 0u;
-                const unsigned char* src0 = in_b + ((size_t)it.b * p.H + (yok ? y : 0)) * p.W * 128 + col_off;
-                const uint32_t dst0 = ring + st * kRowBytes + dst_off;
+                        for (int c = 0; c < 8; ++c) bulk_load(dst0 + c * kChunkBytes, g_zero, kSlots * 16, bar);
+                    } else {
+                        const unsigned char* src = in_b + ((size_t)it.b * p.H + y) * rowb + (size_t)lo * 16;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    if (k == 8 && s_base >= kSlots - 128) break;             // slots 128, 129: threads with s_base < 2
-                    const bool ok = (m >> k) & 1u;
-                    cp_async16(dst0 + k * 256, ok ? src0 + k * 2048 : in_b, ok ? 16u : 0u);
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t d = dst0 + c * kChunkBytes;
+                            if (nleft) bulk_load(d, g_zero, nleft * 16, bar);
+                            bulk_load(d + nleft * 16, src + c * plane, nvalid * 16, bar);
+                            if (nright) bulk_load(d + (nleft + nvalid) * 16, g_zero, nright * 16, bar);
+                        }
+                    }
                 }
-                // arrives on the row's barrier when this thread's copies above have landed (no wait in the producer)
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bFull(st)) : "memory");
             }
+            if (prof) { atomicAdd(&g_tc_prof[0], w0); atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - tstart)); }
         }
-        if (prof && pt == 0) { atomicAdd(&g_tc_prof[0], w0); atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - tstart)); }
+        __syncwarp();
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer
         // The whole warp runs the loop (warp-uniform control and address math stay on the uniform datapath); one
@@ -311,7 +324,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     mbar_wait_t(bTEmpty(blk(t)), ((t / kBlocks) & 1u) ^ 1u, w1, prof);
                 }
                 if (!(p.dbg & 128)) mbar_wait_t(bFull(st), (e / kStages) & 1u, w2, prof);
-                if (!(p.dbg & 32)) k1::fence_proxy_async();   // the row was written through the generic proxy (cp.async); the MMA reads it through the async proxy
                 tc_fence_after();
                 if (leader && !(p.dbg & 4)) {
                     const uint32_t a_row = ring + st * kRowBytes;
@@ -366,7 +378,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * NOUT;
                 const int x = it.x0 + quad * 32 + lane, y = it.y0 + j;
-                const size_t pix = ((size_t)it.b * p.H + y) * p.W + x;
                 if (NOUT == 64) {
                     uint32_t v[64];
                     if (!(p.dbg & 8)) {
@@ -381,17 +392,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bTEmpty(b));
-                    // bf16 row of this pixel -> staging tile in the global (chunk-swizzled) layout -> one 4 KB bulk copy per
-                    // warp (async proxy; the LSU never sees the global stores).  A warp only touches its own 32 staging
-                    // rows, so the only ordering needed is its own: its previous copy (two rows ago) must have read them.
-                    if (lane == 0) {                           // the copy that last read this staging tile has finished reading
-                        if (kEpiGroups == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    }
-                    __syncwarp();
-                    const uint32_t sbuf = (kEpiGroups == 1) ? (t & 1u) : grp;      // two staging tiles in all
-                    const uint32_t swarp = s0 + kOffOut + sbuf * (kTileM * 128) + quad * (32 * 128);
-                    const uint32_t srow = swarp + lane * 128;
+                    // bf16 row of this pixel -> staging tile [chunk][pixel][16 B] (the global layout of a row segment; lanes
+                    // write consecutive 16-byte slots: conflict-free) -> 8 bulk copies of 2 KB by one thread.  The LSU never
+                    // sees a global store.  Two staging tiles: the copies of row t - 1 must have READ their tile before
+                    // row t + 1 overwrites it; thread 0 checks that before the one barrier of this row.
+                    const uint32_t stile = s0 + kOffOut + (t & 1u) * (kTileM * 128);
+                    const uint32_t m = warp * 32 + lane;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         uint32_t o[4];
@@ -401,19 +407,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                             if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
                             o[k] = pack_bf16x2(f0, f1);
                         }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + 16 * (q ^ (lane & 7))), "r"(o[0]), "r"(o[1]),
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stile + q * (kTileM * 16) + m * 16), "r"(o[0]), "r"(o[1]),
                                      "r"(o[2]), "r"(o[3])
                                      : "memory");
                     }
                     k1::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int xw = it.x0 + quad * 32;                       // first pixel of this warp
-                        const int npx = p.W - xw < 32 ? p.W - xw : 32;
-                        if (npx > 0 && !(p.dbg & 2))
-                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out + (pix - lane) * 64),
-                                         "r"(swarp), "r"(npx * 128)
-                                         : "memory");
+                    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (threadIdx.x == 0) {
+                        const int npx = p.W - it.x0 < kTileM ? p.W - it.x0 : kTileM;
+                        unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + (((size_t)it.b * p.H + y) * 8 * p.W + it.x0) * 16;
+                        if (!(p.dbg & 2)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) bulk_store(dst + (size_t)q * p.W * 16, stile + q * (kTileM * 16), npx * 16);
+                        }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 } else {
@@ -427,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     if (lane == 0) mbar_arrive(bTEmpty(b));
                     if (x < p.W && !(p.dbg & 2)) {
                         const float n = __uint_as_float(v0);
+                        const size_t pix = ((size_t)it.b * p.H + y) * p.W + x;
                         p.out_f32[pix] = p.resid ? p.resid[(size_t)it.b * p.resid_bstride + (size_t)y * p.W + x] - n : n;
                     }
                 }
@@ -444,15 +452,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
 
 // First layer: conv3x3 CIN -> 64 + bias + ReLU on the CUDA cores (K = 9 CIN is too thin for the tensor cores and the
 // layer is bound by its 128 B/pixel NHWC write).  x: [B][CIN][H][W] fp32 (rounded to bf16 like a bf16 PyTorch module
-// would), w: [64][CIN][3][3] fp32 (bf16-representable values), out: [B][H][W][64] bf16.
-// Thread = (8 output channels, pixel lane): its 72 CIN weights live in registers for the whole kernel and it walks over
-// kHeadPix pixels; the 8 threads of a pixel write its 128 bytes as one contiguous segment.
+// would), w: [64][CIN][3][3] fp32 (bf16-representable values), out: [B][H][8][W][8] bf16 (chunk-planar rows).
+// Thread = (8 output channels = warp, pixel = lane): its 72 CIN weights live in registers for the whole kernel and it walks
+// over kHeadPix pixels; a warp stores 32 consecutive pixels of one chunk plane (512 contiguous bytes).
 constexpr int kHeadPix = 16;     // pixels per thread
 template <int CIN>
 __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                          const float* __restrict__ w, const float* __restrict__ bias, int B,
                                                          int H, int W) {
-    const int ch = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const int ch = threadIdx.x >> 5, pl = threadIdx.x & 31;      // warp = 8-channel chunk, lane = pixel: coalesced loads and stores
     float wr[CIN][8][9], br[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict
         uint4 o;
         o.x = pack_bf16x2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)); o.y = pack_bf16x2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
         o.z = pack_bf16x2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)); o.w = pack_bf16x2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
-        *reinterpret_cast<uint4*>(out + (size_t)pix * 64 + (ch ^ (xx & 7)) * 8) = o;      // chunk-swizzled activation layout
+        *reinterpret_cast<uint4*>(out + ((((size_t)b * H + yy) * 8 + ch) * W + xx) * 8) = o;      // chunk-planar rows
         if (!more) return;
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci)

@@ -106,15 +106,15 @@ class FusedDnCNN:
         return out
 
 
-def swizzle_chunks(x_nhwc: torch.Tensor) -> torch.Tensor:
-    """Dense (B, H, W, 64) <-> the kernels' inter-layer layout: the 16-byte chunk c (8 channels) of pixel x sits at
-    position c ^ (x & 7).  The permutation is an involution, so the same call converts both ways."""
+def to_chunk_planar(x_nhwc: torch.Tensor) -> torch.Tensor:
+    """Dense (B, H, W, 64) -> the kernels' inter-layer layout (B, H, 8, W, 8): chunk-planar rows."""
     B, H, W, C = x_nhwc.shape
-    v = x_nhwc.reshape(B, H, W, 8, 8)
-    xs = torch.arange(W, device=x_nhwc.device) & 7
-    pos = torch.arange(8, device=x_nhwc.device)[None, :] ^ xs[:, None]          # [W][8]: source chunk of each position
-    idx = pos[None, None, :, :, None].expand(B, H, W, 8, 8)
-    return torch.gather(v, 3, idx).reshape(B, H, W, C).contiguous()
+    return x_nhwc.reshape(B, H, W, 8, 8).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def from_chunk_planar(x_cp: torch.Tensor) -> torch.Tensor:
+    B, H, _, W, _ = x_cp.shape
+    return x_cp.permute(0, 1, 3, 2, 4).reshape(B, H, W, 64).contiguous()
 
 
 def conv64(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.Tensor:
@@ -122,11 +122,11 @@ def conv64(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu:
     lib = _abi.load()
     if x_nhwc.dtype != torch.bfloat16 or x_nhwc.ndim != 4 or x_nhwc.shape[-1] != 64 or not x_nhwc.is_cuda:
         raise ValueError('expected a (B, H, W, 64) bf16 CUDA tensor')
-    x = swizzle_chunks(x_nhwc)
-    B, H, W, _ = (int(v) for v in x.shape)
+    x = to_chunk_planar(x_nhwc)
+    B, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[3])
     wp = pack_conv64(weight.to(x.device))
     bs = bias.to(x.device, torch.float32).contiguous()
     out = torch.empty_like(x)
     _abi.check(lib.pnpadmm_conv64_bf16(x.data_ptr(), out.data_ptr(), wp.data_ptr(), bs.data_ptr(), B, H, W, int(relu),
                                        torch.cuda.current_stream().cuda_stream))
-    return swizzle_chunks(out)
+    return from_chunk_planar(out)
