@@ -451,16 +451,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
 }
 
 // First layer: conv3x3 CIN -> 64 + bias + ReLU on the CUDA cores (K = 9 CIN is too thin for the tensor cores and the
-// layer is bound by its 128 B/pixel NHWC write).  x: [B][CIN][H][W] fp32 (rounded to bf16 like a bf16 PyTorch module
-// would), w: [64][CIN][3][3] fp32 (bf16-representable values), out: [B][H][8][W][8] bf16 (chunk-planar rows).
-// Thread = (8 output channels = warp, pixel = lane): its 72 CIN weights live in registers for the whole kernel and it walks
-// over kHeadPix pixels; a warp stores 32 consecutive pixels of one chunk plane (512 contiguous bytes).
-constexpr int kHeadPix = 16;     // pixels per thread
+// layer is bound by its 128 B/pixel write).  x: [B][CIN][H][W] fp32 (rounded to bf16 like a bf16 PyTorch module would),
+// w: [64][CIN][3][3] fp32 (bf16-representable values), out: [B][H][8][W][8] bf16 (chunk-planar rows).
+// Block = a patch of 32 columns x kHeadRows rows; warp = 8-channel chunk, lane = column.  A thread keeps its 72 CIN
+// weights in registers and slides a 3x3 window DOWN its column: three new (coalesced) loads per pixel instead of nine;
+// a warp stores 32 consecutive pixels of one chunk plane (512 contiguous bytes) per row.
+constexpr int kHeadRows = 16;
 template <int CIN>
 __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                          const float* __restrict__ w, const float* __restrict__ bias, int B,
                                                          int H, int W) {
-    const int ch = threadIdx.x >> 5, pl = threadIdx.x & 31;      // warp = 8-channel chunk, lane = pixel: coalesced loads and stores
+    const int ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float wr[CIN][8][9], br[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -470,59 +471,54 @@ __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict
 #pragma unroll
             for (int t = 0; t < 9; ++t) wr[ci][c][t] = __ldg(w + ((ch * 8 + c) * CIN + ci) * 9 + t);
     }
-    const uint32_t npix = (uint32_t)B * H * W;          // < 2^31 (checked by the host)
-    uint32_t pix = blockIdx.x * (32u * kHeadPix) + pl;
-    if (pix >= npix) return;
-    int xx = (int)(pix % (uint32_t)W);
-    int yy = (int)((pix / (uint32_t)W) % (uint32_t)H);
-    uint32_t b = pix / ((uint32_t)W * H);
-    // the 3x3 neighbourhood of pixel (b, yy, xx), all CIN channels, rounded to bf16
-    auto load_nb = [&](float (&v)[CIN][9], int xq, int yq, uint32_t bq) {
+    const int xt = (W + 31) / 32, yt = (H + kHeadRows - 1) / kHeadRows;
+    const int bx = blockIdx.x % xt, by = (blockIdx.x / xt) % yt, b = blockIdx.x / (xt * yt);
+    const int xx = bx * 32 + lane, y0 = by * kHeadRows;
+    // the block's input patch (kHeadRows + 2 rows x 34 columns, zero outside the image, rounded to bf16) goes to shared
+    // memory first: one round trip to L2 per block instead of one per row of every warp
+    __shared__ float patch[CIN][kHeadRows + 2][34];
+    for (int i = threadIdx.x; i < CIN * (kHeadRows + 2) * 34; i += 256) {
+        const int c = i % 34, r = (i / 34) % (kHeadRows + 2), ci = i / (34 * (kHeadRows + 2));
+        const int y = y0 - 1 + r, xq = bx * 32 - 1 + c;
+        float v = 0.f;
+        if (y >= 0 && y < H && xq >= 0 && xq < W) v = __ldg(x + (((size_t)b * CIN + ci) * H + y) * W + xq);
+        patch[ci][r][c] = __bfloat162float(__float2bfloat16(v));
+    }
+    __syncthreads();
+    if (xx >= W) return;
+    auto load_row = [&](float (&v)[CIN][3], int r) {
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-            const float* img = x + ((size_t)bq * CIN + ci) * (size_t)H * W;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int y2 = yq + ky - 1, x2 = xq + kx - 1;
-                    float t = 0.f;
-                    if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) t = __ldg(img + (size_t)y2 * W + x2);
-                    v[ci][ky * 3 + kx] = t;
-                }
+            v[ci][0] = patch[ci][r][lane]; v[ci][1] = patch[ci][r][lane + 1]; v[ci][2] = patch[ci][r][lane + 2];
         }
     };
-    float cur[CIN][9], nxt[CIN][9];
-    load_nb(cur, xx, yy, b);
-    for (int it = 0; it < kHeadPix; ++it) {
-        // prefetch the next pixel's neighbourhood before the arithmetic of this one (the loop is latency-bound otherwise)
-        const uint32_t pix_n = pix + 32;
-        int xn = xx + 32, yn = yy;
-        uint32_t bn = b;
-        while (xn >= W) { xn -= W; if (++yn == H) { yn = 0; ++bn; } }
-        const bool more = (it + 1 < kHeadPix) && (pix_n < npix);
-        if (more) load_nb(nxt, xn, yn, bn);
+    float r0[CIN][3], r1[CIN][3], r2[CIN][3];
+    load_row(r0, 0);
+    load_row(r1, 1);
+    const int y1 = y0 + kHeadRows < H ? y0 + kHeadRows : H;
+    for (int y = y0; y < y1; ++y) {
+        load_row(r2, y - y0 + 2);
         float f[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) f[c] = br[c];
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float v = __bfloat162float(__float2bfloat16(cur[ci][t]));
+            for (int k = 0; k < 3; ++k)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) f[c] = fmaf(wr[ci][c][t], v, f[c]);
-            }
+                for (int c = 0; c < 8; ++c) {
+                    f[c] = fmaf(wr[ci][c][k], r0[ci][k], f[c]);
+                    f[c] = fmaf(wr[ci][c][3 + k], r1[ci][k], f[c]);
+                    f[c] = fmaf(wr[ci][c][6 + k], r2[ci][k], f[c]);
+                }
         uint4 o;
         o.x = pack_bf16x2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)); o.y = pack_bf16x2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
         o.z = pack_bf16x2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)); o.w = pack_bf16x2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
-        *reinterpret_cast<uint4*>(out + ((((size_t)b * H + yy) * 8 + ch) * W + xx) * 8) = o;      // chunk-planar rows
-        if (!more) return;
+        *reinterpret_cast<uint4*>(out + ((((size_t)b * H + y) * 8 + ch) * W + xx) * 8) = o;      // chunk-planar rows
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) cur[ci][t] = nxt[ci][t];
-        pix = pix_n; xx = xn; yy = yn; b = bn;
+            for (int k = 0; k < 3; ++k) { r0[ci][k] = r1[ci][k]; r1[ci][k] = r2[ci][k]; }
     }
 }
 

@@ -886,8 +886,7 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
     tc::ConvParams p{};
     rc = conv_geometry(p, B, H, W, "dncnn_forward"); if (rc) return rc;
     __nv_bfloat16* act[2] = {static_cast<__nv_bfloat16*>(act0), static_cast<__nv_bfloat16*>(act1)};
-    const size_t per_block = 32 * (size_t)tc::kHeadPix;
-    const unsigned hgrid = (unsigned)(((size_t)B * H * W + per_block - 1) / per_block);
+    const unsigned hgrid = (unsigned)B * ((W + 31) / 32) * ((H + tc::kHeadRows - 1) / tc::kHeadRows);
     if (cin == 1) tc::dncnn_head_kernel<1><<<hgrid, 256, 0, st>>>(x, act[0], w_head, b_head, B, H, W);
     else tc::dncnn_head_kernel<2><<<hgrid, 256, 0, st>>>(x, act[0], w_head, b_head, B, H, W);
     LAUNCH_CHECK("dncnn_head_kernel");
