@@ -319,6 +319,34 @@ def run_ours(args):
         k2 = dict(N=N2, B=B2, iters=IT2, ms=float(np.mean(t2)))
         del s2, y2, z20, x2, z2, w2
         torch.cuda.empty_cache()
+    # K5 (DnCNN on tcgen05, BASELINE config 3's denoiser) against the bf16 tensor peak: one 64->64 layer and one
+    # DnCNN-17 forward at B = 256, 256x256 (activations 2 x 2.1 GB >> L2)
+    k5 = None
+    if rank == 0:
+        from pnp_admm_cnc_mri_b200 import denoisers as pden, dncnn_fused as pdf
+        B5 = 256
+        net = pden.build_model('dncnn_25', seed=0)
+        fused = pdf.FusedDnCNN(net, residual=True, device=dev)
+        x5 = torch.rand(B5, 1, N, N, device=dev)
+        a5 = torch.randn(B5, N, 8, N, 8, device=dev).to(torch.bfloat16)
+        o5 = torch.empty_like(a5)
+        w5 = pdf.pack_conv64(torch.randn(64, 64, 3, 3, device=dev) / 24)
+        b5 = torch.zeros(64, device=dev)
+        st5 = torch.cuda.current_stream().cuda_stream
+
+        def t_of(fn, reps=5, warm=2):
+            ts = []
+            for r in range(warm + reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                if r >= warm:
+                    ts.append(e0.elapsed_time(e1))
+            return float(np.mean(ts))
+        k5 = dict(B=B5, layer_ms=t_of(lambda: _abi.check(lib.pnpadmm_conv64_bf16(a5.data_ptr(), o5.data_ptr(), w5.data_ptr(),
+                                                                               b5.data_ptr(), B5, N, N, 1, st5))),
+                  forward_ms=t_of(lambda: fused(x5)))
+        del fused, x5, a5, o5
+        torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None
 
     fl = ctypes.c_double()
@@ -397,6 +425,22 @@ def run_ours(args):
             'iterations_per_s': its2,
             'peak_source': 'MEASURED_PEAKS.json hbm_gbs (copy bandwidth)' if 'hbm_gbs' in peaks else 'fallback 6450 GB/s',
         }
+        layer_flop = 2.0 * 64 * 64 * 9 * N * N * k5['B']
+        fwd_flop = 2.0 * 555137 * N * N * k5['B']
+        tpeak = peaks.get('bf16_tflops', 1670.0)
+        line['roofline_tensor'] = {
+            'bound': 'tensor', 'kernel': 'conv64_tc_kernel<64> (K5: one DnCNN conv3x3 64->64 + bias + ReLU layer, tcgen05 implicit GEMM)',
+            'achieved': layer_flop / (k5['layer_ms'] * 1e-3) / 1e12, 'peak': tpeak, 'unit': 'TFLOP/s',
+            'frac': layer_flop / (k5['layer_ms'] * 1e-3) / 1e12 / tpeak, 'traffic': 4293e6,
+            'traffic_source': 'profiles/r1_k5_conv64_tc_ncu_summary.txt: dram read 2198 MB + write 2095 MB per launch at B=256 '
+                              '(algorithmic: 2147 MB in x 1.05 halo + 2147 MB out)',
+            'flop_model': '2 x 64 x 64 x 9 = 73728 FLOP per pixel and layer', 'launch_ms': k5['layer_ms'],
+            'hbm_gbs_moved': 2 * 128.0 * N * N * k5['B'] / (k5['layer_ms'] * 1e-3) / 1e9,
+            'peak_source': 'MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)' if 'bf16_tflops' in peaks else 'fallback 1670 TFLOP/s',
+            'workload': f"B={k5['B']}, 256x256, bf16 operands, fp32 accumulation",
+            'dncnn17_forward': {'ms': k5['forward_ms'], 'achieved': fwd_flop / (k5['forward_ms'] * 1e-3) / 1e12,
+                                'what': 'head (CUDA cores) + 15 x conv64_tc_kernel<64> + tail conv64_tc_kernel<16>; BASELINE config 3 '
+                                        'runs two of these per PnP-ADMM-CNC iteration (tools/pnp_bench.py c3)'}}
         if cpu_v is not None:
             line['cpu_baseline'] = {'value': cpu_v, 'unit': 'iterations/s', 'cores': 1, 'kind': 'port',
                                     'sample': '8 images x 50 iterations, 1 thread, NumPy fp64 oracle restatement '
