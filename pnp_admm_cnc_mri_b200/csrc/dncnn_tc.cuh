@@ -15,14 +15,14 @@
 // buffer: the im2col matrix is never materialised, every input row is loaded ONCE per strip, and a k-chunk plane of a
 // row buffer is 2080 CONTIGUOUS bytes of global memory: one 1-D bulk copy (cp.async.bulk, TMA engine) per plane, no
 // tensor map and no LSU instruction on the load path; zero padding comes from a zero buffer.  The row buffers form a
-// 6-deep ring; the 72 KB of weights of the layer
+// 5-deep ring; the 72 KB of weights of the layer
 //     B            : [kx 0..2][k-chunk 0..7][ky 0..2][c_out 0..N)[8 c_in]   (the three ky taps stacked along N)
 // stay resident for the persistent CTA's whole life.  Accumulators live in an 8-block ring in TMEM (see the kernel)
 // so the epilogue warps (tcgen05.ld -> ReLU -> bf16 -> staging tile -> 8 bulk stores of 2 KB) overlap the MMAs.
 //
-//   warps 0-3  : epilogue (TMEM lane quadrant = warp & 3)
-//   warp  4    : TMEM alloc, one elected lane issues the MMAs
-//   warp  5    : producer (one lane issues the bulk copies)
+//   warps 0-7  : two epilogue groups, alternate output rows (TMEM lane quadrant = warp & 3)
+//   warp  8    : TMEM alloc, one elected lane issues the MMAs
+//   warp  9    : producer (one lane issues the bulk copies)
 //   mbarriers  : full[6] / empty[6] (producers <-> MMA), tfull[8] / tempty[8] (MMA <-> epilogue, one pair per block)
 //
 // The first layer (c_in = 1 or 2) and nothing else runs on the CUDA cores (it is a 0.3 ms NHWC write); the last
@@ -42,10 +42,10 @@ constexpr int kSlots = kTileM + 2;             // staged input pixels per row
 constexpr int kPPad = 131;                     // slot pitch of a k-chunk plane, odd: the 8 chunks of a pixel hit 8 bank groups
 constexpr int kChunkBytes = kPPad * 16;        // = LBO of the A descriptor
 constexpr int kRowBytes = 8 * kChunkBytes;     // 16768
-constexpr int kStages = 6;
-constexpr int kThreads = 192;                  // warps 0-3 epilogue, 4 MMA, 5 producer (one lane issues the bulk copies)
-constexpr int kEpiGroups = 1;                  // epilogue groups of four warps; group g takes the output rows t = g (mod kEpiGroups)
+constexpr int kStages = 5;
+constexpr int kEpiGroups = 2;                  // epilogue groups of four warps; group g takes the output rows t = g (mod kEpiGroups)
 constexpr int kMmaWarp = 4 * kEpiGroups;       // warps [0, 4 g): epilogue, then the MMA warp, then the producer warp
+constexpr int kThreads = 32 * (kMmaWarp + 2);
 constexpr int kOffW = 0;
 constexpr int kWBytesMax = 9 * 8 * 64 * 16;    // 73728
 constexpr int kOffRing = kWBytesMax;
@@ -54,8 +54,8 @@ constexpr int kBlocks = 8;                     // accumulator blocks (output row
 constexpr int kNumBars = 2 * kStages + 2 * kBlocks;
 constexpr int kOffTmemPtr = kOffBar + 8 * kNumBars;
 constexpr int kOffBias = kOffTmemPtr + 16;
-constexpr int kOffOut = kOffBias + 64 * 4;     // two staging tiles [8 chunks][128 pixels][16 B]
-constexpr int kSmemBytes = kOffOut + 2 * kTileM * 128;
+constexpr int kOffOut = kOffBias + 64 * 4;     // staging tiles [8 chunks][128 pixels][16 B], two per epilogue group
+constexpr int kSmemBytes = kOffOut + 2 * kEpiGroups * kTileM * 128;
 constexpr int kRowTxBytes = 8 * kSlots * 16;   // bytes a staged input row receives (data + zero padding)
 
 // source of the zero padding (rows above / below the image, the pixel left / right of it)
@@ -314,56 +314,75 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         const uint64_t desc_hi_a = ((uint64_t)(kChunkBytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
         const uint64_t b_desc0 = make_desc(s0 + kOffW, 3 * NOUT * 16, 128);
         const bool leader = elect_one();
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-            const Item it = decode_item(p, item);
-            const int R = it.rows;
-            for (int i = 0; i < R + 2; ++i, ++e) {
-                const uint32_t st = e % kStages;
-                if (i < R && !(p.dbg & 64)) {                  // block of the output row that starts with this input row
-                    const uint32_t t = t_base + i;
-                    mbar_wait_t(bTEmpty(blk(t)), ((t / kBlocks) & 1u) ^ 1u, w1, prof);
-                }
-                if (!(p.dbg & 128)) mbar_wait_t(bFull(st), (e / kStages) & 1u, w2, prof);
-                tc_fence_after();
-                if (leader && !(p.dbg & 4)) {
-                    const uint32_t a_row = ring + st * kRowBytes;
-                    const uint64_t a_desc0 = desc_hi_a | (uint64_t)((a_row & 0x3FFFFu) >> 4);
-                    const int dy_hi = i < 2 ? i : 2;
-                    int dy = i - (R - 1) > 0 ? i - (R - 1) : 0;
-                    while (dy <= dy_hi) {
-                        const uint32_t b = blk(t_base + i - dy);
-                        int n = dy_hi - dy + 1;
-                        if (n > (int)(kBlocks - b)) n = kBlocks - b;
-                        const uint32_t idesc = make_idesc(n * NOUT);
-                        const uint32_t d_tmem = tmem_base + b * NOUT;
-                        const uint64_t b_dy = b_desc0 + (uint64_t)((dy * NOUT * 16) >> 4);
+        // The tensor pipe queues only an instruction or two, so whatever the issuing thread does between the last MMA
+        // of a row and the first of the next is a bubble.  The waits for row e + 1 are therefore taken in the MIDDLE of
+        // row e's MMAs (pre), and only the two commits (post) sit between rows.
+        auto pre = [&](uint32_t ee, int i, int R, uint32_t tb) {           // barriers of input row (ee, i)
+            if (i < R && !(p.dbg & 64)) {                              // block of the output row that starts with this input row
+                const uint32_t t = tb + i;
+                mbar_wait_t(bTEmpty(blk(t)), ((t / kBlocks) & 1u) ^ 1u, w1, prof);
+            }
+            if (!(p.dbg & 128)) mbar_wait_t(bFull(ee % kStages), (ee / kStages) & 1u, w2, prof);
+            tc_fence_after();
+        };
+        auto issue = [&](uint32_t ee, int i, int R, uint32_t tb, int dx0, int dx1) {   // MMAs of taps kx in [dx0, dx1)
+            if (!leader || (p.dbg & 4)) return;
+            const uint32_t a_row = ring + (ee % kStages) * kRowBytes;
+            const uint64_t a_desc0 = desc_hi_a | (uint64_t)((a_row & 0x3FFFFu) >> 4);
+            const int dy_hi = i < 2 ? i : 2;
+            int dy = i - (R - 1) > 0 ? i - (R - 1) : 0;
+            while (dy <= dy_hi) {
+                const uint32_t b = blk(tb + i - dy);
+                int n = dy_hi - dy + 1;
+                if (n > (int)(kBlocks - b)) n = kBlocks - b;
+                const uint32_t idesc = make_idesc(n * NOUT);
+                const uint32_t d_tmem = tmem_base + b * NOUT;
+                const uint64_t b_dy = b_desc0 + (uint64_t)((dy * NOUT * 16) >> 4);
+                for (int dx = dx0; dx < dx1; ++dx) {
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                // start-address field += byte offset / 16 (never carries out of its 14 bits: smem < 256 KB)
-                                const uint64_t ad = a_desc0 + (uint64_t)((dx * 16 + ks * 2 * kChunkBytes) >> 4);
-                                const uint64_t bd = b_dy + (uint64_t)(((dx * 8 + ks * 2) * (3 * NOUT * 16)) >> 4);
-                                tc_mma_bf16(d_tmem, ad, bd, idesc, 1);
-                            }
-                        }
-                        dy += n;
+                    for (int ks = 0; ks < 4; ++ks) {
+                        // start-address field += byte offset / 16 (never carries out of its 14 bits: smem < 256 KB)
+                        const uint64_t ad = a_desc0 + (uint64_t)((dx * 16 + ks * 2 * kChunkBytes) >> 4);
+                        const uint64_t bd = b_dy + (uint64_t)(((dx * 8 + ks * 2) * (3 * NOUT * 16)) >> 4);
+                        tc_mma_bf16(d_tmem, ad, bd, idesc, 1);
                     }
                 }
+                dy += n;
+            }
+        };
+        int item = blockIdx.x;
+        if (item < p.items) {
+            int R = decode_item(p, item).rows, i = 0;
+            pre(e, i, R, t_base);
+            for (;;) {
+                // coordinates of the next input row
+                int n_item = item, n_i = i + 1, n_R = R;
+                uint32_t n_tb = t_base;
+                bool has_next = true;
+                if (n_i == R + 2) {
+                    n_item = item + gridDim.x; n_i = 0; n_tb = t_base + R;
+                    has_next = n_item < p.items;
+                    if (has_next) n_R = decode_item(p, n_item).rows;
+                }
+                issue(e, i, R, t_base, 0, 2);
+                if (has_next) pre(e + 1, n_i, n_R, n_tb);
+                issue(e, i, R, t_base, 2, 3);
                 __syncwarp();
                 if (leader) {
-                    if (!(p.dbg & 128)) tc_commit(bEmpty(st));                // each input row is consumed in one go
+                    if (!(p.dbg & 128)) tc_commit(bEmpty(e % kStages));           // each input row is consumed in one go
                     if (i >= 2 && !(p.dbg & 64)) tc_commit(bTFull(blk(t_base + i - 2)));   // output row i - 2 has its three input rows
                 }
                 __syncwarp();
+                if (!has_next) break;
+                item = n_item; i = n_i; R = n_R; t_base = n_tb; ++e;
             }
-            t_base += R;
         }
         if (prof && lane == 0) { atomicAdd(&g_tc_prof[1], w1); atomicAdd(&g_tc_prof[2], w2); atomicAdd(&g_tc_prof[4], (unsigned long long)(clock64() - tstart)); }
     } else {
         // ------------------------------------------------------------------ epilogue warps
-        // Groups of four warps (TMEM lane quadrant = warp & 3); with kEpiGroups = 2 they take alternate output rows
-        // (measured: no gain, the epilogue is not the bottleneck, and 13 warps cap the kernel at 128 registers).
+        // Groups of four warps (TMEM lane quadrant = warp & 3) take alternate output rows: a row's chain (wait ->
+        // tcgen05.ld -> re-init -> pack -> stage -> barrier -> bulk stores) is ~1.7 k cycles of mostly latency, and with
+        // the MMA warp's waits hidden it is what bounds the pipeline; two rows in flight halve it.
         uint32_t t = 0;
         unsigned long long w3 = 0;
         const long long tstart = clock64();
@@ -394,10 +413,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     if (lane == 0) mbar_arrive(bTEmpty(b));
                     // bf16 row of this pixel -> staging tile [chunk][pixel][16 B] (the global layout of a row segment; lanes
                     // write consecutive 16-byte slots: conflict-free) -> 8 bulk copies of 2 KB by one thread.  The LSU never
-                    // sees a global store.  Two staging tiles: the copies of row t - 1 must have READ their tile before
+                    // sees a global store.  Two staging tiles per group: the copies of the group's previous row must have READ their tile before
                     // row t + 1 overwrites it; thread 0 checks that before the one barrier of this row.
-                    const uint32_t stile = s0 + kOffOut + (t & 1u) * (kTileM * 128);
-                    const uint32_t m = warp * 32 + lane;
+                    const uint32_t stile = s0 + kOffOut + (2 * grp + ((t / kEpiGroups) & 1u)) * (kTileM * 128);
+                    const uint32_t m = quad * 32 + lane;
+                    const bool gleader = (threadIdx.x & 127) == 0;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         uint32_t o[4];
@@ -412,9 +432,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                                      : "memory");
                     }
                     k1::fence_proxy_async();
-                    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (threadIdx.x == 0) {
+                    if (gleader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    if (gleader) {
                         const int npx = p.W - it.x0 < kTileM ? p.W - it.x0 : kTileM;
                         unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + (((size_t)it.b * p.H + y) * 8 * p.W + it.x0) * 16;
                         if (!(p.dbg & 2)) {
@@ -441,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
             }
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all staged rows have been written out
-        if (prof && warp == 0 && lane == 0) { atomicAdd(&g_tc_prof[3], w3); atomicAdd(&g_tc_prof[6], (unsigned long long)(clock64() - tstart)); }
+        if (prof && (threadIdx.x & 127) == 0) { atomicAdd(&g_tc_prof[3], w3); atomicAdd(&g_tc_prof[6], (unsigned long long)(clock64() - tstart)); }
     }
     tc_fence_before();
     __syncthreads();
