@@ -22,7 +22,7 @@
 //
 //   warps 0-7  : two epilogue groups, alternate output rows (TMEM lane quadrant = warp & 3)
 //   warp  8    : TMEM alloc, one elected lane issues the MMAs
-//   warp  9    : producer (one lane issues the bulk copies)
+//   warps 9-10 : producers (one lane each issues the bulk copies of four k-chunk planes)
 //   mbarriers  : full[6] / empty[6] (producers <-> MMA), tfull[8] / tempty[8] (MMA <-> epilogue, one pair per block)
 //
 // The first layer (c_in = 1 or 2) and nothing else runs on the CUDA cores (it is a 0.3 ms NHWC write); the last
@@ -45,7 +45,8 @@ constexpr int kRowBytes = 8 * kChunkBytes;     // 16768
 constexpr int kStages = 5;
 constexpr int kEpiGroups = 2;                  // epilogue groups of four warps; group g takes the output rows t = g (mod kEpiGroups)
 constexpr int kMmaWarp = 4 * kEpiGroups;       // warps [0, 4 g): epilogue, then the MMA warp, then the producer warp
-constexpr int kThreads = 32 * (kMmaWarp + 2);
+constexpr int kProdWarps = 2;                  // producer warps: issuing a bulk copy costs its thread ~140 cycles, so the 8 copies of a row are split
+constexpr int kThreads = 32 * (kMmaWarp + 1 + kProdWarps);
 constexpr int kOffW = 0;
 constexpr int kWBytesMax = 9 * 8 * 64 * 16;    // 73728
 constexpr int kOffRing = kWBytesMax;
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         // whole zero planes for the rows above / below it: the convolution's padding).
         unsigned long long w0 = 0;
         const long long tstart = clock64();
+        const int pw = warp - (kMmaWarp + 1), c0 = pw * (8 / kProdWarps);      // this warp's k-chunk planes
         if (lane == 0) {
             const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in);
             const size_t plane = (size_t)p.W * 16, rowb = 8 * plane;
@@ -283,16 +285,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     const uint32_t st = e % kStages;
                     mbar_wait_t(bEmpty(st), ((e / kStages) & 1u) ^ 1u, w0, prof);
                     const uint32_t bar = bFull(st), dst0 = ring + st * kRowBytes;
-                    if (p.dbg & 1) { mbar_arrive(bar); continue; }
-                    k1::mbar_arm_tx(bar, kRowTxBytes);
+                    if (p.dbg & 1) { if (pw == 0) mbar_arrive(bar); continue; }
+                    if (pw == 0) k1::mbar_arm_tx(bar, kRowTxBytes);       // the other producer warps' bytes may land first: fine
                     const int y = it.y0 - 1 + r;
                     if (y < 0 || y >= p.H) {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) bulk_load(dst0 + c * kChunkBytes, g_zero, kSlots * 16, bar);
+                        for (int c = c0; c < c0 + 8 / kProdWarps; ++c) bulk_load(dst0 + c * kChunkBytes, g_zero, kSlots * 16, bar);
                     } else {
                         const unsigned char* src = in_b + ((size_t)it.b * p.H + y) * rowb + (size_t)lo * 16;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
+                        for (int c = c0; c < c0 + 8 / kProdWarps; ++c) {
                             const uint32_t d = dst0 + c * kChunkBytes;
                             if (nleft) bulk_load(d, g_zero, nleft * 16, bar);
                             bulk_load(d + nleft * 16, src + c * plane, nvalid * 16, bar);
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     }
                 }
             }
-            if (prof) { atomicAdd(&g_tc_prof[0], w0); atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - tstart)); }
+            if (prof && pw == 0) { atomicAdd(&g_tc_prof[0], w0); atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - tstart)); }
         }
         __syncwarp();
     } else if (warp == kMmaWarp) {
@@ -414,10 +416,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     // bf16 row of this pixel -> staging tile [chunk][pixel][16 B] (the global layout of a row segment; lanes
                     // write consecutive 16-byte slots: conflict-free) -> 8 bulk copies of 2 KB by one thread.  The LSU never
                     // sees a global store.  Two staging tiles per group: the copies of the group's previous row must have READ their tile before
-                    // row t + 1 overwrites it; thread 0 checks that before the one barrier of this row.
+                    // the group's next row overwrites it; the issuing lanes check that before the one barrier of this row.
                     const uint32_t stile = s0 + kOffOut + (2 * grp + ((t / kEpiGroups) & 1u)) * (kTileM * 128);
                     const uint32_t m = quad * 32 + lane;
-                    const bool gleader = (threadIdx.x & 127) == 0;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         uint32_t o[4];
@@ -432,14 +433,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                                      : "memory");
                     }
                     k1::fence_proxy_async();
-                    if (gleader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                    if (gleader) {
+                    if (lane == 0) {                           // each warp's lane 0 sends two of the eight chunk planes
                         const int npx = p.W - it.x0 < kTileM ? p.W - it.x0 : kTileM;
                         unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + (((size_t)it.b * p.H + y) * 8 * p.W + it.x0) * 16;
                         if (!(p.dbg & 2)) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) bulk_store(dst + (size_t)q * p.W * 16, stile + q * (kTileM * 16), npx * 16);
+                            for (int q = 2 * quad; q < 2 * quad + 2; ++q) bulk_store(dst + (size_t)q * p.W * 16, stile + q * (kTileM * 16), npx * 16);
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }

@@ -892,6 +892,7 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
     LAUNCH_CHECK("dncnn_head_kernel");
     const int grid = p.items < d->sm_count ? p.items : d->sm_count;
     p.relu = 1;
+    if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);     // timing experiments only
     for (int l = 0; l < n_mid; ++l) {
         p.in = act[l & 1]; p.out = act[(l + 1) & 1];
         p.w = static_cast<const unsigned char*>(w_mid) + (size_t)l * tc::kWBytesMax;
