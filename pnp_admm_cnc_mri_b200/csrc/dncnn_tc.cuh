@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         const uint64_t b_desc0 = make_desc(s0 + kOffW, 3 * NOUT * 16, 128);
         const bool leader = elect_one();
         // The tensor pipe queues only an instruction or two, so whatever the issuing thread does between the last MMA
-        // of a row and the first of the next is a bubble.  The waits for row e + 1 are therefore taken in the MIDDLE of
-        // row e's MMAs (pre), and only the two commits (post) sit between rows.
+        // of a row and the first of the next is a bubble.  The waits for row e + 1 (pre) and the commits of row e - 1
+        // (post) are therefore placed INSIDE row e's MMA stream; nothing but loop control sits between rows.
         auto pre = [&](uint32_t ee, int i, int R, uint32_t tb) {           // barriers of input row (ee, i)
             if (i < R && !(p.dbg & 64)) {                              // block of the output row that starts with this input row
                 const uint32_t t = tb + i;
@@ -352,9 +352,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                 dy += n;
             }
         };
+        // completion signals of input row (ee, i): its ring stage is free, and output row i - 2 has all three input rows
+        auto post = [&](uint32_t ee, int i, uint32_t tb) {
+            __syncwarp();
+            if (leader) {
+                if (!(p.dbg & 128)) tc_commit(bEmpty(ee % kStages));
+                if (i >= 2 && !(p.dbg & 64)) tc_commit(bTFull(blk(tb + i - 2)));
+            }
+            __syncwarp();
+        };
         int item = blockIdx.x;
         if (item < p.items) {
             int R = decode_item(p, item).rows, i = 0;
+            bool have_prev = false;
+            uint32_t p_e = 0, p_tb = 0;
+            int p_i = 0;
             pre(e, i, R, t_base);
             for (;;) {
                 // coordinates of the next input row
@@ -366,18 +378,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     has_next = n_item < p.items;
                     if (has_next) n_R = decode_item(p, n_item).rows;
                 }
-                issue(e, i, R, t_base, 0, 2);
+                // row e: taps kx = 0 | the PREVIOUS row's commits (they then also cover these four MMAs: a few hundred
+                // cycles later, but off the critical gap between rows) | kx = 1 | the NEXT row's waits | kx = 2
+                issue(e, i, R, t_base, 0, 1);
+                if (have_prev) post(p_e, p_i, p_tb);
+                issue(e, i, R, t_base, 1, 2);
                 if (has_next) pre(e + 1, n_i, n_R, n_tb);
                 issue(e, i, R, t_base, 2, 3);
-                __syncwarp();
-                if (leader) {
-                    if (!(p.dbg & 128)) tc_commit(bEmpty(e % kStages));           // each input row is consumed in one go
-                    if (i >= 2 && !(p.dbg & 64)) tc_commit(bTFull(blk(t_base + i - 2)));   // output row i - 2 has its three input rows
-                }
-                __syncwarp();
+                have_prev = true; p_e = e; p_i = i; p_tb = t_base;
                 if (!has_next) break;
                 item = n_item; i = n_i; R = n_R; t_base = n_tb; ++e;
             }
+            post(p_e, p_i, p_tb);
         }
         if (prof && lane == 0) { atomicAdd(&g_tc_prof[1], w1); atomicAdd(&g_tc_prof[2], w2); atomicAdd(&g_tc_prof[4], (unsigned long long)(clock64() - tstart)); }
     } else {
