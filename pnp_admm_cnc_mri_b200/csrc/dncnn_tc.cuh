@@ -72,7 +72,10 @@ struct ConvParams {
     const float* bias;          // [64] (tail: [1])
     int B, H, W, strip, xtiles, ystrips, items;
     int relu;
-    int dbg;                    // timing experiments only (results invalid): 1 = no input copies, 2 = no output stores, 4 = no MMAs
+    // PNPADMM_TC_DEBUG, timing experiments only (every bit but 256 makes the results invalid): 1 = no input copies, 2 = no
+    // output stores, 4 = no MMAs, 8 / 16 = no tcgen05.ld / no accumulator re-init in the epilogue, 64 = no MMA <-> epilogue
+    // handshake (epilogue off), 128 = no producer <-> MMA handshake (producers off), 256 = wait-time attribution (g_tc_prof)
+    int dbg;
 };
 
 PNP_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,12 +138,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1
           "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]),      \
           "=r"(v[o + 30]), "=r"(v[o + 31])                                                                           \
         : "r"(taddr))
-
-PNP_D void st_global_v8(void* p, const uint32_t (&o)[8]) {      // one 256-bit store (SASS STG.256)
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
-                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
-                 : "memory");
-}
 
 // one lane of the (converged) warp
 PNP_D bool elect_one() {
