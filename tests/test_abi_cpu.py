@@ -68,6 +68,16 @@ def test_argument_validation_without_gpu(lib):
     assert lib.pnpadmm_metrics_f32(p, p, 1, 8, 0, p, p, 1024, None) == -2
     assert lib.pnpadmm_metrics_f64(p, p, 64, 256, 0, p, p, 16, None) == -3
     assert lib.pnpadmm_metrics_scratch_bytes(64) == 64 * 32 and lib.pnpadmm_metrics_scratch_bytes(0) == 0
+    # tensor-core denoiser: NULLs, misaligned pointers, channel counts, degenerate sizes
+    assert lib.pnpadmm_conv64_bf16(None, None, None, None, 1, 8, 8, 1, None) == -1
+    assert lib.pnpadmm_conv64_bf16(q + 2, q, q, q, 1, 8, 8, 1, None) == -1
+    assert b'aligned' in lib.pnpadmm_last_error_string()
+    assert lib.pnpadmm_dncnn_forward_bf16(None, None, 1, 1, 8, 8, 15, None, None, None, None, None, None, 1, None, None, None) == -1
+    assert lib.pnpadmm_dncnn_forward_bf16(q, q, 1, 3, 8, 8, 15, q, q, q, q, q, q, 1, q, q, None) == -5
+    assert b'input channels' in lib.pnpadmm_last_error_string()
+    assert lib.pnpadmm_dncnn_forward_bf16(q, q, 1, 1, 8, 8, -1, q, q, q, q, q, q, 1, q, q, None) == -1
+    assert lib.pnpadmm_dncnn_activation_bytes(256, 256, 256) >= 256 * 256 * 256 * 128
+    assert lib.pnpadmm_dncnn_activation_bytes(0, 256, 256) == 0
 
 
 def test_no_cpu_fallback():
