@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
 // Block = a patch of 32 columns x kHeadRows rows; warp = 8-channel chunk, lane = column.  A thread keeps its 72 CIN
 // weights in registers and slides a 3x3 window DOWN its column: three new (coalesced) loads per pixel instead of nine;
 // a warp stores 32 consecutive pixels of one chunk plane (512 contiguous bytes) per row.
-constexpr int kHeadRows = 16;
+constexpr int kHeadRows = 64;
 template <int CIN>
 __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                          const float* __restrict__ w, const float* __restrict__ bias, int B,
