@@ -112,6 +112,31 @@ cudaError_t set_stream_attrs() {
 // ------------------------------------------------------------------------------------------
 bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+// 2-D tensor map of `planes` row-major complex64 planes stacked as [planes N rows][N columns], boxes of C columns x 256 rows
+// (the column-pass tile in four pieces at N = 1024).  The encoder comes from the driver through the runtime's entry-point
+// query, so the library does not link against libcuda.  Returns false if it is unavailable (the cp.async kernel runs).
+bool plane_tensor_map(CUtensorMap* tm, const void* base, int planes, int N, int C) {
+    typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode enc = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<Encode>(f);
+    }();
+    if (!enc || (((uintptr_t)base) & 15)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)planes * N};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)C, 256};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T> struct S2 {
     static bool ok(int) { return false; }
     static cudaError_t set_attrs() { return cudaSuccess; }
@@ -136,6 +161,8 @@ template <> struct S2<float> {
         SET2((s2::cols2_kernel<N, CM_FWD_ACQ>), s2::ColsGeo<N>::kSmemBytes)
         SET2((s2::cols2_kernel<N, CM_INV>), s2::ColsGeo<N>::kSmemBytes)
         SET2((s2::cols2_kernel<N, CM_FWD_BLEND_INV>), s2::ColsGeo<N>::kSmemBytes)
+        SET2((s2::cols2_tma_kernel<N, false>), s2::ColsGeo<N>::kSmemBytes + 32)
+        SET2((s2::cols2_tma_kernel<N, true>), s2::ColsGeo<N>::kSmemBytes + 32)
 #undef SET2
         return cudaSuccess;
     }
@@ -162,6 +189,17 @@ template <> struct S2<float> {
         p.P = planes;
         const long ntiles = (long)planes * (N / G::C);
         const long cap = (long)sm_count * G::kCtasPerSm;
+        if (MODE == CM_FWD_BLEND_INV) {      // iteration pass: K and G tiles through 2-D TMA (PNPADMM_COLS_LSU=1: cp.async variant)
+            static const bool lsu = getenv("PNPADMM_COLS_LSU") != nullptr;
+            CUtensorMap tmK, tmG;
+            if (!lsu && plane_tensor_map(&tmK, p.K, planes, N, G::C) && plane_tensor_map(&tmG, p.G, planes, N, G::C)) {
+                static const bool tma_store = getenv("PNPADMM_COLS_TMA_STORE") != nullptr;   // experiment: measured 1 % slower
+                const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+                if (tma_store) s2::cols2_tma_kernel<N, true><<<grid, G::kThreads, G::kSmemBytes + 32, st>>>(p, mpack, tmK, tmG);
+                else s2::cols2_tma_kernel<N, false><<<grid, G::kThreads, G::kSmemBytes + 32, st>>>(p, mpack, tmK, tmG);
+                return;
+            }
+        }
         s2::cols2_kernel<N, MODE><<<(unsigned)(ntiles < cap ? ntiles : cap), G::kThreads, G::kSmemBytes, st>>>(p, mpack);
     }
     template <int MODE> static int cols(const StreamParams<float>& p, int planes, const uint32_t* mpack, int sm_count, cudaStream_t st) {

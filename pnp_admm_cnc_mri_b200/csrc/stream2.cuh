@@ -19,6 +19,8 @@
 //   conflict-free without padding and each global store instruction covers whole row segments.
 #pragma once
 
+#include <cuda.h>              // CUtensorMap (types only; the encoder is fetched through the runtime)
+
 #include "cluster256.cuh"     // mbarrier / bulk-copy helpers
 #include "stream2_core.cuh"
 #include "streaming.cuh"      // StreamParams, modes, twiddle master table
@@ -341,6 +343,120 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
         __syncthreads();                     // all shared-memory reads of this tile done: slots reusable
     }
     cp_async_wait<0>();
+}
+
+// ----------------------------------------------------------------------------------------------
+// Columns pass of the iteration (col FFT -> residual blend -> col IFFT) with the K and G tiles loaded by 2-D TMA
+// (cp.async.bulk.tensor.2d, boxes of C columns x 256 rows from the row-major planes [planes N][N]): the strided 8 C-byte row
+// pieces of a tile never go through the LSU.  Same tiling, persistent loop, FFT stages and stores as cols2_kernel.
+// ----------------------------------------------------------------------------------------------
+PNP_D void tma_load_2d(uint32_t dst, const void* tmap, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+
+PNP_D void tma_store_2d(const void* tmap, int x, int y, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(src)
+                 : "memory");
+}
+
+// TMA_STORE: the results also leave through the tile slot and 2-D TMA stores instead of 8-byte stores of the LSU.
+template <int N, bool TMA_STORE>
+__global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm)
+cols2_tma_kernel(const StreamParams<float> p, const uint32_t* __restrict__ mpack, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmG) {
+    typedef ColsGeo<N> G;
+    constexpr int T = Plan<N>::T, C = G::C, NT = G::kThreads, TE = G::kTileElems;
+    constexpr int kBoxRows = 256, kBoxes = N / kBoxRows;
+    extern __shared__ __align__(128) unsigned char smem2[];
+    cf32* Kslot = reinterpret_cast<cf32*>(smem2);                  // [2][N][C]
+    cf32* Gs = Kslot + 2 * TE;                                     // [N][C]
+    cf32* TW = Gs + TE;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem2);
+    const uint32_t bar0 = smem0 + G::kSmemBytes;                   // fullK[0], fullK[1], fullG (after the tables)
+
+    const int tid = threadIdx.x, t = tid / C, c = tid % C;
+    constexpr int tiles_per_plane = N / C;
+    const int ntiles = p.P * tiles_per_plane;
+    const size_t nn = (size_t)N * N;
+    const float cf1 = p.cf[1], cf2 = p.cf[2];
+
+    if (tid == 0) {
+        k1::mbar_init(bar0, 1); k1::mbar_init(bar0 + 8, 1); k1::mbar_init(bar0 + 16, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int q = tid; q < 256; q += NT) TW[q] = mk<float>(g_tw256[q].x, g_tw256[q].y);
+    cf32* TW3 = TW + 256;
+    for (int q = tid; q < (Plan<N>::R3 - 1) * 256; q += NT)
+        TW3[q] = ld_tw(reinterpret_cast<const cf32*>(g_tw_f32) + ((q >> 8) + 1) * (q & 255) * (kTwMax / N));
+    const Tw3Table tw3{TW3};
+    __syncthreads();
+
+    // one thread: expect the tile's bytes, then one box per 256 rows
+    auto issue = [&](const CUtensorMap* tm, int tile, uint32_t dst, uint32_t bar) {
+        const int plane = tile / tiles_per_plane, c0 = (tile - plane * tiles_per_plane) * C;
+        k1::mbar_arm_tx(bar, TE * 8);
+#pragma unroll
+        for (int q = 0; q < kBoxes; ++q) tma_load_2d(dst + q * kBoxRows * C * 8, tm, c0, plane * N + q * kBoxRows, bar);
+    };
+
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) issue(&tmK, tile, smem0, bar0);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int plane = tile / tiles_per_plane, c0 = (tile - plane * tiles_per_plane) * C;
+        const int next = tile + gridDim.x;
+        if (tid == 0) {
+            issue(&tmG, tile, smem0 + 2 * TE * 8, bar0 + 16);
+            if (next < ntiles) {
+                // slot s ^ 1 still feeds the TMA store of the previous tile: wait until it has been read
+                if (TMA_STORE) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                issue(&tmK, next, smem0 + (uint32_t)((s ^ 1) * TE * 8), bar0 + 8 * (s ^ 1));
+            }
+        }
+        const uint32_t codes = mpack[(p.mcode_batched ? (size_t)plane * (nn / 16) : 0) + (size_t)t * N + c0 + c];
+
+        k1::mbar_wait(bar0 + 8 * s, (it >> 1) & 1);          // K tile landed (natural row order)
+        ColLine<C> ln;
+        ln.col = Kslot + s * TE + c;
+        cf32 a[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) a[m] = ln.col[(t + T * m) * C];
+        __syncthreads();                     // tile fully read before it is reused as exchange scratch
+        fft_regs<false, N, true>(a, t, ln, TW, tw3);
+        k1::mbar_wait(bar0 + 16, it & 1);                    // G tile landed
+        __syncthreads();                     // forward-transform scratch reads done
+        const cf32* g = Gs + c;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const cf32 gg = g[(t + T * m) * C];
+            const uint32_t code = (codes >> (2 * m)) & 3u;
+            const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
+            a[m] = mk<float>(gg.re - cf * a[m].re, gg.im - cf * a[m].im);
+        }
+        fft_regs<true, N, true>(a, t, ln, TW, tw3);
+        if (TMA_STORE) {
+            __syncthreads();                 // last scratch reads of the inverse transform done
+#pragma unroll
+            for (int m = 0; m < 16; ++m) ln.col[(t + T * m) * C] = a[m];          // natural row order = the box layout
+            k1::fence_proxy_async();         // staged results (and my earlier slot accesses) visible to the async proxy
+            __syncthreads();
+            if (tid == 0) {
+#pragma unroll
+                for (int q = 0; q < kBoxes; ++q)
+                    tma_store_2d(&tmK, c0, plane * N + q * kBoxRows, smem0 + (uint32_t)(s * TE * 8) + q * kBoxRows * C * 8);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            cf32* o = p.K + (size_t)plane * nn + c0 + c;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) o[(size_t)(t + T * m) * N] = a[m];
+            k1::fence_proxy_async();         // my generic accesses of the slots precede the next TMA writes into them
+            __syncthreads();                 // all shared-memory reads of this tile done: slots reusable
+        }
+    }
+    if (TMA_STORE && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores done before the CTA's smem goes away
 }
 
 // mcode [N][N] bytes -> packed words [T][N] (one word per column-pass thread and tile)
