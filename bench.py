@@ -411,11 +411,11 @@ def run_ours(args):
         its2 = k2['B'] * k2['iters'] / (k2['ms'] * 1e-3)
         moved = its2 * 36.5 * k2['N'] ** 2 / 1e9
         line['roofline_streaming'] = {
-            'bound': 'hbm', 'kernel': 'rows2_kernel<1024> + cols2_kernel<1024> (K2, one pair per iteration)',
+            'bound': 'hbm', 'kernel': 'rows2_kernel<1024> + cols2_tma_kernel<1024> (K2, one pair per iteration; column tiles loaded by 2-D TMA)',
             'achieved': moved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': moved / hbm_peak,
             'traffic': 2319e6 * k2['B'] / 64,
-            'traffic_source': 'profiles/r1_k2v2_ncu_summary.txt: dram read+write of one rows2 + one cols2 launch at N=1024, '
-                              'B=64 (1554 MB + 765 MB), scaled by B/64',
+            'traffic_source': 'profiles/r1_k2_tma_ncu_summary.txt: dram read+write of one rows2 + one cols2 launch at N=1024, '
+                              'B=64 (1551 MB + 763 MB; r1_k2v2_ncu_summary.txt: 1554 + 765), scaled by B/64',
             'bytes_model': '73 N^2 per packed plane-iteration = 36.5 N^2 per image-iteration (rows pass 48 B/px: K 8+8, '
                            'z,w of two images 16+16; cols pass 25 B/px: K 8+8, G 8, codes 1/4): DESIGN.md 5',
             'achieved_survey_q57': its2 * 57 * k2['N'] ** 2 / 1e9,
