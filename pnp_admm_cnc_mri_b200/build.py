@@ -37,7 +37,9 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, os.path.join(CSRC, 'pnpadmm.cu')]
+    # PNPADMM_NVCC_EXTRA: extra flags, e.g. "-DPNPADMM_TC_EXPERIMENTS -DPNPADMM_K1_EXPERIMENTS" to compile the timing switches in
+    extra = os.environ.get('PNPADMM_NVCC_EXTRA', '').split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, os.path.join(CSRC, 'pnpadmm.cu')]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)

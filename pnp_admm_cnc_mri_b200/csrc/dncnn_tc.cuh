@@ -72,7 +72,8 @@ struct ConvParams {
     const float* bias;          // [64] (tail: [1])
     int B, H, W, strip, xtiles, ystrips, items;
     int relu;
-    // PNPADMM_TC_DEBUG, timing experiments only (every bit but 256 makes the results invalid): 1 = no input copies, 2 = no
+    // PNPADMM_TC_DEBUG, timing experiments only, compiled in with -DPNPADMM_TC_EXPERIMENTS (PNPADMM_NVCC_EXTRA of build.py);
+    // every bit but 256 makes the results invalid: 1 = no input copies, 2 = no
     // output stores, 4 = no MMAs, 8 / 16 = no tcgen05.ld / no accumulator re-init in the epilogue, 64 = no MMA <-> epilogue
     // handshake (epilogue off), 128 = no producer <-> MMA handshake (producers off), 256 = wait-time attribution (g_tc_prof)
     int dbg;
@@ -198,7 +199,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
     constexpr int kWBytes = 9 * 8 * NOUT * 16;
     constexpr uint32_t kTmemColsK = kBlocks * NOUT;          // 512 (all of TMEM) or 128
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool prof = (p.dbg & 256) != 0;
+#ifdef PNPADMM_TC_EXPERIMENTS
+    const int dbg = p.dbg;                     // timing experiments (see ConvParams::dbg); production builds compile them out
+#else
+    constexpr int dbg = 0;
+#endif
+    const bool prof = (dbg & 256) != 0;
     const uint32_t s0 = smem_u32(smem);
     const uint32_t ring = s0 + kOffRing, bars = s0 + kOffBar;
     auto bFull = [&](uint32_t i) { return bars + 8 * i; };
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
             const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in);
             const size_t plane = (size_t)p.W * 16, rowb = 8 * plane;
             uint32_t e = 0;
-            for (int item = blockIdx.x; item < ((p.dbg & 128) ? 0 : p.items); item += gridDim.x) {
+            for (int item = blockIdx.x; item < ((dbg & 128) ? 0 : p.items); item += gridDim.x) {
                 const Item it = decode_item(p, item);
                 const int xs = it.x0 - 1;
                 const int lo = xs < 0 ? 0 : xs;
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     const uint32_t st = e % kStages;
                     mbar_wait_t(bEmpty(st), ((e / kStages) & 1u) ^ 1u, w0, prof);
                     const uint32_t bar = bFull(st), dst0 = ring + st * kRowBytes;
-                    if (p.dbg & 1) { if (pw == 0) mbar_arrive(bar); continue; }
+                    if (dbg & 1) { if (pw == 0) mbar_arrive(bar); continue; }
                     if (pw == 0) k1::mbar_arm_tx(bar, kRowTxBytes);       // the other producer warps' bytes may land first: fine
                     const int y = it.y0 - 1 + r;
                     if (y < 0 || y >= p.H) {
@@ -317,15 +323,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         // of a row and the first of the next is a bubble.  The waits for row e + 1 (pre) and the commits of row e - 1
         // (post) are therefore placed INSIDE row e's MMA stream; nothing but loop control sits between rows.
         auto pre = [&](uint32_t ee, int i, int R, uint32_t tb) {           // barriers of input row (ee, i)
-            if (i < R && !(p.dbg & 64)) {                              // block of the output row that starts with this input row
+            if (i < R && !(dbg & 64)) {                              // block of the output row that starts with this input row
                 const uint32_t t = tb + i;
                 mbar_wait_t(bTEmpty(blk(t)), ((t / kBlocks) & 1u) ^ 1u, w1, prof);
             }
-            if (!(p.dbg & 128)) mbar_wait_t(bFull(ee % kStages), (ee / kStages) & 1u, w2, prof);
+            if (!(dbg & 128)) mbar_wait_t(bFull(ee % kStages), (ee / kStages) & 1u, w2, prof);
             tc_fence_after();
         };
         auto issue = [&](uint32_t ee, int i, int R, uint32_t tb, int dx0, int dx1) {   // MMAs of taps kx in [dx0, dx1)
-            if (!leader || (p.dbg & 4)) return;
+            if (!leader || (dbg & 4)) return;
             const uint32_t a_row = ring + (ee % kStages) * kRowBytes;
             const uint64_t a_desc0 = desc_hi_a | (uint64_t)((a_row & 0x3FFFFu) >> 4);
             const int dy_hi = i < 2 ? i : 2;
@@ -353,8 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         auto post = [&](uint32_t ee, int i, uint32_t tb) {
             __syncwarp();
             if (leader) {
-                if (!(p.dbg & 128)) tc_commit(bEmpty(ee % kStages));
-                if (i >= 2 && !(p.dbg & 64)) tc_commit(bTFull(blk(tb + i - 2)));
+                if (!(dbg & 128)) tc_commit(bEmpty(ee % kStages));
+                if (i >= 2 && !(dbg & 64)) tc_commit(bTFull(blk(tb + i - 2)));
             }
             __syncwarp();
         };
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         const long long tstart = clock64();
         const uint32_t grp = warp >> 2, quad = warp & 3;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        for (int item = blockIdx.x; item < ((p.dbg & 64) ? 0 : p.items); item += gridDim.x) {
+        for (int item = blockIdx.x; item < ((dbg & 64) ? 0 : p.items); item += gridDim.x) {
             const Item it = decode_item(p, item);
             for (int j = 0; j < it.rows; ++j, ++t) {
                 if (kEpiGroups > 1 && (t % kEpiGroups) != grp) continue;
@@ -410,12 +416,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                 const int x = it.x0 + quad * 32 + lane, y = it.y0 + j;
                 if (NOUT == 64) {
                     uint32_t v[64];
-                    if (!(p.dbg & 8)) {
+                    if (!(dbg & 8)) {
                     PNP_TMEM_LD32(taddr, v, 0);
                     PNP_TMEM_LD32(taddr + 32, v, 32);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     }
-                    if (!(p.dbg & 16)) {
+                    if (!(dbg & 16)) {
                     init_block(taddr);                           // next use of the block starts from the bias again
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     }
@@ -447,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     if (lane == 0) {                           // each warp's lane 0 sends two of the eight chunk planes
                         const int npx = p.W - it.x0 < kTileM ? p.W - it.x0 : kTileM;
                         unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + (((size_t)it.b * p.H + y) * 8 * p.W + it.x0) * 16;
-                        if (!(p.dbg & 2)) {
+                        if (!(dbg & 2)) {
 #pragma unroll
                             for (int q = 2 * quad; q < 2 * quad + 2; ++q) bulk_store(dst + (size_t)q * p.W * 16, stile + q * (kTileM * 16), npx * 16);
                         }
@@ -462,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bTEmpty(b));
-                    if (x < p.W && !(p.dbg & 2)) {
+                    if (x < p.W && !(dbg & 2)) {
                         const float n = __uint_as_float(v0);
                         const size_t pix = ((size_t)it.b * p.H + y) * p.W + x;
                         p.out_f32[pix] = p.resid ? p.resid[(size_t)it.b * p.resid_bstride + (size_t)y * p.W + x] - n : n;

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Time one 64->64 tensor-core layer (pnpadmm_conv64_bf16): python tools/conv64_time.py [B] [reps]
-PNPADMM_TC_DEBUG=1|2|4 (or sums) skips input copies / output stores / MMAs (timing experiments, results invalid)."""
+PNPADMM_TC_DEBUG=1|2|4 (or sums) skips input copies / output stores / MMAs, 256 prints the wait-time attribution (timing
+experiments, results invalid; needs a library built with PNPADMM_NVCC_EXTRA=-DPNPADMM_TC_EXPERIMENTS)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Head + tail only (a 2-layer DnCNN) through the fused path: isolates the N = 16 tail kernel for PNPADMM_TC_DEBUG runs."""
+"""Head + tail only (a 2-layer DnCNN) through the fused path: isolates the N = 16 tail kernel for PNPADMM_TC_DEBUG runs
+(library built with PNPADMM_NVCC_EXTRA=-DPNPADMM_TC_EXPERIMENTS)."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
