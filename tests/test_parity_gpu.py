@@ -1,5 +1,6 @@
 """GPU parity: the CUDA path (through the C ABI) against the fp64 oracle on the same inputs.
 Gates (BASELINE.json north_star): fp32 rel-L2 <= 1e-4 and |dPSNR| <= 0.01 dB; fp64 rel-L2 <= 1e-10."""
+import os
 import numpy as np
 import pytest
 
@@ -452,3 +453,32 @@ def test_full_size_batches_replicate_small_ones(pk, N, B, kernel):
     else:   # hybrid: copies computed by the cluster kernel and by the streaming kernels differ only by rounding
         assert rel(reps, np.broadcast_to(reps[:1], reps.shape)) < 2e-5
         assert np.array_equal(reps[1], reps[0])                                    # both inside the K1 share
+
+
+@pytest.mark.gpu
+def test_k2_column_pass_variants_bit_identical(tmp_path):
+    """The iteration's columns pass has three data-movement variants (2-D TMA tile loads = default, cp.async loads, TMA loads +
+    TMA stores); the arithmetic is the same code, so the reconstructions must agree bit for bit.  The variants are selected by
+    environment variables read once per process, hence the subprocesses."""
+    import subprocess
+    import sys
+    script = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "import pnp_admm_cnc_mri_b200 as pk\n"
+        "from pnp_admm_cnc_mri_b200 import data\n"
+        "out = []\n"
+        "for N in (256, 512, 1024):\n"
+        "    imgs = data.phantoms(3, N, seed0=7)\n"
+        "    x = pk.admm_solve(imgs, data.make_mask('radial', N, seed=2), data.make_noise(N, seed=4), prox='cnc', kernel='streaming',\n"
+        "                      alpha=0.45, iter_num=4, lambda1=0.5, reo=0.05, b=64)\n"
+        "    out.append(x.ravel())\n"
+        "np.save(sys.argv[1], np.concatenate(out))\n")
+    results = []
+    for k, env_add in enumerate(({}, {'PNPADMM_COLS_LSU': '1'}, {'PNPADMM_COLS_TMA_STORE': '1'})):
+        f = str(tmp_path / f'v{k}.npy')
+        env = dict(os.environ, **env_add)
+        subprocess.run([sys.executable, '-c', script, f], check=True, env=env, timeout=300)
+        results.append(np.load(f))
+    assert np.array_equal(results[0], results[1])
+    assert np.array_equal(results[0], results[2])
