@@ -61,6 +61,56 @@ def test_pack_dncnn_layer_split():
         df.conv_layers(denoisers.build_model('ircnn_gray'))      # dilated convolutions are not on this kernel
 
 
+def _simulate_input_stationary_schedule(strip_rows, blocks=8):
+    """Model of the MMA warp's bookkeeping in conv64_tc_kernel (csrc/dncnn_tc.cuh): input row i of a strip of R output
+    rows feeds the output rows j = i - dy; output row t (running count) accumulates in TMEM block (-t) mod 8; a window of
+    consecutive dy taps is one instruction unless it wraps around the block ring.  Returns (per output row: the set of
+    (input row, dy) contributions it received, instructions issued per input row)."""
+    blk = lambda t: (blocks - (t % blocks)) % blocks
+    acc = {b: None for b in range(blocks)}          # block -> (owner t, set of contributions)
+    done, n_instr = {}, []
+    t_base = 0
+    for R in strip_rows:
+        for i in range(R + 2):
+            if i < R:                                # first contribution to output row t_base + i: its block must be free
+                b = blk(t_base + i)
+                assert acc[b] is None, 'block reused before it was drained'
+                acc[b] = (t_base + i, set())
+            dy_hi = min(i, 2)
+            dy = max(i - (R - 1), 0)
+            count = 0
+            while dy <= dy_hi:
+                b = blk(t_base + i - dy)
+                n = min(dy_hi - dy + 1, blocks - b)
+                for k in range(n):                   # one instruction of N = 64 n: blocks b .. b + n - 1 <-> taps dy .. dy + n - 1
+                    owner, contrib = acc[b + k]
+                    assert owner == t_base + i - (dy + k), 'window block does not belong to the intended output row'
+                    contrib.add((i, dy + k))
+                count += 1
+                dy += n
+            n_instr.append(count)
+            if i >= 2:                               # output row i - 2 is complete: the epilogue drains and frees its block
+                b = blk(t_base + i - 2)
+                owner, contrib = acc[b]
+                done[owner] = (i - 2, contrib)
+                acc[b] = None
+        t_base += R
+    assert all(v is None for v in acc.values())
+    return done, n_instr
+
+
+@pytest.mark.parametrize('strips', [[64, 64, 64, 64], [1], [2, 1, 3], [5, 7, 64, 2], [64] * 9])
+def test_input_stationary_schedule_bookkeeping(strips):
+    done, n_instr = _simulate_input_stationary_schedule(strips)
+    assert len(done) == sum(strips)
+    for t, (j, contrib) in done.items():
+        # output row j of its strip = taps dy = 0, 1, 2 applied to the input rows j, j + 1, j + 2 (strip-local, row 0 = y0 - 1)
+        assert contrib == {(j + dy, dy) for dy in range(3)}, (t, j, contrib)
+    assert max(n_instr) <= 2 and min(n_instr) >= 1          # a window is split only where it wraps around the ring
+    if strips == [64] * 9:
+        assert sum(c == 2 for c in n_instr) / len(n_instr) < 0.3
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
