@@ -7,8 +7,9 @@
 //     D[m = pixel x0+m of row y][n = c_out] = sum over 9 taps (ky, kx) and 64 c_in of
 //         act[y + ky - 1][x0 + m + kx - 1][c_in] * w[c_out][c_in][ky][kx]            M = 128, N = 64, K = 576
 //
-// issued as 36 `tcgen05.mma.cta_group::1.kind::f16` (128 x 64 x 16, bf16 in, fp32 accumulate in TMEM) by one
-// thread.  Activations are bf16 in CHUNK-PLANAR ROWS, [B][H][8 chunks][W][8 channels]: a row of the image is 8 planes of
+// issued as `tcgen05.mma.cta_group::1.kind::f16` (bf16 in, fp32 accumulate in TMEM) by one elected thread: 12 instructions
+// of 128 x 192 x 16 per input row, the three ky taps stacked along N (input-stationary schedule, see the kernel).
+// Activations are bf16 in CHUNK-PLANAR ROWS, [B][H][8 chunks][W][8 channels]: a row of the image is 8 planes of
 // W x 16 bytes.  Shared memory uses the NO-SWIZZLE K-major canonical layout (core matrix = 8 rows x 16 B = 128 B):
 //     A row buffer : [k-chunk 0..7][slot 0..130][8 c_in]   slot s <-> pixel x0 - 1 + s (1-pixel halo each side)
 // so the tap shift kx is a 16-byte shift of the descriptor start address and the tap shift ky selects another row
@@ -23,9 +24,10 @@
 //   warps 0-7  : two epilogue groups, alternate output rows (TMEM lane quadrant = warp & 3)
 //   warp  8    : TMEM alloc, one elected lane issues the MMAs
 //   warps 9-10 : producers (one lane each issues the bulk copies of four k-chunk planes)
-//   mbarriers  : full[6] / empty[6] (producers <-> MMA), tfull[8] / tempty[8] (MMA <-> epilogue, one pair per block)
+//   mbarriers  : full[5] / empty[5] (producers <-> MMA, one pair per ring stage), tfull[8] / tempty[8] (MMA <-> epilogue,
+//                one pair per TMEM block)
 //
-// The first layer (c_in = 1 or 2) and nothing else runs on the CUDA cores (it is a 0.3 ms NHWC write); the last
+// The first layer (c_in = 1 or 2) and nothing else runs on the CUDA cores (bound by its 128 B per pixel write); the last
 // layer (c_out = 1) reuses the tensor-core kernel with N = 16 (rows 1..15 of B are zero) and an fp32 epilogue
 // that applies the residual  out = x - n(x).
 #pragma once
@@ -39,12 +41,12 @@ namespace tc {
 
 constexpr int kTileM = 128;                    // output pixels per tile
 constexpr int kSlots = kTileM + 2;             // staged input pixels per row
-constexpr int kPPad = 131;                     // slot pitch of a k-chunk plane, odd: the 8 chunks of a pixel hit 8 bank groups
+constexpr int kPPad = 131;                     // slot pitch of a k-chunk plane (130 used; odd, so the 8 chunk planes start in 8 different bank groups)
 constexpr int kChunkBytes = kPPad * 16;        // = LBO of the A descriptor
 constexpr int kRowBytes = 8 * kChunkBytes;     // 16768
 constexpr int kStages = 5;
 constexpr int kEpiGroups = 2;                  // epilogue groups of four warps; group g takes the output rows t = g (mod kEpiGroups)
-constexpr int kMmaWarp = 4 * kEpiGroups;       // warps [0, 4 g): epilogue, then the MMA warp, then the producer warp
+constexpr int kMmaWarp = 4 * kEpiGroups;       // warps [0, 4 g): epilogue, then the MMA warp, then the producer warps
 constexpr int kProdWarps = 2;                  // producer warps: issuing a bulk copy costs its thread ~140 cycles, so the 8 copies of a row are split
 constexpr int kThreads = 32 * (kMmaWarp + 1 + kProdWarps);
 constexpr int kOffW = 0;
