@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
 
     if (warp > kMmaWarp) {
         // ------------------------------------------------------------------ producer: input rows -> ring
-        // One lane streams the input rows with 1-D bulk copies (TMA engine, no LSU): in the chunk-planar layout the
+        // One lane of each producer warp streams its half of the k-chunk planes of the input rows with 1-D bulk copies (TMA
+        // engine, no LSU): in the chunk-planar layout the
         // 130 pixels a row buffer needs from one 8-channel chunk are 2080 contiguous bytes of global memory and of the
         // A operand's plane, so a row is 8 copies (+ 16-byte zero copies for the pixel left / right of the image and
         // whole zero planes for the rows above / below it: the convolution's padding).
