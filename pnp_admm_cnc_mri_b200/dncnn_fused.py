@@ -67,6 +67,8 @@ class FusedDnCNN:
     """``y = D(x)`` for a DnCNN (residual, 1 input channel) or FDnCNN (non-residual, 2 input channels).
 
     x: (B, cin, H, W) float32 CUDA tensor -> (B, 1, H, W) float32.  Work is enqueued on the current stream.
+    The instance owns the two bf16 activation buffers (2 x B*H*W*128 bytes, re-allocated when the shape changes), so calls on
+    one instance must be stream-ordered; use one instance per stream for concurrent forwards.
     """
 
     def __init__(self, net: nn.Module, residual: bool, device='cuda'):
