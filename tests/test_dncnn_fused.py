@@ -167,6 +167,39 @@ def test_dncnn_forward_gpu(name, shape):
     assert _rel(got, want) < 1e-2
 
 
+def _forward_with_bf16_rounding_points(net, x):
+    """fp32 PyTorch convolutions with the roundings K5 applies: network input, weights and biases in bf16, every activation
+    rounded to bf16 after the ReLU, fp32 accumulation, fp32 last layer and residual."""
+    convs = df.conv_layers(net)
+    h = x.to(torch.bfloat16).float()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        for k, c in enumerate(convs):
+            h = F.conv2d(h, c.weight.to(torch.bfloat16).float(), c.bias.to(torch.bfloat16).float(), padding=1)
+            if k < len(convs) - 1:
+                h = F.relu(h).to(torch.bfloat16).float()
+    return h
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,shape', [('dncnn_25', (2, 256, 256)), ('fdncnn_gray', (1, 96, 160))])
+def test_dncnn_forward_matches_same_rounding_points_gpu(name, shape):
+    """Against an fp32 evaluation that rounds where K5 rounds, only the fp32 summation order is left, and the bf16 rounding
+    flips it causes (a pre-rounding difference of 1e-6 relative moves ~1e-4 of the activations across a bf16 boundary per
+    layer, each by 2^-8 relative).  Measured on B200: rel-L2 of n(x) 5.0e-4 (DnCNN-17), 1.4e-3 (FDnCNN-20); gate 5e-3.
+    (PyTorch's own bf16 forward is 3.6e-2 from fp32 on the same network.)"""
+    B, H, W = shape
+    net = denoisers.build_model(name, seed=5).cuda()       # default init (a contraction: rounding differences do not amplify)
+    cin = df.conv_layers(net)[0].in_channels
+    x = torch.rand(B, cin, H, W, generator=torch.Generator().manual_seed(3)).cuda()
+    got = df.FusedDnCNN(net, residual=(cin == 1))(x)
+    with torch.no_grad():
+        n_want = _forward_with_bf16_rounding_points(net, x)
+    n_got = (x[:, :1] - got) if cin == 1 else got
+    err = _rel(n_got, n_want)
+    print('rel-L2 of n(x) against the same-rounding-points evaluation:', err)
+    assert err < 5e-3, err
+
+
 @pytest.mark.gpu
 def test_denoiser_dispatch_uses_fused_gpu():
     d = denoisers.build_denoiser('dncnn_25', seed=1)
