@@ -321,9 +321,12 @@ def run_ours(args):
         torch.cuda.empty_cache()
     # K5 (DnCNN on tcgen05, BASELINE config 3's denoiser) against the bf16 tensor peak: one 64->64 layer and one
     # DnCNN-17 forward at B = 256, 256x256 (activations 2 x 2.1 GB >> L2)
+    clocks = sampler.stop() if rank == 0 else None     # the headline legs end here; the tensor-core leg below samples its own clocks
     k5 = None
     if rank == 0:
         from pnp_admm_cnc_mri_b200 import denoisers as pden, dncnn_fused as pdf
+        sampler5 = ClockSampler(local)
+        sampler5.start()
         B5 = 256
         net = pden.build_model('dncnn_25', seed=0)
         fused = pdf.FusedDnCNN(net, residual=True, device=dev)
@@ -345,9 +348,9 @@ def run_ours(args):
         k5 = dict(B=B5, layer_ms=t_of(lambda: _abi.check(lib.pnpadmm_conv64_bf16(a5.data_ptr(), o5.data_ptr(), w5.data_ptr(),
                                                                                b5.data_ptr(), B5, N, N, 1, st5))),
                   forward_ms=t_of(lambda: fused(x5)))
+        k5['clocks'] = sampler5.stop()
         del fused, x5, a5, o5
         torch.cuda.empty_cache()
-    clocks = sampler.stop() if rank == 0 else None
 
     fl = ctypes.c_double()
     _abi.check(lib.pnpadmm_measure_fp32_peak(fl, None))
@@ -438,6 +441,7 @@ def run_ours(args):
             'hbm_gbs_moved': 2 * 128.0 * N * N * k5['B'] / (k5['layer_ms'] * 1e-3) / 1e9,
             'peak_source': 'MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)' if 'bf16_tflops' in peaks else 'fallback 1670 TFLOP/s',
             'workload': f"B={k5['B']}, 256x256, bf16 operands, fp32 accumulation",
+            'clocks': k5['clocks'],
             'dncnn17_forward': {'ms': k5['forward_ms'], 'achieved': fwd_flop / (k5['forward_ms'] * 1e-3) / 1e12,
                                 'what': 'head (CUDA cores) + 15 x conv64_tc_kernel<64> + tail conv64_tc_kernel<16>; BASELINE config 3 '
                                         'runs two of these per PnP-ADMM-CNC iteration (tools/pnp_bench.py c3)'}}
