@@ -33,13 +33,16 @@ def _script(tag: str) -> str:
     return hits[0]
 
 
-def run_script(tag: str, argv=(), images=None, mask_file=None, model_zoo=None):
+def run_script(tag: str, argv=(), images=None, mask_file=None, model_zoo=None, post=None):
     """Execute reference script ``tag`` ('【1】', '【3】', '【4】', '【6】').
 
     images    : list of PNG paths to expose as testsets/Set1 (default: reference set1 = 05.png)
     mask_file : basename of the CS_MRI mask the script's k=0 slot should see
                 (default Q_Random30.mat).  The scripts hard-code k=0 (S1:191).
     model_zoo : optional dict name -> state_dict saved as model_zoo/<name>.pth (PnP scripts)
+    post      : optional callable(g) run after the script, still inside the scratch cwd, e.g. to call the
+                script's own (unmodified) functions for the presets its driver does not reach (S3:375-376,
+                S6:610-611 hard-code the model index); its return value is stored as g['_post'].
     Returns the script's globals dict (``g['out']`` is the 22-slot list).
     """
     if not reference_available():
@@ -74,7 +77,10 @@ def run_script(tag: str, argv=(), images=None, mask_file=None, model_zoo=None):
         script = _script(tag)
         sys.argv = [script] + [str(a) for a in argv]
         os.chdir(scratch)
-        return runpy.run_path(script, run_name='__main__')
+        g = runpy.run_path(script, run_name='__main__')
+        if post is not None:
+            g['_post'] = post(g)
+        return g
     finally:
         os.chdir(cwd0)
         sys.argv = argv0

@@ -56,6 +56,8 @@ struct DeviceState {
     int max_cl8 = 0, max_cl16 = 0;  // co-resident clusters of the 8-CTA / 16-CTA variants of K1
     int k1_cluster = 8;           // geometry used by default
     cudaStream_t side = nullptr;  // hybrid schedule: the K2 share of a batch runs here, beside K1
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;   // fork / join of the hybrid schedule (created once, with the side stream)
+    std::mutex mu;                // guards the side stream's fork/join pairs and this device's K2 graph cache
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
@@ -247,8 +249,8 @@ int ensure_device(DeviceState** out) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kMaxDevices) return fail(PNPADMM_ERR_CUDA, "device ordinal %d out of range", dev);
-    std::lock_guard<std::mutex> lk(g_mu);
     DeviceState& d = g_dev[dev];
+    std::lock_guard<std::mutex> lk(g_mu);      // first-time initialisation only does real work under it
     if (!d.ready) {
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
@@ -292,6 +294,8 @@ int ensure_device(DeviceState** out) {
         }
         d.max_clusters_256 = d.k1_cluster == 16 ? d.max_cl16 : d.max_cl8;
         CUDA_TRY(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.fork_ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.join_ev, cudaEventDisableTiming));
         d.ready = true;
     }
     *out = &d;
@@ -587,10 +591,12 @@ int stream2_launch_sequence(const StreamParams<T>& p0, int planes, const uint32_
     return PNPADMM_OK;
 }
 
-// The sequence is 2 * iters + 1 launches with fixed arguments: it is captured once per configuration into a
-// CUDA graph (small per-device cache keyed by every kernel argument) and replayed with one launch, so a caller
-// that reconstructs batch after batch through the same buffers spends ~10 us of host time per call instead of
-// ~0.4 ms.  Skipped when the caller is itself capturing the stream, or with PNPADMM_NO_GRAPH=1.
+// The sequence is 2 * iters + 1 launches with fixed arguments: it is captured into a CUDA graph (small per-device
+// cache keyed by every kernel argument) and replayed with one launch, so a caller that reconstructs batch after
+// batch through the same buffers spends ~10 us of host time per call instead of ~0.4 ms.  A key is only captured
+// the SECOND time it is seen in a row (callers that allocate fresh x, z, w per call would otherwise pay a capture
+// + instantiation per call and thrash the cache).  Skipped when the caller is itself capturing the stream, or with
+// PNPADMM_NO_GRAPH=1.  The cache is guarded by the device's own mutex (DeviceState::mu), not the global one.
 struct K2GraphKey {
     StreamParams<float> p;
     const uint32_t* mpack;
@@ -604,36 +610,56 @@ struct K2GraphEntry {
     unsigned long long stamp = 0;
 };
 constexpr int kGraphSlots = 6;
-K2GraphEntry g_k2graphs[kMaxDevices][kGraphSlots];
-unsigned long long g_graph_clock = 0;
+struct K2GraphCache {
+    K2GraphEntry slot[kGraphSlots];
+    K2GraphKey last_miss;
+    bool have_miss = false;
+    unsigned long long clock = 0;
+};
+K2GraphCache g_k2graphs[kMaxDevices];
+
+// Keys are compared byte-wise: both sides are built by memset(0) + memcpy of structs whose padding is itself
+// zeroed (base_params memsets StreamParams before filling it), so padding never carries stack garbage.
+void make_key(K2GraphKey* key, const StreamParams<float>& p, const uint32_t* mpack, int planes, int iters, int sms) {
+    memset(key, 0, sizeof(*key));
+    memcpy(&key->p, &p, sizeof(p));
+    key->mpack = mpack; key->planes = planes; key->iters = iters; key->sms = sms;
+}
 
 template <typename T>
-int stream2_replay(const StreamParams<T>& p, int planes, const uint32_t* mpack, int iters, int sms, cudaStream_t st) {
+int stream2_replay(const StreamParams<T>& p, int planes, const uint32_t* mpack, int iters, int sms, cudaStream_t st, bool) {
     return stream2_launch_sequence<T>(p, planes, mpack, iters, sms, st);
 }
+// `locked`: the caller already holds the device mutex (hybrid schedule).
 template <>
-int stream2_replay<float>(const StreamParams<float>& p, int planes, const uint32_t* mpack, int iters, int sms, cudaStream_t st) {
+int stream2_replay<float>(const StreamParams<float>& p, int planes, const uint32_t* mpack, int iters, int sms, cudaStream_t st,
+                          bool locked) {
     static const char* off = getenv("PNPADMM_NO_GRAPH");
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if ((off && atoi(off) != 0) || iters < 4 || cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    if ((off && atoi(off) != 0) || iters < 4 || st == nullptr || st == cudaStreamLegacy ||   // the legacy stream cannot be captured
+        cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
         (void)cudaGetLastError();
         return stream2_launch_sequence<float>(p, planes, mpack, iters, sms, st);
     }
     int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
     K2GraphKey key;
-    memset(&key, 0, sizeof(key));
-    key.p = p; key.mpack = mpack; key.planes = planes; key.iters = iters; key.sms = sms;
-    std::lock_guard<std::mutex> lk(g_mu);
+    make_key(&key, p, mpack, planes, iters, sms);
+    std::unique_lock<std::mutex> lk(g_dev[dev].mu, std::defer_lock);
+    if (!locked) lk.lock();
+    K2GraphCache& c = g_k2graphs[dev];
     K2GraphEntry* slot = nullptr;
     K2GraphEntry* victim = nullptr;
     for (int i = 0; i < kGraphSlots; ++i) {
-        K2GraphEntry& e = g_k2graphs[dev][i];
+        K2GraphEntry& e = c.slot[i];
         if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) { slot = &e; break; }
         if (!victim || (victim->valid && (!e.valid || e.stamp < victim->stamp))) victim = &e;
     }
     if (!slot) {
-        // the legacy default stream cannot be captured: launch directly there
-        if (st == nullptr || st == cudaStreamLegacy) return stream2_launch_sequence<float>(p, planes, mpack, iters, sms, st);
+        if (!c.have_miss || memcmp(&c.last_miss, &key, sizeof(key)) != 0) {   // first sighting: launch directly, remember it
+            memcpy(&c.last_miss, &key, sizeof(key)); c.have_miss = true;
+            return stream2_launch_sequence<float>(p, planes, mpack, iters, sms, st);
+        }
+        c.have_miss = false;
         slot = victim;
         if (slot->valid) {   // evict before the capture starts (graph destruction is not a capture-safe call)
             (void)cudaGraphExecDestroy(slot->exec);
@@ -658,19 +684,19 @@ int stream2_replay<float>(const StreamParams<float>& p, int planes, const uint32
             (void)cudaGraphDestroy(g);
             return fail(PNPADMM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e_inst));
         }
-        slot->key = key; slot->graph = g; slot->exec = ex; slot->valid = true;
+        memcpy(&slot->key, &key, sizeof(key)); slot->graph = g; slot->exec = ex; slot->valid = true;
     }
-    slot->stamp = ++g_graph_clock;
+    slot->stamp = ++c.clock;
     CUDA_TRY(cudaGraphLaunch(slot->exec, st));
     return PNPADMM_OK;
 }
 
 template <typename T>
 int stream2_iterate(const Workspace<T>& w, T* x, T* z, T* wv, int B, int N, const ProxParams<T>& pp, int iters, int sms,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool locked = false) {
     StreamParams<T> p = base_params(w, B, N);
     p.z = z; p.w = wv; p.x = x; p.prox = pp;
-    return stream2_replay<T>(p, w.P, w.mpack, iters, sms, st);
+    return stream2_replay<T>(p, w.P, w.mpack, iters, sms, st, locked);
 }
 
 // Hybrid schedule for N = 256: the cluster kernel can only use the SMs that form whole 8-SM groups inside
@@ -759,19 +785,18 @@ int iterate_impl(T* x, T* z, T* wv, int B, int N, int mask_batched, int prox, in
         w2.P = w.P - P1;
         w2.K = w.K + (size_t)P1 * nn; w2.G = w.G + (size_t)P1 * nn;
         if (w.solo) { w2.mcode = w.mcode + (size_t)P1 * nn; w2.mpack = w.mpack + (size_t)P1 * (nn / 16); }
-        cudaEvent_t fork, join;
-        CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(fork, st));
-        CUDA_TRY(cudaStreamWaitEvent(d->side, fork, 0));
+        // The fork / join events live in DeviceState (no allocation per call).  A stream wait captures the record
+        // that precedes it, so one pair serves every caller as long as each record + wait pair (and the side stream's
+        // launch order) is not interleaved with another host thread's: the device mutex.
+        std::lock_guard<std::mutex> lk(d->mu);
+        CUDA_TRY(cudaEventRecord(d->fork_ev, st));
+        CUDA_TRY(cudaStreamWaitEvent(d->side, d->fork_ev, 0));
         rc = ClusterDispatch<T>::run(w1, z, wv, x, z, wv, nullptr, B1, iters, pp, d, st);
         if (rc == PNPADMM_OK)
             rc = stream2_iterate<T>(w2, x + (size_t)B1 * nn, z + (size_t)B1 * nn, wv + (size_t)B1 * nn, B - B1, N, pp, iters,
-                                    d->sm_count - 8 * d->max_clusters_256, d->side);
-        CUDA_TRY(cudaEventRecord(join, d->side));
-        CUDA_TRY(cudaStreamWaitEvent(st, join, 0));
-        CUDA_TRY(cudaEventDestroy(fork));
-        CUDA_TRY(cudaEventDestroy(join));
+                                    d->sm_count - 8 * d->max_clusters_256, d->side, /*locked=*/true);
+        CUDA_TRY(cudaEventRecord(d->join_ev, d->side));
+        CUDA_TRY(cudaStreamWaitEvent(st, d->join_ev, 0));
         return rc;
     }
 

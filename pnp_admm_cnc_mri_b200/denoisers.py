@@ -246,6 +246,11 @@ class Denoiser:
         self.dtype = dtype
         self.device = torch.device(device)
         self.x8 = bool(x8) and self.arch in ('drunet', 'ircnn')       # only these branches look at x8 (S3:39-62)
+        if self.arch == 'ircnn' and ircnn_weights is None and weights is not None:
+            # KAIR's ircnn_gray.pth is ONE file holding 25 state-dicts keyed '0'..'24' (S3:187-189 `model25`)
+            sd = torch.load(weights, map_location='cpu') if isinstance(weights, (str, bytes)) else weights
+            if isinstance(sd, dict) and '0' in sd and isinstance(sd['0'], dict):
+                ircnn_weights, weights = sd, None
         net = model if model is not None else build_model(model_name, seed, weights)
         # DnCNN / FDnCNN in bf16 on a GPU run on the hand-written tensor-core kernels (csrc/dncnn_tc.cuh) unless
         # fused=False asks for the stock PyTorch module (the A/B baseline); other architectures stay in PyTorch.
@@ -299,8 +304,10 @@ class Denoiser:
         else:
             if self.ircnn_weights is not None:                                                      # S3:280-288
                 idx = int(math.ceil(float(self.sigmas[i]) * 255. / 2.) - 1)
-                if idx != self._ircnn_idx:
-                    self.net.load_state_dict(self.ircnn_weights[idx], strict=True)
+                if idx != self._ircnn_idx:                                                          # `former_idx`, starts at 0
+                    sets = self.ircnn_weights
+                    sd = sets[str(idx)] if isinstance(sets, dict) and str(idx) in sets else sets[idx]
+                    self.net.load_state_dict(sd, strict=True)
                     self._ircnn_idx = idx
             y = self._run(x)                                                                        # S3:56
         if mode:

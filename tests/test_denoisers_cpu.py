@@ -83,3 +83,39 @@ def test_oracle_pnp_matches_unmodified_scripts(cs_inputs, gold):
     assert np.abs(x - gold['cnc_dncnn']).max() < 2e-5
     x = orc.pnp_admm_l1(img, m, nz, _cpu_denoiser('drunet_gray', it, True, nz), iter_num=it, reo=0.26)  # S3:347
     assert np.abs(x - gold['l1_drunet']).max() < 2e-5
+
+
+def test_ircnn_sigma_indexed_weight_switch():
+    """S3:280-288 / S6:289-298: before every IRCNN call the reference picks one of 25 weight sets by
+    `current_idx = np.int(np.ceil(sigmas[i] * 255. / 2.) - 1)` and reloads only when the index changes
+    (`former_idx` starts at 0, so the very first call already swaps the random-init net for set 24).  The
+    reference branch itself is dead on NumPy >= 1.24 (`np.int`), so the rule is restated here and the live set is
+    identified per iteration from the output: 25 synthetic state-dicts, 50 iterations of the DPIR schedule."""
+    it = 50
+    sets = {str(k): dn.build_model('ircnn_gray', seed=100 + k).state_dict() for k in range(25)}   # KAIR layout: str keys
+    D = dn.Denoiser('ircnn_gray', iter_num=it, x8=False, dtype=torch.float32, device='cpu', seed=0, ircnn_weights=sets)
+    sig = orc.get_rho_sigma(sigma=max(0.255 / 255., 15 / 255.), iter_num=it, modelSigma1=49, modelSigma2=15.0, w=1.0)[1]
+    want_idx = [int(np.ceil(float(s) * 255. / 2.) - 1) for s in sig]
+    assert want_idx[0] == 24 and want_idx[-1] == 7 and sorted(set(want_idx), reverse=True) == list(range(24, 6, -1))
+    x = torch.rand(1, 1, 40, 56, generator=torch.Generator().manual_seed(3))
+    probe = dn.build_model('ircnn_gray', seed=0)
+    loads = []
+    orig = D.net.load_state_dict
+    D.net.load_state_dict = lambda sd, strict=True: (loads.append(1), orig(sd, strict=strict))[1]
+    for i in range(it):
+        y = D(x, i)
+        probe.load_state_dict(sets[str(want_idx[i])], strict=True)
+        with torch.no_grad():                              # (channels_last vs contiguous kernels: equal to rounding)
+            assert (y - probe(x)).abs().max() < 1e-6, (i, want_idx[i])
+        others = [k for k in (want_idx[i] - 1, want_idx[i] + 1) if 0 <= k < 25]
+        for k in others:                                   # and it is not a neighbouring set
+            probe.load_state_dict(sets[str(k)], strict=True)
+            with torch.no_grad():
+                assert (y - probe(x)).abs().max() > 1e-3
+    assert len(loads) == len(set(want_idx))                # one reload per index change, none in between
+    # a list indexed by int works too, and `weights=` given the 25-set dict is recognised as such
+    D2 = dn.Denoiser('ircnn_gray', iter_num=it, dtype=torch.float32, device='cpu', seed=0, weights=sets)
+    D3 = dn.Denoiser('ircnn_gray', iter_num=it, dtype=torch.float32, device='cpu', seed=0,
+                     ircnn_weights=[sets[str(k)] for k in range(25)])
+    for i in (0, 17, 49):
+        assert torch.equal(D2(x, i), D(x, i)) and torch.equal(D3(x, i), D(x, i))

@@ -20,13 +20,22 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
-def oracle_batch(imgs, mask, noises, prox, P):
+def _oracle_one(job):
+    prox, im, m, n, P = job
     fn = orc.admm_l1 if prox == 'l1' else orc.admm_cnc
-    out = []
-    for i, im in enumerate(imgs):
-        m = mask[i] if mask.ndim == 3 else mask
-        n = noises[i] if noises.ndim == 3 else noises
-        out.append(fn(im, m.astype(np.float64), n, return_state=True, **P))
+    return fn(im, m.astype(np.float64), n, return_state=True, **P)
+
+
+def oracle_batch(imgs, mask, noises, prox, P, workers=1):
+    """The fp64 oracle per image; `workers` > 1 spreads the images over host processes (large N, full depth)."""
+    jobs = [(prox, im, mask[i] if mask.ndim == 3 else mask, noises[i] if noises.ndim == 3 else noises, P)
+            for i, im in enumerate(imgs)]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(min(workers, len(jobs))) as pool:
+            out = pool.map(_oracle_one, jobs, chunksize=1)
+    else:
+        out = [_oracle_one(j) for j in jobs]
     return [np.stack([o[k] for o in out]) for k in range(4)]
 
 
@@ -114,7 +123,7 @@ def test_config2_batch64_cnc(pk, cs_inputs):
 # ---------------------------------------------------------------------------------------------
 # fp64 validation build over sizes, odd batches, per-image masks / noise
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('N', [16, 32, 64, 128, 256, 512])
+@pytest.mark.parametrize('N', [16, 32, 64, 128, 256, 512, 1024])
 @pytest.mark.parametrize('prox', ['l1', 'cnc'])
 def test_fp64_sizes(pk, N, prox):
     from pnp_admm_cnc_mri_b200 import data
@@ -125,7 +134,7 @@ def test_fp64_sizes(pk, N, prox):
     P = dict(kat.L1_DEFAULTS) if prox == 'l1' else dict(kat.CNC_DEFAULTS)
     P['iter_num'] = 12
     x, z, w, y = pk.admm_solve(imgs, m, nz, prox=prox, dtype='float64', return_state=True, **P)
-    xr, zr, wr, yr = oracle_batch(imgs, m, nz, prox, P)
+    xr, zr, wr, yr = oracle_batch(imgs, m, nz, prox, P, workers=3)
     assert rel(y, yr) < 1e-11
     assert rel(x, xr) < TOL64 and rel(z, zr) < TOL64
     assert np.abs(w - wr).max() < 1e-9
@@ -148,6 +157,45 @@ def test_fp32_sizes(pk, N, kernel, prox):
         assert rel(x[k], xr[k]) < TOL32, (N, prox, k)
         assert abs(orc.calculate_psnr(x[k].astype(np.float64) * 255, imgs[k] * 255.)
                    - orc.calculate_psnr(xr[k] * 255, imgs[k] * 255.)) < TOL_PSNR
+
+
+@pytest.mark.parametrize('N', [512, 1024])
+@pytest.mark.parametrize('prox,kind', [('cnc', 'cartesian'), ('cnc', 'radial'), ('cnc', 'random'),
+                                       ('l1', 'cartesian'), ('l1', 'radial'), ('l1', 'random')])
+def test_full_depth_large_sizes_fp32(pk, N, prox, kind):
+    """The reference depth (50 iterations, S1:171 / S4:176; BASELINE config 5) on the K2 streaming kernels at
+    N = 512 and 1024, every mask kind, odd batch (last packed plane half empty): SURVEY 7 warns that the fp32
+    headroom of CNC shrinks with depth, so the gate is checked where it is tightest."""
+    from pnp_admm_cnc_mri_b200 import data
+    B = 3
+    imgs = data.phantoms(B, N, seed0=40 + N // 512)
+    m = data.make_mask(kind, N, seed=4)
+    nz = data.make_noise(N, seed=8)
+    P = dict(kat.L1_DEFAULTS) if prox == 'l1' else dict(kat.CNC_DEFAULTS)
+    assert P['iter_num'] == 50
+    x, z, w, y = pk.admm_solve(imgs, m, nz, prox=prox, kernel='streaming', return_state=True, **P)
+    xr, zr, wr, yr = oracle_batch(imgs, m, nz, prox, P, workers=B)
+    for k in range(B):
+        e = rel(x[k], xr[k])
+        dp = abs(orc.calculate_psnr(x[k].astype(np.float64) * 255, imgs[k] * 255.) - orc.calculate_psnr(xr[k] * 255, imgs[k] * 255.))
+        print(f'N={N} {prox} {kind} image {k}: rel-L2 {e:.2e}, |dPSNR| {dp:.1e} dB')
+        assert e < TOL32, (N, prox, kind, k, e)
+        assert rel(z[k], zr[k]) < TOL32
+        assert dp < TOL_PSNR
+
+
+@pytest.mark.parametrize('prox', ['l1', 'cnc'])
+def test_full_depth_fp64_1024(pk, prox):
+    """fp64 validation build at the largest size and the reference depth: <= 1e-10 after 50 iterations."""
+    from pnp_admm_cnc_mri_b200 import data
+    N, B = 1024, 2
+    imgs = data.phantoms(B, N, seed0=60)
+    m = data.make_mask('radial', N, seed=5)
+    nz = data.make_noise(N, seed=9)
+    P = dict(kat.L1_DEFAULTS) if prox == 'l1' else dict(kat.CNC_DEFAULTS)
+    x, z, w, y = pk.admm_solve(imgs, m, nz, prox=prox, dtype='float64', return_state=True, **P)
+    xr, zr, wr, yr = oracle_batch(imgs, m, nz, prox, P, workers=B)
+    assert rel(x, xr) < TOL64 and rel(z, zr) < TOL64
 
 
 @pytest.mark.parametrize('dtype,kernel,tol', [('float64', 'auto', TOL64), ('float32', 'cluster', TOL32),

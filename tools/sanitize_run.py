@@ -1,0 +1,44 @@
+"""Small solves for compute-sanitizer (tools/sanitize.sh): one K1 solve with the chunked schedule, one hybrid
+K1 + K2 solve, one K2 solve at N = 512, each checked against the oracle so a sanitizer-induced timing change
+that exposed a protocol bug would also show up as a wrong answer."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pnp_admm_cnc_mri_b200 as pk                      # noqa: E402
+from pnp_admm_cnc_mri_b200 import data                  # noqa: E402
+from oracle import reference_numpy as orc               # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+P = dict(alpha=0.45, iter_num=6, lambda1=0.5, reo=0.05, b=64)
+
+
+def check(x, imgs, m, nz, tag, n_check=2):
+    for k in range(n_check):
+        xr = orc.admm_cnc(imgs[k], m.astype(np.float64), nz, **P)
+        e = np.linalg.norm(x[k] - xr) / np.linalg.norm(xr)
+        assert e < 1e-4, (tag, k, e)
+    print(tag, 'ok', flush=True)
+
+
+N = 256
+m = data.make_mask('random', N, seed=0)
+nz = data.make_noise(N, seed=3)
+if which in ('all', 'k1'):
+    os.environ['PNPADMM_K1_CHUNKS'] = '3'               # plane state handed between clusters through L2
+    imgs = data.phantoms(5, N, seed0=1)
+    check(pk.admm_solve(imgs, m, nz, prox='cnc', kernel='cluster', **P), imgs, m, nz, 'K1 chunked B=5')
+    del os.environ['PNPADMM_K1_CHUNKS']
+if which in ('all', 'hybrid'):
+    os.environ['PNPADMM_HYBRID_P2'] = '2'
+    B = 2 * (int(os.environ.get('SAN_NCL', '14')) + 3)  # more planes than resident clusters, so the split is live
+    imgs = np.concatenate([data.phantoms(4, N, seed0=1)] * (B // 4 + 1))[:B]
+    check(pk.admm_solve(imgs, m, nz, prox='cnc', kernel='auto', **P), imgs, m, nz, f'hybrid B={B}')
+if which in ('all', 'k2'):
+    N2 = 512
+    m2 = data.make_mask('radial', N2, seed=1)
+    nz2 = data.make_noise(N2, seed=4)
+    imgs = data.phantoms(3, N2, seed0=2)
+    check(pk.admm_solve(imgs, m2, nz2, prox='cnc', kernel='streaming', **P), imgs, m2, nz2, 'K2 N=512 B=3', 1)
