@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PNPADMM_ABI_VERSION 1
+#define PNPADMM_ABI_VERSION 2
 
 #define PNPADMM_OK                 0
 #define PNPADMM_ERR_BAD_ARG       -1   /* NULL pointer, B <= 0, iters < 0, unknown enum ...          */
@@ -61,6 +61,13 @@ const char* pnpadmm_last_error_string(void);
 /* sm_count, max co-resident 8-CTA clusters of the N=256 kernel (0 if it cannot launch),
  * compute capability.  Any out pointer may be NULL. */
 int pnpadmm_device_info(int* sm_count, int* max_clusters_256, int* cc_major, int* cc_minor);
+
+/* How a reconstruction of (B, N, iters) is scheduled on the current device and how many kernels it launches
+ * (introspection for benchmarks; nothing is enqueued): packed planes given to the cluster kernel and to the
+ * streaming kernels (hybrid schedule at N == 256), chunks of the cluster schedule, kernel launches of one
+ * pnpadmm_acquire_f32 and of one pnpadmm_solve_f32.  Any out pointer may be NULL. */
+int pnpadmm_plan_info(int B, int N, int mask_batched, int iters, int kernel, int* planes_cluster,
+                      int* planes_streaming, int* chunks, int* launches_acquire, int* launches_solve);
 
 /* Bytes of device workspace needed by every call below for (B, N, precision, mask layout). */
 size_t pnpadmm_workspace_bytes(int B, int N, int is_f64, int mask_batched);
@@ -153,20 +160,28 @@ int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, co
                                  void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
 
 /* Pipelined form of the same call for back-to-back batches: the H2D copies run on `h2d`, the kernels
- * on `compute`, the D2H copy on `d2h` (three distinct streams), with two device slots so that the
- * copies of batch i-1 / i+1 overlap the kernels of batch i.  Alternate slot = 0, 1, 0, ... between
- * calls; ordering between the streams uses library-owned events (created once per device).  Returns
- * after everything is enqueued; pnpadmm_reconstruct_host_wait(slot) blocks the host until the h_x
- * passed with that slot has been written.  The host buffers of a slot must stay untouched until then.
- * d_scratch: pnpadmm_host_pipeline_scratch_bytes(B, N) bytes. */
-size_t pnpadmm_host_pipeline_scratch_bytes(int B, int N);
-int pnpadmm_reconstruct_host_pipelined_f32(const uint8_t* h_img, const uint8_t* h_mask, const float* h_noise,
+ * on `compute`, the D2H copy on `d2h` (three distinct streams), with n_slots (2..4) device slots so that the
+ * copies of neighbouring batches overlap the kernels of batch i.  Rotate slot = 0, 1, .., n_slots-1, 0, ..
+ * between calls.  The ordering events live in a CALLER-OWNED pipeline object (created once, outside the hot
+ * loop), so several pipelines - other host threads, other stream / scratch sets - can share a device; calls on
+ * one pipeline object are serialised by the library.  From the second batch on the compute section of a slot
+ * (uint8 -> unit scale, acquisition, zero-fill, prepare, iterations) is replayed as ONE CUDA-graph launch.
+ * Returns after everything is enqueued; pnpadmm_reconstruct_host_wait(pipe, slot) blocks the host until the
+ * h_x passed with that slot has been written.  The host buffers of a slot must stay untouched until then.
+ * d_scratch: pnpadmm_host_pipeline_scratch_bytes(B, N, n_slots) bytes, one per pipeline. */
+#define PNPADMM_PIPELINE_MAX_SLOTS 4
+typedef struct pnpadmm_pipeline_s* pnpadmm_pipeline_t;
+int pnpadmm_pipeline_create(pnpadmm_pipeline_t* out, int n_slots);     /* on the current device */
+int pnpadmm_pipeline_destroy(pnpadmm_pipeline_t pipe);                 /* after the streams have drained */
+size_t pnpadmm_host_pipeline_scratch_bytes(int B, int N, int n_slots);
+int pnpadmm_reconstruct_host_pipelined_f32(pnpadmm_pipeline_t pipe,
+                                           const uint8_t* h_img, const uint8_t* h_mask, const float* h_noise,
                                            float* h_x, int B, int N,
                                            int prox, int iters, double lambda1, double reo, double alpha, double b,
                                            int kernel, void* d_scratch, size_t scratch_bytes,
                                            void* ws, size_t ws_bytes, int slot,
                                            pnpadmm_stream_t compute, pnpadmm_stream_t h2d, pnpadmm_stream_t d2h);
-int pnpadmm_reconstruct_host_wait(int slot);
+int pnpadmm_reconstruct_host_wait(pnpadmm_pipeline_t pipe, int slot);
 
 /* ---------------------------------------------------------------------------------------
  * Pointwise pieces used by the PnP variants (denoiser runs outside this library).

@@ -101,10 +101,15 @@ def main():
                 continue
             o, _ = g['PNP_ADMM_CNC_D'](nm, g['mask'][0], g['noises'], **g['PNP_ADMM_CNC_D_opts'][m])
             res[nm] = (np.asarray(o[0]).copy(), dict(g['PNP_ADMM_CNC_D_opts'][m]))
+        # the driver keeps only out2[0] of the DnCNN pair (S6:618): call the unmodified function again for all three images
+        o2, _ = g['PNP_ADMM_CNC_DnCNN'](g['name1'][1], g['name1'][0], g['mask'][0], g['noises'], **g['PNP_ADMM_CNC_DnCNN_opts'])
+        res['_dncnn_pair'] = ([np.asarray(a).copy() for a in o2[:3]], np.asarray(g['out2']).copy())
         return res
     g6 = rr.run_script('【6】', images=paths3, model_zoo=zoo, post=post6)
     out['cnc_drunet'] = np.stack([np.asarray(g6['out'][order.index(n)]) for n in IMAGES3]).astype(np.float32)
-    out['cnc_dncnn'] = np.stack([np.asarray(g6['out2'][order.index(n)]) for n in IMAGES3]).astype(np.float32)
+    pair3, pair_first = g6['_post'].pop('_dncnn_pair')
+    assert np.array_equal(pair3[0], pair_first)                # same function, same inputs: deterministic
+    out['cnc_dncnn'] = np.stack([pair3[order.index(n)] for n in IMAGES3]).astype(np.float32)
     print(f'[S6] driver done, {time.time() - t0:.0f} s', flush=True)
     P4 = dict(alpha=1, iter_num=50, lambda1=0.8, reo=0.8, b=0.45)        # S6:577
     P2 = dict(alpha=1.2, iter_num=50, lambda1=4, reo=0.45, b=0.3)        # S6:571

@@ -12,15 +12,16 @@ LIB_PATH = os.path.join(PKG, 'libpnpadmm.so')
 OK, ERR_BAD_ARG, ERR_BAD_SIZE, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 PROX_L1, PROX_CNC = 0, 1
 KERNEL_AUTO, KERNEL_CLUSTER, KERNEL_STREAMING = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/pnpadmm.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    'pnpadmm_abi_version', 'pnpadmm_last_error_string', 'pnpadmm_device_info', 'pnpadmm_workspace_bytes',
+    'pnpadmm_abi_version', 'pnpadmm_last_error_string', 'pnpadmm_device_info', 'pnpadmm_plan_info', 'pnpadmm_workspace_bytes',
     'pnpadmm_acquire_f32', 'pnpadmm_acquire_f64', 'pnpadmm_zero_filled_f32', 'pnpadmm_zero_filled_f64',
     'pnpadmm_prepare_f32', 'pnpadmm_prepare_f64', 'pnpadmm_xupdate_f32', 'pnpadmm_xupdate_f64',
     'pnpadmm_iterate_f32', 'pnpadmm_iterate_f64', 'pnpadmm_solve_f32', 'pnpadmm_solve_f64',
     'pnpadmm_host_scratch_bytes', 'pnpadmm_reconstruct_host_f32',
+    'pnpadmm_pipeline_create', 'pnpadmm_pipeline_destroy',
     'pnpadmm_host_pipeline_scratch_bytes', 'pnpadmm_reconstruct_host_pipelined_f32', 'pnpadmm_reconstruct_host_wait',
     'pnpadmm_soft_f32', 'pnpadmm_soft_f64', 'pnpadmm_cnc_combine_f32', 'pnpadmm_cnc_combine_f64',
     'pnpadmm_dual_update_f32', 'pnpadmm_dual_update_f64', 'pnpadmm_measure_fp32_peak',
@@ -52,6 +53,8 @@ def load() -> ctypes.CDLL:
     lib.pnpadmm_last_error_string.argtypes = []
     lib.pnpadmm_device_info.restype = i
     lib.pnpadmm_device_info.argtypes = [POINTER(c_int)] * 4
+    lib.pnpadmm_plan_info.restype = i
+    lib.pnpadmm_plan_info.argtypes = [i, i, i, i, i] + [POINTER(c_int)] * 5
     lib.pnpadmm_workspace_bytes.restype = z
     lib.pnpadmm_workspace_bytes.argtypes = [i, i, i, i]
     lib.pnpadmm_host_scratch_bytes.restype = z
@@ -83,11 +86,15 @@ def load() -> ctypes.CDLL:
         f = getattr(lib, 'pnpadmm_metrics_' + sfx); f.restype = i
         f.argtypes = [p, p, i, i, i, p, p, z, p]
     lib.pnpadmm_host_pipeline_scratch_bytes.restype = z
-    lib.pnpadmm_host_pipeline_scratch_bytes.argtypes = [i, i]
+    lib.pnpadmm_host_pipeline_scratch_bytes.argtypes = [i, i, i]
+    lib.pnpadmm_pipeline_create.restype = i
+    lib.pnpadmm_pipeline_create.argtypes = [POINTER(c_void_p), i]
+    lib.pnpadmm_pipeline_destroy.restype = i
+    lib.pnpadmm_pipeline_destroy.argtypes = [p]
     lib.pnpadmm_reconstruct_host_pipelined_f32.restype = i
-    lib.pnpadmm_reconstruct_host_pipelined_f32.argtypes = [p, p, p, p, i, i, i, i, d, d, d, d, i, p, z, p, z, i, p, p, p]
+    lib.pnpadmm_reconstruct_host_pipelined_f32.argtypes = [p, p, p, p, p, i, i, i, i, d, d, d, d, i, p, z, p, z, i, p, p, p]
     lib.pnpadmm_reconstruct_host_wait.restype = i
-    lib.pnpadmm_reconstruct_host_wait.argtypes = [i]
+    lib.pnpadmm_reconstruct_host_wait.argtypes = [p, i]
     lib.pnpadmm_measure_fp32_peak.restype = i
     lib.pnpadmm_measure_fp32_peak.argtypes = [POINTER(c_double), p]
     lib.pnpadmm_dncnn_activation_bytes.restype = z

@@ -66,6 +66,22 @@ PNP_D void mbar_wait(uint32_t bar, uint32_t parity) {
         if ((++spins & 63u) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// Poll `spin` times before going to sleep: a sleeping warp frees its issue slots for the other CTA of the SM but pays the
+// hardware's wake-up latency on the critical path of the iteration (experiment knob PNPADMM_K1_SPIN).
+PNP_D void mbar_wait_spin(uint32_t bar, uint32_t parity, int spin) {
+    for (int i = 0; i < spin; ++i) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    mbar_wait(bar, parity);
+}
 PNP_D int ld_acquire_gpu(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -87,6 +103,52 @@ struct RemoteAsync {
                      : "memory");
     }
 };
+
+// Transposes with rotated destinations: CTA `rank` starts its 16 remote stores at peer 4 (rank % 4) instead of peer 0, so the
+// 16 CTAs of a cluster do not all address the same destination at the same time (experiment knob PNPADMM_K1_ROT).
+template <int OFF, int CL, class Remote>
+PNP_D void row_store_remote_off(const Ctx<CL>& c, const ThreadState& s, const Remote& R) {
+    typedef Geo<CL> G;
+    const int t = c.rt();
+    const int grow = G::kRows * c.rank + c.row();
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        constexpr int dummy = 0; (void)dummy;
+        const int j = (jj + OFF) & 15;
+        const int off = G::kOffB2 + (grow * G::kRows + G::local(t, j)) * 8;
+        R.st(G::dest(j), off, s.a[j], BAR_FULL2);
+    }
+}
+template <int OFF, int CL, class Remote>
+PNP_D void col_store_remote_off(const Ctx<CL>& c, const ThreadState& s, const Remote& R) {
+    typedef Geo<CL> G;
+    const int t = c.ct();
+    const int kc = G::kRows * c.rank + c.cc();
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        const int j = (jj + OFF) & 15;
+        const int off = G::kOffB1 + (G::local(t, j) * kN + kc) * 8;
+        R.st(G::dest(j), off, s.a[j], BAR_FULL1);
+    }
+}
+template <int CL, class Remote>
+PNP_D void row_store_remote_rot(const Ctx<CL>& c, const ThreadState& s, const Remote& R) {
+    switch (c.rank & 3) {
+        case 0: row_store_remote_off<0>(c, s, R); break;
+        case 1: row_store_remote_off<4>(c, s, R); break;
+        case 2: row_store_remote_off<8>(c, s, R); break;
+        default: row_store_remote_off<12>(c, s, R); break;
+    }
+}
+template <int CL, class Remote>
+PNP_D void col_store_remote_rot(const Ctx<CL>& c, const ThreadState& s, const Remote& R) {
+    switch (c.rank & 3) {
+        case 0: col_store_remote_off<0>(c, s, R); break;
+        case 1: col_store_remote_off<4>(c, s, R); break;
+        case 2: col_store_remote_off<8>(c, s, R); break;
+        default: col_store_remote_off<12>(c, s, R); break;
+    }
+}
 
 struct ClusterParams {
     int B;                 // images
@@ -111,6 +173,8 @@ struct ClusterParams {
     int* progress;         // [P][16], zeroed before the launch
     int* queue;            // next unclaimed task, zeroed before the launch
     int dbg;               // timing experiments only (results invalid): 1 = no transposes, 2 = no G staging
+    int rot;               // rotate the transpose destinations per rank (PNPADMM_K1_ROT, default 0)
+    int spin;              // polls of a tile barrier before the waiting warp goes to sleep (PNPADMM_K1_SPIN, default 0)
 };
 
 // mcode [N][N] bytes -> packed words (one word per column-phase thread and iteration)
@@ -144,7 +208,6 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
         mbar_init(bFree1, kCluster);                        // one arrival per CTA
         mbar_init(bFree2, kCluster * G::kWarps);      // one arrival per warp of every CTA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_arm_tx(bFull1, kTileBytes); mbar_arm_tx(bFull2, kTileBytes); mbar_arm_tx(bG, kTileBytes);
     }
     RemoteAsync<CL> R;
     R.init(smem);
@@ -234,14 +297,17 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
         row_read_step2<false>(c, s);
         prefetch_g();
         wait_free2();
-        if (!(dbg & 1)) row_store_remote(c, s, R);
+        if (!(dbg & 1)) { if (p.rot) row_store_remote_rot(c, s, R); else row_store_remote(c, s, R); }
 
         for (int it = it0; it < it1; ++it) {
             // ---- column phase: col FFT -> residual blend -> col IFFT -> transpose back (DSMEM)
             const uint32_t codes = mpack[c.ct() * kN + kRows * c.rank + c.cc()];
+            // A tile barrier has one pending arrival: thread 0's expect_tx, made right before the wait, so a phase
+            // cannot complete early (bytes landing first only drive the tx-count negative) and no arrival is left
+            // without a wait when the kernel exits (compute-sanitizer synccheck).
             if (!(dbg & 1)) {
-                mbar_wait(bFull2, nFull2 & 1); ++nFull2;
                 if (threadIdx.x == 0) mbar_arm_tx(bFull2, kTileBytes);
+                mbar_wait_spin(bFull2, nFull2 & 1, p.spin); ++nFull2;
             }
             col_load(c, s);
             __syncthreads();
@@ -249,8 +315,8 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
             __syncthreads();
             col_read_step2<false>(c, s);
             if (!(dbg & 2)) {
-                mbar_wait(bG, nG & 1); ++nG;
                 if (threadIdx.x == 0) mbar_arm_tx(bG, kTileBytes);
+                mbar_wait(bG, nG & 1); ++nG;
             }
             col_blend(c, s, c.B1(), codes, cf1, cf2);
             fence_proxy_async();
@@ -264,14 +330,14 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
             if (!(dbg & 1)) {
                 if (lane < kCluster) mbar_arrive_remote(mapa(bFree2, lane));   // this warp no longer reads B2
                 mbar_wait(bFree1, nFree1 & 1); ++nFree1;
-                col_store_remote(c, s, R);
+                if (p.rot) col_store_remote_rot(c, s, R); else col_store_remote(c, s, R);
             }
 
             // ---- row phase: row IFFT -> |v + r| -> prox -> dual -> row FFT -> transpose (DSMEM)
             const bool last = (it == it1 - 1);
             if (!(dbg & 1)) {
-                mbar_wait(bFull1, nFull1 & 1); ++nFull1;
                 if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
+                mbar_wait_spin(bFull1, nFull1 & 1, p.spin); ++nFull1;
             }
             row_load(c, s);
             __syncwarp();
@@ -286,7 +352,7 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
                 row_read_step2<false>(c, s);
                 prefetch_g();
                 wait_free2();
-                if (!(dbg & 1)) row_store_remote(c, s, R);
+                if (!(dbg & 1)) { if (p.rot) row_store_remote_rot(c, s, R); else row_store_remote(c, s, R); }
             }
         }
         if (!final_chunk) {   // publish this rank's rows of z, w for the cluster that continues the plane
@@ -298,6 +364,181 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
         }
     }
     cluster_sync_all();   // no CTA exits while a peer could still signal one of its barriers
+}
+
+
+// =============================================================================================
+// Blocked-tile variant of K1 (16-CTA clusters): the two transposes of an iteration leave each CTA as 16 bulk copies of
+// 2 KB (cp.async.bulk shared::cta -> shared::cluster, completion counted in bytes on the destination's FULL barrier)
+// issued by one warp, instead of 16 st.async per thread through the LSU.  The LSU / MIO queue then carries only the
+// local exchanges, so the second CTA of the SM keeps computing while this one's tile is on the SM-to-SM network.
+//   * staging: the outgoing tile is first written to this CTA's own B1 (row phase) / B2 (column phase) as
+//     [dest][256 entries] (cluster256_core.cuh), contiguous 8-byte stores, then fence.proxy.async + CTA barrier.
+//   * a bulk copy out of shared memory has no completion the SENDER could wait on, so buffer reuse is ordered by two
+//     arrival barriers that say "all 16 CTAs of the cluster have RECEIVED their whole tile":  RCV2 (each CTA arrives
+//     at every peer after its own FULL2 wait) means every row->column copy has landed, hence every B1 staging buffer
+//     has been read and every CTA has left its row phase: B1 tiles may be overwritten by the column->row copies.
+//     RCV1 likewise (after FULL1) frees the B2 tiles for the next row->column copies.
+//   * the data term G of the blend is read from L2 (tile-ordered copy, 256 contiguous bytes per warp and j); B1 cannot
+//     stage it any more (it holds the outgoing tile until RCV2).
+// =============================================================================================
+enum { BK_FULL1 = 0, BK_FULL2 = 1, BK_RCV1 = 2, BK_RCV2 = 3 };
+
+__global__ void __launch_bounds__(Geo<16>::kThreads, 2) cluster256_bk_kernel(const ClusterParams p) {
+    typedef Geo<16> G;
+    constexpr int kCluster = 16, kTileBytes = G::kTileBytes;
+    extern __shared__ __align__(128) unsigned char smem[];
+    Ctx<16> c;
+    c.rank = (int)cluster_ctarank();
+    c.tid = threadIdx.x;
+    c.smem = smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t bar0 = smem0 + G::kOffBar;
+    const uint32_t bFull1 = bar0 + 8 * BK_FULL1, bFull2 = bar0 + 8 * BK_FULL2;
+    const uint32_t bRcv1 = bar0 + 8 * BK_RCV1, bRcv2 = bar0 + 8 * BK_RCV2;
+
+    fill_tw(reinterpret_cast<cf32*>(smem + G::kOffTW), reinterpret_cast<const cf32*>(g_tw_f32), threadIdx.x);
+    if (threadIdx.x == 0) {
+        mbar_init(bFull1, 1); mbar_init(bFull2, 1);
+        mbar_init(bRcv1, kCluster); mbar_init(bRcv2, kCluster);      // one arrival per CTA of the cluster
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();   // all CTAs resident, all barriers initialised, before any DSMEM traffic
+
+    const float cf1 = p.cf[1], cf2 = p.cf[2];
+    uint32_t nFull1 = 0, nFull2 = 0;   // completed waits = phases of FULL1 / FULL2 and of RCV1 / RCV2
+    ThreadState s;
+    const size_t nn = (size_t)kN * kN;
+    const int mode = (p.prox.prox == PROX_NONE) ? PROX_NONE : prox_mode(p.prox);
+    const int ntasks = p.P * p.n_chunks;
+    const uint32_t sTask = bar0 + 48;
+    const uint32_t sTask0 = mapa(sTask, 0);
+
+    // warp 0 sends the staged tile: lane j copies block j (2 KB) into peer j, at this CTA's block, and signals `bar` there
+    auto send_tile = [&](int off_src, int off_dst, int bar) {
+        if (warp == 0 && lane < kCluster) {
+            const int dst = (lane + c.rank) & 15;          // every CTA starts with a different peer: no hot destination
+            const uint32_t peer = mapa(smem0, dst);
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             peer + (uint32_t)(off_dst + 2048 * c.rank)),
+                         "r"(smem0 + (uint32_t)(off_src + 2048 * dst)), "r"(2048), "r"(peer + (uint32_t)(G::kOffBar + 8 * bar))
+                         : "memory");
+        }
+    };
+    auto announce = [&](uint32_t bar_local) {      // "this CTA has received its tile" -> every peer
+        if (warp == 0 && lane < kCluster) mbar_arrive_remote(mapa(bar_local, lane));
+    };
+
+    for (;;) {
+        if (c.rank == 0 && threadIdx.x == 0) {
+            const int t = atomicAdd(p.queue, 1);
+            asm volatile("st.shared.s32 [%0], %1;" ::"r"(sTask), "r"(t) : "memory");
+        }
+        cluster_sync_all();
+        int task;
+        asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(task) : "r"(sTask0) : "memory");
+        cluster_sync_all();
+        if (task >= ntasks) break;
+        const int plane = task % p.P, chunk = task / p.P;
+        const int it0 = chunk * p.chunk;
+        const int it1 = (it0 + p.chunk < p.iters) ? it0 + p.chunk : p.iters;
+        const bool final_chunk = (it1 == p.iters);
+        const int ia = p.solo ? plane : 2 * plane;
+        const bool has_b = !p.solo && (2 * plane + 1 < p.B);
+        PlaneIO io;
+        const float* zsrc = (chunk == 0) ? p.z_in : p.z;
+        const float* wsrc = (chunk == 0) ? p.w_in : p.w;
+        io.z_in_a = zsrc + ia * nn; io.w_in_a = wsrc + ia * nn;
+        io.z_in_b = has_b ? io.z_in_a + nn : nullptr; io.w_in_b = has_b ? io.w_in_a + nn : nullptr;
+        io.x_a = p.x + ia * nn; io.z_a = p.z ? p.z + ia * nn : nullptr; io.w_a = p.w ? p.w + ia * nn : nullptr;
+        io.xpw_a = p.xpw ? p.xpw + ia * nn : nullptr;
+        io.x_b = io.x_a + nn; io.z_b = io.z_a ? io.z_a + nn : nullptr; io.w_b = io.w_a ? io.w_a + nn : nullptr;
+        io.xpw_b = io.xpw_a ? io.xpw_a + nn : nullptr;
+        if (chunk > 0) {
+            if (threadIdx.x == 0) {
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(p.progress + plane * 16 + c.rank) < chunk)
+                    if (++spins > (1u << 26)) __trap();
+            }
+            __syncthreads();
+        }
+        const cf32* Gtile = p.G + plane * nn + (size_t)c.rank * (kTileBytes / 8);
+        const uint32_t* mpack = p.mpack + (p.mcode_batched ? (size_t)plane * 16 * kN : 0);
+
+        // row -> column transpose of the tile in registers: stage in B1, then 16 bulk copies into the peers' B2
+        auto send_rows = [&]() {
+            __syncwarp();                  // the half-warps are done reading the scratch (= their staging slots)
+            row_stage_bk(c, s);
+            fence_proxy_async();           // generic-proxy stores -> visible to the bulk copies (async proxy)
+            __syncthreads();
+            if (warp == 0) {
+                if (nFull1 > 0) mbar_wait(bRcv1, (nFull1 - 1) & 1);   // every B2 tile has been consumed and re-read
+                send_tile(G::kOffB1, G::kOffB2, BK_FULL2);
+            }
+        };
+
+        // ---- prologue: first forward row FFT of z - w
+        row_load_state(c, s, io);
+        row_step1_write_bk<false>(c, s);
+        __syncwarp();
+        row_read_step2_bk<false>(c, s);
+        send_rows();
+
+        for (int it = it0; it < it1; ++it) {
+            // ---- column phase: col FFT -> residual blend -> col IFFT -> transpose back
+            const uint32_t codes = mpack[c.ct() * kN + 16 * c.rank + c.cc()];
+            if (threadIdx.x == 0) mbar_arm_tx(bFull2, kTileBytes);   // the one pending arrival, right before the wait
+            mbar_wait_spin(bFull2, nFull2 & 1, p.spin); ++nFull2;
+            announce(bRcv2);
+            col_load(c, s);
+            __syncthreads();
+            col_step1_write<false>(c, s);
+            __syncthreads();
+            col_read_step2<false>(c, s);
+            col_blend_g(c, s, Gtile, codes, cf1, cf2);
+            __syncthreads();                               // scratch reads done
+            col_step1_write<true>(c, s);
+            __syncthreads();
+            col_read_step2<true>(c, s);
+            __syncthreads();                               // scratch reads done: B2 becomes the staging buffer
+            col_stage_bk(c, s);
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) {
+                mbar_wait(bRcv2, (nFull2 - 1) & 1);         // every CTA has left its row phase, every B1 staging was read
+                send_tile(G::kOffB2, G::kOffB1, BK_FULL1);
+            }
+
+            // ---- row phase: row IFFT -> |v + r| -> prox -> dual -> row FFT -> transpose
+            const bool last = (it == it1 - 1);
+            if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
+            mbar_wait_spin(bFull1, nFull1 & 1, p.spin); ++nFull1;
+            announce(bRcv1);
+            row_load_bk(c, s);
+            __syncwarp();
+            row_step1_write_bk<true>(c, s);
+            __syncwarp();
+            row_read_step2_bk<true>(c, s);
+            row_prox_dispatch(mode, c, s, p.prox, has_b, last, final_chunk, io);
+            if (!last) {
+                __syncwarp();
+                row_step1_write_bk<false>(c, s);
+                __syncwarp();
+                row_read_step2_bk<false>(c, s);
+                send_rows();
+            }
+        }
+        if (!final_chunk) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                st_release_gpu(p.progress + plane * 16 + c.rank, chunk + 1);
+            }
+        }
+    }
+    cluster_sync_all();
 }
 
 }  // namespace k1

@@ -336,6 +336,74 @@ PNP_HD void col_store_remote(const Ctx<CL>& c, const ThreadState& s, const Remot
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Blocked-tile variant (CL = 16 only): both transposes leave a CTA as 16 contiguous 2 KB blocks, one per peer, so they
+// can be sent with the TMA engine (cp.async.bulk shared::cta -> shared::cluster) instead of 4096 8-byte remote stores
+// through the LSU.  Every tile is addressed as [peer 16][256 entries]:
+//   B2  [src rank s][row r][col c]   = element (image row 16 s + r, column-of-this-CTA c)   (same bytes as [256][16])
+//   B1  [src rank s][row r][col c]   = element (row-of-this-CTA r, frequency column 16 s + c)
+//   outgoing staging (in B1 at the end of a row phase, in B2 at the end of a column phase): [dest j][tid]
+// With tid = 16 row + t (row phases) = 16 t + c (column phases) every access below is `base + 256 j + tid`: a warp
+// touches 256 contiguous bytes.  A warp's row-FFT scratch is its own 16 input chunks (256 B in each peer block).
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+PNP_D cf32 ld_g(const cf32* p) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return mk<float>(v.x, v.y); }
+#else
+inline cf32 ld_g(const cf32* p) { return *p; }
+#endif
+
+PNP_HD void row_load_bk(const Ctx<16>& c, ThreadState& s) {
+    const cf32* src = c.B1() + c.tid;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s.a[j] = src[256 * j];
+}
+
+// scratch slot of row-local index k (0..255) for the half-warp of `tid`: chunk k / 16, entry (tid & ~15) + k % 16
+template <bool INV>
+PNP_HD void row_step1_write_bk(const Ctx<16>& c, ThreadState& s) {
+    const int t = c.rt();
+    fft256_step1<INV>(s.a, t, c.TW());
+    cf32* sc = c.B1() + (c.tid & ~15);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) sc[k1 * 256 + (t ^ k1)] = s.a[k1];
+}
+
+template <bool INV>
+PNP_HD void row_read_step2_bk(const Ctx<16>& c, ThreadState& s) {
+    const int t = c.rt();
+    const cf32* sc = c.B1() + t * 256 + (c.tid & ~15);
+    cf32 v[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = sc[n2 ^ t];
+    fft256_step2<INV>(v, s.a);
+}
+
+// forward row FFT output X[row][k = t + 16 j] -> staging block of peer j (lands in its B2 at block `rank`)
+PNP_HD void row_stage_bk(const Ctx<16>& c, const ThreadState& s) {
+    cf32* st = c.B1() + c.tid;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) st[256 * j] = s.a[j];
+}
+
+// inverse column FFT output at image row t + 16 j -> staging block of peer j (lands in its B1 at block `rank`)
+PNP_HD void col_stage_bk(const Ctx<16>& c, const ThreadState& s) {
+    cf32* st = c.B2() + c.tid;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) st[256 * j] = s.a[j];
+}
+
+// the blend with the data term read straight from the tile-ordered global copy Gt (this CTA's 32 KB block)
+PNP_HD void col_blend_g(const Ctx<16>& c, ThreadState& s, const cf32* Gtile, uint32_t codes, float cf1, float cf2) {
+    const cf32* g = Gtile + c.tid;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const cf32 gg = ld_g(g + 256 * j);
+        const uint32_t code = (codes >> (2 * j)) & 3u;
+        const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
+        s.a[j] = mk<float>(gg.re - cf * s.a[j].re, gg.im - cf * s.a[j].im);
+    }
+}
+
 // TW[k1*16 + n2] = W_256^(k1*n2) from the master table W_4096^m
 PNP_HD void fill_tw(cf32* TW, const cf32* master4096, int i) {
     const int k1 = i >> 4, n2 = i & 15;

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "../../include/pnpadmm.h"
@@ -225,6 +226,11 @@ int probe_clusters(int sm_count) {
         (void)cudaGetLastError();
         return 0;
     }
+    if (CL == 16 && (cudaFuncSetAttribute(k1::cluster256_bk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes) != cudaSuccess ||
+                     cudaFuncSetAttribute(k1::cluster256_bk_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+        (void)cudaGetLastError();
+        return 0;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(CL * sm_count);
@@ -276,6 +282,8 @@ int ensure_device(DeviceState** out) {
         CUDA_TRY(set_stream_attrs<float>());
         CUDA_TRY(set_stream_attrs<double>());
         CUDA_TRY(S2<float>::set_attrs());
+        CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(tc::conv64_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(tc::conv64_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         d.max_cl8 = probe_clusters<8>(d.sm_count);
@@ -513,6 +521,13 @@ void plan_chunks(int P, int iters, int max_clusters, int* chunk, int* n_chunks) 
     }
 }
 
+// 16-CTA geometry: transposes as bulk copies through the TMA engine (cluster256_bk_kernel); PNPADMM_K1_BULK=0 selects the
+// st.async kernel for A/B runs.
+bool k1_bulk_enabled() {
+    static const bool on = [] { const char* e = getenv("PNPADMM_K1_BULK"); return e ? atoi(e) != 0 : false; }();
+    return on;
+}
+
 template <int CL>
 int launch_cluster_t(k1::ClusterParams& cp, int max_clusters, cudaStream_t st) {
     typedef k1::Geo<CL> G;
@@ -545,6 +560,10 @@ int launch_cluster_t(k1::ClusterParams& cp, int max_clusters, cudaStream_t st) {
         cfg.numAttrs = 2;
     }
     if (const char* e = getenv("PNPADMM_K1_STAGGER")) cp.dbg = atoi(e) << 8;   // experiments: start delay of odd clusters (us)
+    if (CL == 16 && k1_bulk_enabled()) {
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_bk_kernel, (const k1::ClusterParams)cp));
+        return PNPADMM_OK;
+    }
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_kernel<CL>, (const k1::ClusterParams)cp));
     return PNPADMM_OK;
 }
@@ -572,6 +591,10 @@ template <> struct ClusterDispatch<float> {
         cp.prox = pp;
         const char* dbg = getenv("PNPADMM_K1_DEBUG");   // timing experiments only
         cp.dbg = dbg ? atoi(dbg) : 0;
+        static const int spin = [] { const char* e = getenv("PNPADMM_K1_SPIN"); return e ? atoi(e) : 0; }();
+        cp.spin = spin;
+        static const int rot = [] { const char* e = getenv("PNPADMM_K1_ROT"); return e ? atoi(e) : 0; }();
+        cp.rot = rot;
         return launch_cluster(cp, d, st);
     }
 };
@@ -594,7 +617,7 @@ int stream2_launch_sequence(const StreamParams<T>& p0, int planes, const uint32_
 // The sequence is 2 * iters + 1 launches with fixed arguments: it is captured into a CUDA graph (small per-device
 // cache keyed by every kernel argument) and replayed with one launch, so a caller that reconstructs batch after
 // batch through the same buffers spends ~10 us of host time per call instead of ~0.4 ms.  A key is only captured
-// the SECOND time it is seen in a row (callers that allocate fresh x, z, w per call would otherwise pay a capture
+// the SECOND time it is seen (among the last 8 distinct keys; callers that allocate fresh x, z, w per call would otherwise pay a capture
 // + instantiation per call and thrash the cache).  Skipped when the caller is itself capturing the stream, or with
 // PNPADMM_NO_GRAPH=1.  The cache is guarded by the device's own mutex (DeviceState::mu), not the global one.
 struct K2GraphKey {
@@ -610,10 +633,11 @@ struct K2GraphEntry {
     unsigned long long stamp = 0;
 };
 constexpr int kGraphSlots = 6;
+constexpr int kMissRing = 8;
 struct K2GraphCache {
     K2GraphEntry slot[kGraphSlots];
-    K2GraphKey last_miss;
-    bool have_miss = false;
+    K2GraphKey seen[kMissRing];      // keys launched directly so far (ring): a key found here is captured
+    int n_seen = 0, next_seen = 0;
     unsigned long long clock = 0;
 };
 K2GraphCache g_k2graphs[kMaxDevices];
@@ -655,11 +679,14 @@ int stream2_replay<float>(const StreamParams<float>& p, int planes, const uint32
         if (!victim || (victim->valid && (!e.valid || e.stamp < victim->stamp))) victim = &e;
     }
     if (!slot) {
-        if (!c.have_miss || memcmp(&c.last_miss, &key, sizeof(key)) != 0) {   // first sighting: launch directly, remember it
-            memcpy(&c.last_miss, &key, sizeof(key)); c.have_miss = true;
+        bool seen = false;
+        for (int i = 0; i < c.n_seen && !seen; ++i) seen = memcmp(&c.seen[i], &key, sizeof(key)) == 0;
+        if (!seen) {   // first sighting: launch directly, remember it (a caller cycling through a few buffer sets still hits)
+            memcpy(&c.seen[c.next_seen], &key, sizeof(key));
+            c.next_seen = (c.next_seen + 1) % kMissRing;
+            if (c.n_seen < kMissRing) ++c.n_seen;
             return stream2_launch_sequence<float>(p, planes, mpack, iters, sms, st);
         }
-        c.have_miss = false;
         slot = victim;
         if (slot->valid) {   // evict before the capture starts (graph destruction is not a capture-safe call)
             (void)cudaGraphExecDestroy(slot->exec);
@@ -876,13 +903,6 @@ int metrics_impl(const T* x, const uint8_t* ref, int B, int N, int quantize, dou
     if (!scratch || scratch_bytes < sizeof(MetricsAcc) * (size_t)B || ((uintptr_t)scratch & 15))
         return fail(PNPADMM_ERR_WORKSPACE, "metrics: scratch must be 16-byte aligned and hold %zu bytes", sizeof(MetricsAcc) * (size_t)B);
     DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
-    static bool attr_set[kMaxDevices] = {};
-    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
-    if (!attr_set[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetSmemBytes));
-        CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetSmemBytes));
-        attr_set[dev] = true;
-    }
     MetricsAcc* acc = (MetricsAcc*)scratch;
     CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(MetricsAcc) * (size_t)B, st));
     const int tiles = (N + kMetTile - 1) / kMetTile;
@@ -991,6 +1011,33 @@ int pnpadmm_device_info(int* sm_count, int* max_clusters_256, int* cc_major, int
     return PNPADMM_OK;
 }
 
+// Kernel launches of the calls below, kept next to the code that makes them (bench.py reports them as gpu_launches):
+//   acquire: rows<FWD_IMG> + cols<FWD_ACQ>;  zero_filled: cols<INV> + rows<INV_ABS>;  solve adds copy_zero, write_cf,
+//   prepare, pack_mcode (fp32, N in {256, 512, 1024}), then the iteration kernels.
+int pnpadmm_plan_info(int B, int N, int mask_batched, int iters, int kernel, int* planes_cluster, int* planes_streaming,
+                      int* chunks, int* launches_acquire, int* launches_solve) {
+    if (B <= 0 || iters < 0) return fail(PNPADMM_ERR_BAD_ARG, "plan_info: B <= 0 or iters < 0");
+    int rc = check_n(N, false); if (rc) return rc;
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    bool use_cluster; rc = pick_kernel(kernel, N, false, d, &use_cluster); if (rc) return rc;
+    const int P = mask_batched ? B : (B + 1) / 2;
+    int p1 = 0, p2 = P, nch = 1;
+    if (use_cluster) {
+        p1 = (kernel == PNPADMM_KERNEL_AUTO && S2<float>::ok(N)) ? plan_hybrid(d, P, iters) : P;
+        p2 = P - p1;
+        int chunk; plan_chunks(p1, iters, d->max_clusters_256, &chunk, &nch);
+    }
+    const bool s2 = S2<float>::ok(N);
+    int it_launches = 0;
+    if (iters > 0) it_launches = (p1 > 0 ? 1 : 0) + (p2 > 0 ? 1 + 2 * iters : 0);
+    if (planes_cluster) *planes_cluster = p1;
+    if (planes_streaming) *planes_streaming = p2;
+    if (chunks) *chunks = nch;
+    if (launches_acquire) *launches_acquire = 2;
+    if (launches_solve) *launches_solve = 2 /* zero-fill */ + 1 /* copy_zero */ + 2 /* write_cf, prepare */ + (s2 ? 1 : 0) /* pack */ + it_launches;
+    return PNPADMM_OK;
+}
+
 size_t pnpadmm_workspace_bytes(int B, int N, int is_f64, int mask_batched) {
     if (B <= 0 || N <= 0) return 0;
     return ws_bytes_impl(B, N, is_f64 ? 8 : 4, mask_batched);
@@ -1088,49 +1135,109 @@ int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, co
     return PNPADMM_OK;
 }
 
-// Pipelined variant: copies on their own streams, double-buffered device slots, ordering by library-owned events.
-size_t pnpadmm_host_pipeline_scratch_bytes(int B, int N) {
-    if (B <= 0 || N <= 0) return 0;
+// Pipelined variant: copies on their own streams, n_slots device slots, ordering by the events of a caller-owned
+// pipeline object (pnpadmm_pipeline_create), so any number of pipelines can share a device.
+size_t pnpadmm_host_pipeline_scratch_bytes(int B, int N, int n_slots) {
+    if (B <= 0 || N <= 0 || n_slots < 2 || n_slots > PNPADMM_PIPELINE_MAX_SLOTS) return 0;
     const size_t nn = (size_t)N * N, n = (size_t)B * nn;
-    // per slot: img u8, mask u8, noise c64, x f32;  shared by both slots (compute stream only): img f32, y c64, z, w
-    return 2 * (align_up(n) + align_up(nn) + align_up(nn * 8) + align_up(n * 4)) + align_up(n * 4) + align_up(n * 8) +
+    // per slot: img u8, mask u8, noise c64, x f32;  shared by all slots (compute stream only): img f32, y c64, z, w
+    return n_slots * (align_up(n) + align_up(nn) + align_up(nn * 8) + align_up(n * 4)) + align_up(n * 4) + align_up(n * 8) +
            2 * align_up(n * 4);
 }
 
+}  // extern "C"
+
 namespace {
-struct PipeEvents { bool ready = false; cudaEvent_t in_ready[2], done[2], out_done[2]; };
-PipeEvents g_pipe[kMaxDevices];
+struct PipeKey {
+    void* d_scratch; void* ws; size_t scratch_bytes, wsb;
+    double lambda1, reo, alpha, b;
+    int B, N, prox, iters, kernel, slot, n_slots, pad;
+};
+struct PipeGraph {
+    bool valid = false;
+    PipeKey key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long stamp = 0;
+};
+constexpr int kPipeGraphs = 8;
 }  // namespace
 
-int pnpadmm_reconstruct_host_pipelined_f32(const uint8_t* h_img, const uint8_t* h_mask, const float* h_noise, float* h_x,
-                                           int B, int N, int prox, int iters, double lambda1, double reo, double alpha,
-                                           double b, int kernel, void* d_scratch, size_t scratch_bytes, void* ws, size_t wsb,
-                                           int slot, pnpadmm_stream_t compute, pnpadmm_stream_t h2d, pnpadmm_stream_t d2h) {
-    if (!h_img || !h_mask || !h_noise || !h_x || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: NULL pointer or B <= 0");
-    if (slot != 0 && slot != 1) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: slot must be 0 or 1");
-    int rc = check_n(N, false); if (rc) return rc;
-    if (!d_scratch || ((uintptr_t)d_scratch) % kAlign || scratch_bytes < pnpadmm_host_pipeline_scratch_bytes(B, N))
-        return fail(PNPADMM_ERR_WORKSPACE, "reconstruct_host_pipelined: d_scratch NULL, misaligned or smaller than %zu bytes",
-                    pnpadmm_host_pipeline_scratch_bytes(B, N));
-    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
-    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
-    PipeEvents& ev = g_pipe[dev];
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (!ev.ready) {
-            for (int i = 0; i < 2; ++i) {
-                CUDA_TRY(cudaEventCreateWithFlags(&ev.in_ready[i], cudaEventDisableTiming));
-                CUDA_TRY(cudaEventCreateWithFlags(&ev.done[i], cudaEventDisableTiming));
-                CUDA_TRY(cudaEventCreateWithFlags(&ev.out_done[i], cudaEventDisableTiming));
-            }
-            ev.ready = true;
+// The object behind pnpadmm_pipeline_t: the ordering events of one pipeline and the captured compute sections
+// (u8 -> unit, acquisition, zero-fill, prepare, iterations: one graph launch per step instead of ~25 driver calls).
+struct pnpadmm_pipeline_s {
+    int dev = 0, n_slots = 2;
+    cudaEvent_t in_ready[PNPADMM_PIPELINE_MAX_SLOTS], done[PNPADMM_PIPELINE_MAX_SLOTS], out_done[PNPADMM_PIPELINE_MAX_SLOTS];
+    bool used[PNPADMM_PIPELINE_MAX_SLOTS];
+    PipeGraph graphs[kPipeGraphs];
+    PipeKey last_key[PNPADMM_PIPELINE_MAX_SLOTS];     // configuration of the previous call per slot
+    bool have_last[PNPADMM_PIPELINE_MAX_SLOTS];
+    unsigned long long clock = 0;
+    std::mutex mu;
+};
+
+extern "C" {
+
+int pnpadmm_pipeline_create(pnpadmm_pipeline_t* out, int n_slots) {
+    if (!out) return fail(PNPADMM_ERR_BAD_ARG, "pipeline_create: NULL pointer");
+    if (n_slots < 2 || n_slots > PNPADMM_PIPELINE_MAX_SLOTS)
+        return fail(PNPADMM_ERR_BAD_ARG, "pipeline_create: n_slots=%d must be in [2, %d]", n_slots, PNPADMM_PIPELINE_MAX_SLOTS);
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    pnpadmm_pipeline_s* p = new (std::nothrow) pnpadmm_pipeline_s();
+    if (!p) return fail(PNPADMM_ERR_CUDA, "pipeline_create: out of host memory");
+    CUDA_TRY(cudaGetDevice(&p->dev));
+    p->n_slots = n_slots;
+    for (int i = 0; i < PNPADMM_PIPELINE_MAX_SLOTS; ++i) { p->in_ready[i] = p->done[i] = p->out_done[i] = nullptr; p->used[i] = false; p->have_last[i] = false; }
+    for (int i = 0; i < n_slots; ++i) {
+        if (cudaEventCreateWithFlags(&p->in_ready[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->out_done[i], cudaEventDisableTiming) != cudaSuccess) {
+            const cudaError_t e = cudaGetLastError();
+            pnpadmm_pipeline_destroy(p);
+            return fail(PNPADMM_ERR_CUDA, "pipeline_create: cudaEventCreate failed: %s", cudaGetErrorString(e));
         }
     }
+    *out = p;
+    return PNPADMM_OK;
+}
+
+int pnpadmm_pipeline_destroy(pnpadmm_pipeline_t p) {
+    if (!p) return PNPADMM_OK;
+    for (int i = 0; i < PNPADMM_PIPELINE_MAX_SLOTS; ++i) {
+        if (p->in_ready[i]) (void)cudaEventDestroy(p->in_ready[i]);
+        if (p->done[i]) (void)cudaEventDestroy(p->done[i]);
+        if (p->out_done[i]) (void)cudaEventDestroy(p->out_done[i]);
+    }
+    for (int i = 0; i < kPipeGraphs; ++i)
+        if (p->graphs[i].valid) { (void)cudaGraphExecDestroy(p->graphs[i].exec); (void)cudaGraphDestroy(p->graphs[i].graph); }
+    (void)cudaGetLastError();
+    delete p;
+    return PNPADMM_OK;
+}
+
+int pnpadmm_reconstruct_host_pipelined_f32(pnpadmm_pipeline_t pipe, const uint8_t* h_img, const uint8_t* h_mask,
+                                           const float* h_noise, float* h_x, int B, int N, int prox, int iters, double lambda1,
+                                           double reo, double alpha, double b, int kernel, void* d_scratch, size_t scratch_bytes,
+                                           void* ws, size_t wsb, int slot, pnpadmm_stream_t compute, pnpadmm_stream_t h2d,
+                                           pnpadmm_stream_t d2h) {
+    if (!pipe) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: NULL pipeline (pnpadmm_pipeline_create)");
+    if (!h_img || !h_mask || !h_noise || !h_x || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: NULL pointer or B <= 0");
+    const int S = pipe->n_slots;
+    if (slot < 0 || slot >= S) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: slot must be in [0, %d)", S);
+    int rc = check_n(N, false); if (rc) return rc;
+    rc = check_prox(prox, iters, reo, b); if (rc) return rc;
+    if (!d_scratch || ((uintptr_t)d_scratch) % kAlign || scratch_bytes < pnpadmm_host_pipeline_scratch_bytes(B, N, S))
+        return fail(PNPADMM_ERR_WORKSPACE, "reconstruct_host_pipelined: d_scratch NULL, misaligned or smaller than %zu bytes",
+                    pnpadmm_host_pipeline_scratch_bytes(B, N, S));
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != pipe->dev) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: pipeline belongs to device %d, current device is %d", pipe->dev, dev);
     cudaStream_t sc = ST(compute), si = ST(h2d), so = ST(d2h);
     const size_t nn = (size_t)N * N, n = (size_t)B * nn;
     unsigned char* p = (unsigned char*)d_scratch;
-    uint8_t* d_img8[2]; uint8_t* d_mask[2]; float* d_noise[2]; float* d_x[2];
-    for (int i = 0; i < 2; ++i) {
+    uint8_t* d_img8[PNPADMM_PIPELINE_MAX_SLOTS]; uint8_t* d_mask[PNPADMM_PIPELINE_MAX_SLOTS];
+    float* d_noise[PNPADMM_PIPELINE_MAX_SLOTS]; float* d_x[PNPADMM_PIPELINE_MAX_SLOTS];
+    for (int i = 0; i < S; ++i) {
         d_img8[i] = p; p += align_up(n);
         d_mask[i] = p; p += align_up(nn);
         d_noise[i] = (float*)p; p += align_up(nn * 8);
@@ -1140,32 +1247,84 @@ int pnpadmm_reconstruct_host_pipelined_f32(const uint8_t* h_img, const uint8_t* 
     float* d_y = (float*)p; p += align_up(n * 8);
     float* d_z = (float*)p; p += align_up(n * 4);
     float* d_w = (float*)p;
+    std::lock_guard<std::mutex> lk(pipe->mu);
     // inputs of this slot: free once the compute of the previous call on the slot has finished (done[slot])
-    CUDA_TRY(cudaStreamWaitEvent(si, ev.done[slot], 0));
+    if (pipe->used[slot]) CUDA_TRY(cudaStreamWaitEvent(si, pipe->done[slot], 0));
     CUDA_TRY(cudaMemcpyAsync(d_img8[slot], h_img, n, cudaMemcpyHostToDevice, si));
     CUDA_TRY(cudaMemcpyAsync(d_mask[slot], h_mask, nn, cudaMemcpyHostToDevice, si));
     CUDA_TRY(cudaMemcpyAsync(d_noise[slot], h_noise, nn * 8, cudaMemcpyHostToDevice, si));
-    CUDA_TRY(cudaEventRecord(ev.in_ready[slot], si));
+    CUDA_TRY(cudaEventRecord(pipe->in_ready[slot], si));
     // compute: needs the inputs, and the slot's output buffer drained by the previous D2H
-    CUDA_TRY(cudaStreamWaitEvent(sc, ev.in_ready[slot], 0));
-    CUDA_TRY(cudaStreamWaitEvent(sc, ev.out_done[slot], 0));
-    u8_to_unit_kernel<float><<<grid_1d(n, d->sm_count), 256, 0, sc>>>(d_img8[slot], d_img, n);
-    LAUNCH_CHECK("u8_to_unit_kernel");
-    rc = acquire_impl<float>(d_img, d_mask[slot], d_noise[slot], d_y, B, N, 0, 0, 0, ws, wsb, sc); if (rc) return rc;
-    rc = solve_impl<float>(d_y, d_mask[slot], d_x[slot], d_z, d_w, B, N, 0, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, sc);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(ev.done[slot], sc));
-    CUDA_TRY(cudaStreamWaitEvent(so, ev.done[slot], 0));
+    CUDA_TRY(cudaStreamWaitEvent(sc, pipe->in_ready[slot], 0));
+    if (pipe->used[slot]) CUDA_TRY(cudaStreamWaitEvent(sc, pipe->out_done[slot], 0));
+    auto enqueue_compute = [&]() -> int {
+        u8_to_unit_kernel<float><<<grid_1d(n, d->sm_count), 256, 0, sc>>>(d_img8[slot], d_img, n);
+        LAUNCH_CHECK("u8_to_unit_kernel");
+        int r = acquire_impl<float>(d_img, d_mask[slot], d_noise[slot], d_y, B, N, 0, 0, 0, ws, wsb, sc); if (r) return r;
+        return solve_impl<float>(d_y, d_mask[slot], d_x[slot], d_z, d_w, B, N, 0, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, sc);
+    };
+    // The compute section has fixed arguments per (slot, parameters): replay it as one graph from the second sighting on.
+    static const char* nograph = getenv("PNPADMM_NO_GRAPH");
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    bool graphable = !(nograph && atoi(nograph) != 0) && sc != nullptr && sc != cudaStreamLegacy &&
+                     cudaStreamIsCapturing(sc, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
+    (void)cudaGetLastError();
+    PipeGraph* g = nullptr;
+    if (graphable) {
+        PipeKey key;
+        memset(&key, 0, sizeof(key));
+        key.d_scratch = d_scratch; key.ws = ws; key.scratch_bytes = scratch_bytes; key.wsb = wsb;
+        key.lambda1 = lambda1; key.reo = reo; key.alpha = alpha; key.b = b;
+        key.B = B; key.N = N; key.prox = prox; key.iters = iters; key.kernel = kernel; key.slot = slot; key.n_slots = S;
+        PipeGraph* victim = nullptr;
+        for (int i = 0; i < kPipeGraphs; ++i) {
+            PipeGraph& e = pipe->graphs[i];
+            if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) { g = &e; break; }
+            if (!victim || (victim->valid && (!e.valid || e.stamp < victim->stamp))) victim = &e;
+        }
+        if (!g && pipe->have_last[slot] && memcmp(&pipe->last_key[slot], &key, sizeof(key)) == 0) {
+            // second call in a row with this configuration on this slot: capture the section
+            g = victim;
+            if (g->valid) { (void)cudaGraphExecDestroy(g->exec); (void)cudaGraphDestroy(g->graph); g->valid = false; }
+            if (cudaStreamBeginCapture(sc, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int r = enqueue_compute();
+                cudaGraph_t gr = nullptr;
+                const cudaError_t e_end = cudaStreamEndCapture(sc, &gr);
+                cudaGraphExec_t ex = nullptr;
+                if (r == PNPADMM_OK && e_end == cudaSuccess && gr && cudaGraphInstantiate(&ex, gr, 0) == cudaSuccess) {
+                    memcpy(&g->key, &key, sizeof(key)); g->graph = gr; g->exec = ex; g->valid = true;
+                } else {
+                    if (gr) (void)cudaGraphDestroy(gr);
+                    (void)cudaGetLastError();
+                    if (r != PNPADMM_OK) return r;
+                    g = nullptr;                     // fall back to direct launches
+                }
+            } else {
+                (void)cudaGetLastError();
+                g = nullptr;
+            }
+        }
+        memcpy(&pipe->last_key[slot], &key, sizeof(key)); pipe->have_last[slot] = true;
+    }
+    if (g) {
+        g->stamp = ++pipe->clock;
+        CUDA_TRY(cudaGraphLaunch(g->exec, sc));
+    } else {
+        rc = enqueue_compute(); if (rc) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(pipe->done[slot], sc));
+    CUDA_TRY(cudaStreamWaitEvent(so, pipe->done[slot], 0));
     CUDA_TRY(cudaMemcpyAsync(h_x, d_x[slot], n * 4, cudaMemcpyDeviceToHost, so));
-    CUDA_TRY(cudaEventRecord(ev.out_done[slot], so));
+    CUDA_TRY(cudaEventRecord(pipe->out_done[slot], so));
+    pipe->used[slot] = true;
     return PNPADMM_OK;
 }
 
-int pnpadmm_reconstruct_host_wait(int slot) {
-    if (slot != 0 && slot != 1) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_wait: slot must be 0 or 1");
-    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
-    if (!g_pipe[dev].ready) return PNPADMM_OK;   // nothing was ever enqueued
-    CUDA_TRY(cudaEventSynchronize(g_pipe[dev].out_done[slot]));
+int pnpadmm_reconstruct_host_wait(pnpadmm_pipeline_t pipe, int slot) {
+    if (!pipe) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_wait: NULL pipeline");
+    if (slot < 0 || slot >= pipe->n_slots) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_wait: slot must be in [0, %d)", pipe->n_slots);
+    if (!pipe->used[slot]) return PNPADMM_OK;   // nothing was ever enqueued on this slot
+    CUDA_TRY(cudaEventSynchronize(pipe->out_done[slot]));
     return PNPADMM_OK;
 }
 

@@ -76,6 +76,8 @@ class FusedDnCNN:
             raise _abi.PnpAdmmError('no CUDA device visible: the tensor-core denoiser has no CPU path')
         self.lib = _abi.load()
         self.device = torch.device(device)
+        if self.device.type == 'cuda' and self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.residual = bool(residual)
         self.w, self.cin, self.n_mid = pack_dncnn(net, self.device)
         if self.cin not in (1, 2):
@@ -95,16 +97,20 @@ class FusedDnCNN:
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         if x.ndim != 4 or x.shape[1] != self.cin or not x.is_cuda:
             raise ValueError(f'expected a CUDA tensor of shape (B, {self.cin}, H, W), got {tuple(x.shape)} on {x.device}')
+        if x.device != self.w['w_head'].device:
+            raise ValueError(f'input on {x.device} but the packed weights live on {self.w["w_head"].device}')
         x = x.float().contiguous()
         B, _, H, W = (int(v) for v in x.shape)
-        a0, a1 = self._buffers(B, H, W)
-        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
         w = self.w
-        _abi.check(self.lib.pnpadmm_dncnn_forward_bf16(
-            x.data_ptr(), out.data_ptr(), B, self.cin, H, W, self.n_mid, w['w_head'].data_ptr(), w['b_head'].data_ptr(),
-            w['w_mid'].data_ptr() if self.n_mid else None, w['b_mid'].data_ptr() if self.n_mid else None,
-            w['w_tail'].data_ptr(), w['b_tail'].data_ptr(), int(self.residual), a0.data_ptr(), a1.data_ptr(),
-            torch.cuda.current_stream().cuda_stream))
+        # the library launches on the CURRENT device and stream: make them the tensors' own
+        with torch.cuda.device(x.device):
+            a0, a1 = self._buffers(B, H, W)
+            out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+            _abi.check(self.lib.pnpadmm_dncnn_forward_bf16(
+                x.data_ptr(), out.data_ptr(), B, self.cin, H, W, self.n_mid, w['w_head'].data_ptr(), w['b_head'].data_ptr(),
+                w['w_mid'].data_ptr() if self.n_mid else None, w['b_mid'].data_ptr() if self.n_mid else None,
+                w['w_tail'].data_ptr(), w['b_tail'].data_ptr(), int(self.residual), a0.data_ptr(), a1.data_ptr(),
+                torch.cuda.current_stream().cuda_stream))
         return out
 
 
@@ -129,6 +135,7 @@ def conv64(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu:
     wp = pack_conv64(weight.to(x.device))
     bs = bias.to(x.device, torch.float32).contiguous()
     out = torch.empty_like(x)
-    _abi.check(lib.pnpadmm_conv64_bf16(x.data_ptr(), out.data_ptr(), wp.data_ptr(), bs.data_ptr(), B, H, W, int(relu),
-                                       torch.cuda.current_stream().cuda_stream))
+    with torch.cuda.device(x.device):
+        _abi.check(lib.pnpadmm_conv64_bf16(x.data_ptr(), out.data_ptr(), wp.data_ptr(), bs.data_ptr(), B, H, W, int(relu),
+                                           torch.cuda.current_stream().cuda_stream))
     return from_chunk_planar(out)

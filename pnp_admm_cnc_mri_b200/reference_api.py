@@ -12,8 +12,11 @@ directory, reconstructs every image with the given mask / noise, writes ``result
 append-mode log, and returns the 22-slot list ``out`` whose first n entries are the reconstructions
 (S1:44-45,132).  Differences, all additive: the images are reconstructed as ONE batch on the GPU;
 keyword-only extras (``testset_name``, ``testsets``, ``results``, ``save_E``, ``images``, ``image_names``,
-``model_zoo``, ``denoiser_dtype``) override what the reference hard-codes; when ``model_zoo/<name>.pth``
-is absent the network is random-initialised (the KAIR checkpoints are not redistributable).
+``model_zoo``, ``denoiser_dtype``, ``dtype``, ``device``) override what the reference hard-codes; when
+``model_zoo/<name>.pth`` is absent the network is random-initialised (the KAIR checkpoints are not redistributable).
+``dtype='float64'`` runs ADMM_L1 / ADMM_CNC on the fp64 validation build (the reference loop is float64; the default
+float32 kernels agree with it to <= 1e-4 relative).  PSNR / SSIM / RE are evaluated on the device
+(``pnpadmm_metrics_*``, the reference's formulas in double precision), one call per batch.
 """
 from __future__ import annotations
 
@@ -29,12 +32,12 @@ import torch
 from . import metrics
 from .denoisers import Denoiser, build_model, count_params
 from .pnp import pnp_admm_cnc, pnp_admm_l1
-from .solver import admm_solve
+from .solver import admm_solve, image_metrics
 from .solver import soft as _soft_cuda
 
 IMG_EXTENSIONS = ('.jpg', '.JPG', '.jpeg', '.JPEG', '.png', '.PNG', '.ppm', '.PPM', '.bmp', '.BMP', '.tif')
 _EXTRA = ('testset_name', 'testsets', 'results', 'save_E', 'images', 'image_names', 'model_zoo', 'denoiser_dtype',
-          'fix_model2', 'seed')
+          'fix_model2', 'seed', 'dtype', 'device')
 
 
 # ----------------------------------------------------------------------------------------------
@@ -170,16 +173,28 @@ class _Run:
         self.out = [A] * slots                                           # S1:44-45
         self.psnr1 = [0] * 22
         self.res = OrderedDict(psnr=[], ssim=[], re=[])
+        self.scores = None
+
+    def check_slots(self, n_images: int):
+        """The reference raises IndexError at `out[n] = x` for the image past the last slot (S1:132), after having
+        reconstructed the ones before; a batch is reconstructed at once, so fail before launching it."""
+        if n_images > len(self.out):
+            raise IndexError(f'list assignment index out of range: {n_images} images but the reference\'s `out` list has '
+                             f'{len(self.out)} slots (S1:44-45)')
+
+    def score(self, x: torch.Tensor, img_H, as_uint8: bool):
+        """PSNR / SSIM / RE of the whole batch on the device (utils_image.py:543-636 in double precision;
+        img_E = 255 x, S1:133, or uint8(round(255 x)), S6:315): one (B,3) array comes back."""
+        ref = torch.as_tensor(np.stack(img_H)).to(x.device)
+        self.scores = image_metrics(x, ref, quantize=as_uint8).cpu().numpy()
 
     def record(self, n, x, img_H, name, suffix, as_uint8: bool, psnr_fmt: str):
-        self.out[n] = x                                                  # IndexError past the last slot, as in the reference
+        self.out[n] = x
         img_E = np.uint8((x * 255.0).round()) if as_uint8 else x * 255   # S6:315 | S1:133
         if self.save_E:
             import cv2
             cv2.imwrite(os.path.join(self.E_path, os.path.splitext(name)[0] + suffix), np.squeeze(img_E))
-        p = metrics.calculate_psnr(img_E, img_H)
-        s = metrics.calculate_ssim(img_E, img_H)
-        r = metrics.calculate_re(img_E, img_H)
+        p, s, r = (float(v) for v in self.scores[n])
         for k, v in zip(('psnr', 'ssim', 're'), (p, s, r)):
             self.res[k].append(v)
         self.logger.info(('{:s} - PSNR: ' + psnr_fmt + ' dB; SSIM: {:.4f} ; RE: {:.4f}.').format(name, p, s, r))
@@ -221,8 +236,13 @@ def ADMM_L1(mask, noises, **ADMM_L1_opts):
     run = _Run('ADMM_L1', extras)
     img_H, names, L_path = _load_images(extras)
     run.logger.info(L_path)
+    run.check_slots(len(names))
     img_L = _stack(img_H)
-    x = admm_solve(img_L, mask, noises, prox='l1', iter_num=iter_num, lambda1=lambda1, reo=reo)
+    _zero_fill_print(img_L, mask, noises)                                # S1:99-101
+    xd = admm_solve(torch.as_tensor(img_L), mask, noises, prox='l1', iter_num=iter_num, lambda1=lambda1, reo=reo,
+                    dtype=extras.get('dtype', 'float32'), device=extras.get('device'))
+    run.score(xd, img_H, False)
+    x = xd.cpu().numpy()
     for n, name in enumerate(names):
         run.record(n, x[n].astype(np.float64), img_H[n], name, '_PDG L1.png', False, '{:.2f}')
     run.averages()
@@ -239,8 +259,13 @@ def ADMM_CNC(mask, noises, **ADMM_CNC_opts):
     run = _Run('ADMM_CNC', extras)
     img_H, names, L_path = _load_images(extras)
     run.logger.info(L_path)
+    run.check_slots(len(names))
     img_L = _stack(img_H)
-    x = admm_solve(img_L, mask, noises, prox='cnc', iter_num=iter_num, lambda1=lambda1, reo=reo, alpha=alpha, b=b)
+    _zero_fill_print(img_L, mask, noises)                                # S4:103-105
+    xd = admm_solve(torch.as_tensor(img_L), mask, noises, prox='cnc', iter_num=iter_num, lambda1=lambda1, reo=reo, alpha=alpha,
+                    b=b, dtype=extras.get('dtype', 'float32'), device=extras.get('device'))
+    run.score(xd, img_H, False)
+    x = xd.cpu().numpy()
     for n, name in enumerate(names):
         run.record(n, x[n].astype(np.float64), img_H[n], name, '_ADMM CNC.png', False, '{:.4f}')
     run.averages()
@@ -263,7 +288,7 @@ def _denoiser(model_name, iter_num, x8, noises, extras, logger, weights_name=Non
     logger.info('Model path: {:s}{}'.format(path, '' if os.path.exists(path) else '  (absent: random-init weights)'))
     logger.info('Params number: {}'.format(count_params(model)))
     return Denoiser(model_name, iter_num=iter_num, x8=x8, noises=noises, model=model, ircnn_weights=ircnn_weights,
-                    dtype=extras.get('denoiser_dtype', torch.bfloat16))
+                    dtype=extras.get('denoiser_dtype', torch.bfloat16), device=extras.get('device') or 'cuda')
 
 
 def PNP_ADMM_L1_D(model_name, mask, noises, **PNP_ADMM_L1_D_opts):
@@ -274,8 +299,12 @@ def PNP_ADMM_L1_D(model_name, mask, noises, **PNP_ADMM_L1_D_opts):
     x8 = 'drunet' in model_name          # S3:87 sets True; the dncnn / fdncnn / ircnn branches reset it (S3:130,142,181)
     D = _denoiser(model_name, iter_num, x8, noises, extras, run.logger)
     img_H, names, L_path = _load_images(extras)
+    run.check_slots(len(names))
     img_L = _stack(img_H)
-    x = pnp_admm_l1(img_L, mask, noises, D, iter_num=iter_num, reo=reo)
+    _zero_fill_print(img_L, mask, noises)                                # S3:241-243
+    xd = pnp_admm_l1(torch.as_tensor(img_L), mask, noises, D, iter_num=iter_num, reo=reo, device=extras.get('device'))
+    run.score(xd, img_H, False)
+    x = xd.cpu().numpy()
     for n, name in enumerate(names):
         run.record(n, x[n], img_H[n], name, '_' + model_name + '_PNP_ADMM_L1_D.png', False, '{:.2f}')
     run.averages()
@@ -292,8 +321,12 @@ def PNP_ADMM_CNC_D(model_name, mask, noises, **PNP_ADMM_CNC_D_opts):
     run = _Run(model_name, extras)
     D = _denoiser(model_name, iter_num, False, noises, extras, run.logger)   # x8 = False (S6:93)
     img_H, names, L_path = _load_images(extras)
+    run.check_slots(len(names))
     img_L = _stack(img_H)
-    x = pnp_admm_cnc(img_L, mask, noises, D, None, alpha=alpha, iter_num=iter_num, lambda1=lambda1, reo=reo, b=b)
+    xd = pnp_admm_cnc(torch.as_tensor(img_L), mask, noises, D, None, alpha=alpha, iter_num=iter_num, lambda1=lambda1, reo=reo, b=b,
+                      device=extras.get('device'))
+    run.score(xd, img_H, True)
+    x = xd.cpu().numpy()
     for n, name in enumerate(names):
         run.record(n, x[n], img_H[n], name, 'PNP_ADMM_CNC_D.png', True, '{:.4f}')
     run.averages(alpha)
@@ -315,8 +348,13 @@ def PNP_ADMM_CNC_DnCNN(model_name1, model_name2, mask, noises, **PNP_ADMM_CNC_Dn
     D2 = _denoiser(model_name2, iter_num, False, noises, extras, run.logger, weights_name=w2)
     img_H, names, L_path = _load_images(extras)
     run.logger.info(L_path)
+    run.check_slots(len(names))
     img_L = _stack(img_H)
-    x = pnp_admm_cnc(img_L, mask, noises, D1, D2, alpha=alpha, iter_num=iter_num, lambda1=lambda1, reo=reo, b=b)
+    _zero_fill_print(img_L, mask, noises)                                # S6:479-481
+    xd = pnp_admm_cnc(torch.as_tensor(img_L), mask, noises, D1, D2, alpha=alpha, iter_num=iter_num, lambda1=lambda1, reo=reo, b=b,
+                      device=extras.get('device'))
+    run.score(xd, img_H, True)
+    x = xd.cpu().numpy()
     for n, name in enumerate(names):
         run.record(n, x[n], img_H[n], name, 'PNP_ADMM_CNC_DnCNN.png', True, '{:.4f}')
     run.averages(alpha)

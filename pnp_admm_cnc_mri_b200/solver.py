@@ -180,6 +180,74 @@ class AdmmSolver:
         return x, z, w
 
 
+class HostPipeline:
+    """Back-to-back reconstructions from HOST buffers (the drop-in functions' situation: uint8 images on the host in,
+    float32 reconstructions on the host out), pipelined over `n_slots` device slots: H2D copies, kernels and the D2H
+    copy run on three streams so the copies of neighbouring batches overlap the kernels.  Owns the C-ABI pipeline
+    object (events + captured compute graphs), its streams, the device scratch and the workspace; several
+    HostPipelines can coexist on one device.
+
+        pipe = HostPipeline(B, N, n_slots=3)
+        pipe.submit(slot, h_img_u8, h_mask_u8, h_noise_c64_as_float, h_x, prox='cnc', iter_num=50, ...)
+        pipe.wait(slot)          # h_x of that slot is valid
+
+    Host tensors should be pinned (otherwise the copies are synchronous)."""
+
+    def __init__(self, B: int, N: int, n_slots: int = 2, device=None):
+        import ctypes
+        self.lib = _abi.load()
+        self.device = _require_cuda(device)
+        self.B, self.N, self.n_slots = int(B), int(N), int(n_slots)
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.pnpadmm_host_pipeline_scratch_bytes(self.B, self.N, self.n_slots)
+            if nbytes == 0:
+                raise ValueError(f'bad pipeline shape B={B}, N={N}, n_slots={n_slots} (2..4 slots)')
+            h = ctypes.c_void_p()
+            _abi.check(self.lib.pnpadmm_pipeline_create(ctypes.byref(h), self.n_slots))
+            self._h = h
+            self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.ws_bytes = self.lib.pnpadmm_workspace_bytes(self.B, self.N, 0, 0)
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+            self.s_compute, self.s_h2d, self.s_d2h = (torch.cuda.Stream(self.device) for _ in range(3))
+
+    def submit(self, slot: int, h_img: torch.Tensor, h_mask: torch.Tensor, h_noise: torch.Tensor, h_x: torch.Tensor, *,
+               prox: str = 'cnc', iter_num: int = 50, lambda1: float = 0.5, reo: float = 0.05, alpha: float = 0.45,
+               b: float = 64.0, kernel: str = 'auto') -> None:
+        B, N = self.B, self.N
+        if not (h_img.dtype == torch.uint8 and tuple(h_img.shape) == (B, N, N) and h_img.is_contiguous() and not h_img.is_cuda):
+            raise ValueError(f'h_img must be a contiguous host uint8 tensor of shape {(B, N, N)}')
+        if not (h_mask.dtype == torch.uint8 and tuple(h_mask.shape) == (N, N) and h_mask.is_contiguous() and not h_mask.is_cuda):
+            raise ValueError(f'h_mask must be a contiguous host uint8 tensor of shape {(N, N)}')
+        if not (h_noise.dtype == torch.float32 and h_noise.numel() == 2 * N * N and h_noise.is_contiguous() and not h_noise.is_cuda):
+            raise ValueError('h_noise must be a contiguous host float32 tensor holding (N,N) complex64 as (re, im) pairs')
+        if not (h_x.dtype == torch.float32 and tuple(h_x.shape) == (B, N, N) and h_x.is_contiguous() and not h_x.is_cuda):
+            raise ValueError(f'h_x must be a contiguous host float32 tensor of shape {(B, N, N)}')
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pnpadmm_reconstruct_host_pipelined_f32(
+                self._h, h_img.data_ptr(), h_mask.data_ptr(), h_noise.data_ptr(), h_x.data_ptr(), B, N, _PROX[prox],
+                int(iter_num), float(lambda1), float(reo), float(alpha), float(b), _KERNEL[kernel],
+                self.scratch.data_ptr(), self.scratch.numel(), self.ws.data_ptr(), self.ws_bytes, int(slot),
+                self.s_compute.cuda_stream, self.s_h2d.cuda_stream, self.s_d2h.cuda_stream))
+
+    def wait(self, slot: int) -> None:
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pnpadmm_reconstruct_host_wait(self._h, int(slot)))
+
+    def close(self) -> None:
+        if getattr(self, '_h', None) is not None and self._h:
+            with torch.cuda.device(self.device):
+                for s in (self.s_compute, self.s_h2d, self.s_d2h):
+                    s.synchronize()
+                self.lib.pnpadmm_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def admm_solve(images: ArrayLike, mask: ArrayLike, noises: ArrayLike, *, prox: str = 'l1', iter_num: int = 50,
                lambda1: float = 0.1, reo: float = 0.015, alpha: float = 0.45, b: float = 64.0,
                dtype: str = 'float32', kernel: str = 'auto', return_state: bool = False, device=None):

@@ -98,6 +98,82 @@ int emulate(const float* z_in, const float* w_in, float* x, float* z, float* w, 
 #undef FOR_ALL
     return 0;
 }
+
+// Blocked-tile variant (cluster256_bk_kernel): staging + 16 bulk copies of 2 KB per CTA and transpose, G read from
+// the tile-ordered global copy.
+int emulate_bk(const float* z_in, const float* w_in, float* x, float* z, float* w, float* xpw, const float* G_,
+               const uint8_t* mcode_, int mcode_batched, float cf1, float cf2, int B, int P, int solo, int iters,
+               const ProxParams<float>& pp) {
+    constexpr int CL = 16;
+    typedef Geo<CL> G;
+    std::vector<cf32> master = master_table();
+    std::vector<std::vector<unsigned char>> smem(CL, std::vector<unsigned char>(G::kSmemBytes, 0));
+    unsigned char* all[CL];
+    for (int r = 0; r < CL; ++r) all[r] = smem[r].data();
+    std::vector<ThreadState> st((size_t)CL * G::kThreads);
+    for (int r = 0; r < CL; ++r)
+        for (int i = 0; i < 256; ++i) fill_tw(reinterpret_cast<cf32*>(all[r] + G::kOffTW), master.data(), i);
+    const int mode = pp.prox == PROX_NONE ? PROX_NONE : prox_mode(pp);
+#define FOR_ALL(body)                                                   \
+    for (int r = 0; r < CL; ++r)                                        \
+        for (int t = 0; t < G::kThreads; ++t) {                         \
+            Ctx<CL> c; c.rank = r; c.tid = t; c.smem = all[r];          \
+            ThreadState& s = st[(size_t)r * G::kThreads + t];           \
+            body;                                                       \
+        }
+    // send_tile: block j of CTA r's staging buffer -> block r of CTA j's destination tile
+    auto send = [&](int off_src, int off_dst) {
+        std::vector<std::vector<unsigned char>> snap(CL);
+        for (int r = 0; r < CL; ++r) snap[r].assign(all[r] + off_src, all[r] + off_src + G::kTileBytes);
+        for (int r = 0; r < CL; ++r)
+            for (int j = 0; j < CL; ++j) std::memcpy(all[j] + off_dst + 2048 * r, snap[r].data() + 2048 * j, 2048);
+    };
+    const size_t nn = (size_t)kN * kN;
+    std::vector<cf32> Gt(nn);
+    for (int plane = 0; plane < P; ++plane) {
+        const int ia = solo ? plane : 2 * plane;
+        const bool has_b = !solo && (2 * plane + 1 < B);
+        PlaneIO io;
+        io.z_in_a = z_in + ia * nn; io.w_in_a = w_in + ia * nn;
+        io.z_in_b = has_b ? io.z_in_a + nn : nullptr; io.w_in_b = has_b ? io.w_in_a + nn : nullptr;
+        io.x_a = x + ia * nn; io.z_a = z ? z + ia * nn : nullptr; io.w_a = w ? w + ia * nn : nullptr;
+        io.xpw_a = xpw ? xpw + ia * nn : nullptr;
+        io.x_b = io.x_a + nn; io.z_b = io.z_a ? io.z_a + nn : nullptr; io.w_b = io.w_a ? io.w_a + nn : nullptr;
+        io.xpw_b = io.xpw_a ? io.xpw_a + nn : nullptr;
+        const cf32* Gp = reinterpret_cast<const cf32*>(G_) + plane * nn;
+        for (int kr = 0; kr < kN; ++kr)                 // what prepare_kernel writes for the cluster kernel
+            for (int kc = 0; kc < kN; ++kc) Gt[g_tiled_elem(G::kRows, kr, kc)] = Gp[kr * kN + kc];
+        const uint8_t* mcode = mcode_ + (mcode_batched ? plane * nn : 0);
+        FOR_ALL(row_load_state(c, s, io));
+        FOR_ALL(row_step1_write_bk<false>(c, s));
+        FOR_ALL(row_read_step2_bk<false>(c, s));
+        FOR_ALL(row_stage_bk(c, s));
+        send(G::kOffB1, G::kOffB2);
+        for (int it = 0; it < iters; ++it) {
+            FOR_ALL(col_load(c, s));
+            FOR_ALL(col_step1_write<false>(c, s));
+            FOR_ALL(col_read_step2<false>(c, s);
+                    col_blend_g(c, s, Gt.data() + (size_t)c.rank * (G::kTileBytes / 8),
+                                pack_codes(mcode, c.ct(), G::kRows * c.rank + c.cc()), cf1, cf2));
+            FOR_ALL(col_step1_write<true>(c, s));
+            FOR_ALL(col_read_step2<true>(c, s));
+            FOR_ALL(col_stage_bk(c, s));
+            send(G::kOffB2, G::kOffB1);
+            const bool last = (it == iters - 1);
+            FOR_ALL(row_load_bk(c, s));
+            FOR_ALL(row_step1_write_bk<true>(c, s));
+            FOR_ALL(row_read_step2_bk<true>(c, s); row_prox_dispatch(mode, c, s, pp, has_b, last, true, io));
+            if (!last) {
+                FOR_ALL(row_step1_write_bk<false>(c, s));
+                FOR_ALL(row_read_step2_bk<false>(c, s));
+                FOR_ALL(row_stage_bk(c, s));
+                send(G::kOffB1, G::kOffB2);
+            }
+        }
+    }
+#undef FOR_ALL
+    return 0;
+}
 }  // namespace
 
 extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float* z, float* w, float* xpw,
@@ -107,6 +183,8 @@ extern "C" int k1_emulate(const float* z_in, const float* w_in, float* x, float*
     ProxParams<float> pp;
     pp.prox = prox; pp.general = 0; pp.thr_l1 = thr_l1; pp.inv_b = inv_b; pp.one_m_alpha = one_m_alpha;
     pp.alpha = alpha; pp.coef = coef; pp.thr_cnc = thr_cnc;
+    if (cluster == 116)   // 16-CTA geometry, blocked tiles + bulk-copy transposes
+        return emulate_bk(z_in, w_in, x, z, w, xpw, G_, mcode_, mcode_batched, cf1, cf2, B, P, solo, iters, pp);
     if (cluster == 16)
         return emulate<16>(z_in, w_in, x, z, w, xpw, G_, mcode_, mcode_batched, cf1, cf2, B, P, solo, iters, pp);
     return emulate<8>(z_in, w_in, x, z, w, xpw, G_, mcode_, mcode_batched, cf1, cf2, B, P, solo, iters, pp);

@@ -25,7 +25,7 @@ def test_header_symbols_all_exported(lib):
     assert declared == sorted(_abi.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.pnpadmm_abi_version() == 1
+    assert lib.pnpadmm_abi_version() == _abi.ABI_VERSION == 2
 
 
 def test_workspace_sizes(lib):
@@ -51,18 +51,21 @@ def test_argument_validation_without_gpu(lib):
     assert rc == -1 and b'prox' in lib.pnpadmm_last_error_string()
     rc = lib.pnpadmm_soft_f32(None, None, 0.1, 10, None)
     assert rc == -1
-    # pipelined host call: NULL buffers, bad slot, undersized scratch
-    assert lib.pnpadmm_reconstruct_host_pipelined_f32(None, None, None, None, 4, 256, 1, 5, 0.5, 0.05, 0.45, 64.0, 0,
-                                                      None, 0, None, 0, 0, None, None, None) == -1
-    assert lib.pnpadmm_reconstruct_host_pipelined_f32(p, p, p, p, 4, 256, 1, 5, 0.5, 0.05, 0.45, 64.0, 0,
-                                                      p, 1024, p, 1024, 2, None, None, None) == -1
-    assert b'slot' in lib.pnpadmm_last_error_string()
+    # pipelined host call: the pipeline object is caller-owned (two pipelines may share a device); without one the
+    # call is rejected before anything else, and creating one needs a device
+    assert lib.pnpadmm_reconstruct_host_pipelined_f32(None, p, p, p, p, 4, 256, 1, 5, 0.5, 0.05, 0.45, 64.0, 0,
+                                                      p, 1024, p, 1024, 0, None, None, None) == -1
+    assert b'pipeline' in lib.pnpadmm_last_error_string()
+    assert lib.pnpadmm_reconstruct_host_wait(None, 0) == -1
+    assert lib.pnpadmm_pipeline_destroy(None) == 0
+    h = ctypes.c_void_p()
+    assert lib.pnpadmm_pipeline_create(ctypes.byref(h), 7) == -1 and b'n_slots' in lib.pnpadmm_last_error_string()
+    assert lib.pnpadmm_pipeline_create(None, 2) == -1
+    assert lib.pnpadmm_host_pipeline_scratch_bytes(64, 256, 2) > lib.pnpadmm_host_scratch_bytes(64, 256)
+    assert lib.pnpadmm_host_pipeline_scratch_bytes(64, 256, 3) > lib.pnpadmm_host_pipeline_scratch_bytes(64, 256, 2)
+    assert lib.pnpadmm_host_pipeline_scratch_bytes(64, 256, 1) == 0 and lib.pnpadmm_host_pipeline_scratch_bytes(64, 256, 5) == 0
     big = (ctypes.c_char * 4096)()
     q = (ctypes.addressof(big) + 255) // 256 * 256
-    assert lib.pnpadmm_reconstruct_host_pipelined_f32(p, p, p, p, 4, 256, 1, 5, 0.5, 0.05, 0.45, 64.0, 0,
-                                                      q, 1024, p, 1024, 1, None, None, None) == -3
-    assert lib.pnpadmm_reconstruct_host_wait(3) == -1
-    assert lib.pnpadmm_host_pipeline_scratch_bytes(64, 256) > lib.pnpadmm_host_scratch_bytes(64, 256)
     # device metrics: NULLs, unsupported size, scratch too small
     assert lib.pnpadmm_metrics_f32(None, None, 1, 256, 0, None, None, 0, None) == -1
     assert lib.pnpadmm_metrics_f32(p, p, 1, 8, 0, p, p, 1024, None) == -2

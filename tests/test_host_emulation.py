@@ -72,7 +72,7 @@ def test_fft256_line(emu):
         assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 3e-7
 
 
-@pytest.mark.parametrize('cluster', [8, 16])
+@pytest.mark.parametrize('cluster', [8, 16, 116])      # 116 = 16-CTA geometry with blocked tiles + bulk-copy transposes
 @pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
 def test_k1_emulated_solve_matches_oracle(emu, cs_inputs, prox, P, cluster):
     idx = [4, 0, 7]                                      # odd count: last plane has an empty b slot

@@ -380,37 +380,92 @@ def test_pipelined_host_call_matches_sync_call(pk, cs_inputs):
     solver = pk.AdmmSolver(B, N)
     st = torch.cuda.current_stream().cuda_stream
     scratch = torch.empty(lib.pnpadmm_host_scratch_bytes(B, N), dtype=torch.uint8, device='cuda')
-    want = []
-    for i in range(4):
-        hx = torch.empty((B, N, N), dtype=torch.float32).pin_memory()
-        _abi.check(lib.pnpadmm_reconstruct_host_f32(imgs[i].data_ptr(), masks[i % 3].data_ptr(), noise.data_ptr(), hx.data_ptr(),
-                                                    B, N, _abi.PROX_CNC, P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'],
-                                                    _abi.KERNEL_AUTO, scratch.data_ptr(), scratch.numel(), solver.ws.data_ptr(),
-                                                    solver.ws_bytes, st))
-        torch.cuda.synchronize()
-        want.append(hx.clone())
-    ps = torch.empty(lib.pnpadmm_host_pipeline_scratch_bytes(B, N), dtype=torch.uint8, device='cuda')
-    sc, si, so = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    torch.cuda.synchronize()
-    hx2 = [torch.empty((B, N, N), dtype=torch.float32).pin_memory() for _ in range(2)]
-    got = {}
-    for i in range(4):
-        if i >= 2:
-            _abi.check(lib.pnpadmm_reconstruct_host_wait(i & 1))
-            got[i - 2] = hx2[i & 1].clone()
-        _abi.check(lib.pnpadmm_reconstruct_host_pipelined_f32(
-            imgs[i].data_ptr(), masks[i % 3].data_ptr(), noise.data_ptr(), hx2[i & 1].data_ptr(), B, N, _abi.PROX_CNC,
-            P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'], _abi.KERNEL_AUTO, ps.data_ptr(), ps.numel(),
-            solver.ws.data_ptr(), solver.ws_bytes, i & 1, sc.cuda_stream, si.cuda_stream, so.cuda_stream))
-    for i in (2, 3):
-        _abi.check(lib.pnpadmm_reconstruct_host_wait(i & 1))
-        got[i] = hx2[i & 1].clone()
-    torch.cuda.synchronize()
-    for i in range(4):
-        assert torch.equal(got[i], want[i]), i
+    want = {}
+    for j in range(4):
+        for k in range(3):
+            hx = torch.empty((B, N, N), dtype=torch.float32).pin_memory()
+            _abi.check(lib.pnpadmm_reconstruct_host_f32(imgs[j].data_ptr(), masks[k].data_ptr(), noise.data_ptr(), hx.data_ptr(),
+                                                        B, N, _abi.PROX_CNC, P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'],
+                                                        _abi.KERNEL_AUTO, scratch.data_ptr(), scratch.numel(), solver.ws.data_ptr(),
+                                                        solver.ws_bytes, st))
+            torch.cuda.synchronize()
+            want[(j, k)] = hx.clone()
+    # the pipelined call through the package's HostPipeline (owns the C-ABI pipeline object, streams, scratch):
+    # 2 and 3 slots, more steps than slots so that slots are reused and the captured compute graphs are replayed
+    for S in (2, 3):
+        pipe = pk.HostPipeline(B, N, n_slots=S)
+        hx2 = [torch.empty((B, N, N), dtype=torch.float32).pin_memory() for _ in range(S)]
+        got = {}
+        steps = 9
+        for i in range(steps):
+            if i >= S:
+                pipe.wait(i % S)
+                got[i - S] = hx2[i % S].clone()
+            pipe.submit(i % S, imgs[i % 4], masks[i % 3], noise, hx2[i % S], prox='cnc', **P)
+        for i in range(steps - S, steps):
+            pipe.wait(i % S)
+            got[i] = hx2[i % S].clone()
+        for i in range(steps):
+            assert torch.equal(got[i], want[(i % 4, i % 3)]), (S, i)
+        pipe.close()
     # and against the oracle for one image of the last step
     xr = orc.admm_cnc(orc.preprocess_uint8(cs_inputs['images'][9]), cs_inputs['masks'][0].astype(np.float64), cs_inputs['noises'], **P)
-    assert rel(got[3][0].numpy(), xr) < TOL32
+    assert rel(want[(3, 0)][0].numpy(), xr) < TOL32
+
+
+def test_two_pipelines_share_a_device(pk, cs_inputs):
+    """the ordering events used to be one global set per device, so two pipelines on one device
+    (two host threads, or two scratch / stream sets) re-recorded each other's events and a slot's inputs could be
+    overwritten before its compute had read them.  The events now live in a caller-owned pipeline object: two
+    HostPipelines driven from two host threads, interleaved, must both reproduce the single-stream results."""
+    import threading
+    from pnp_admm_cnc_mri_b200 import _abi
+    lib = _abi.load()
+    B, N = 4, 256
+    P = dict(kat.CNC_DEFAULTS, iter_num=12)
+    masks = [torch.as_tensor(cs_inputs['masks'][k].copy()).pin_memory() for k in range(3)]
+    noise = torch.view_as_real(torch.as_tensor(cs_inputs['noises']).to(torch.complex64)).contiguous().pin_memory()
+    sets = {t: [torch.as_tensor(cs_inputs['images'][k:k + B].copy()).pin_memory() for k in ks]
+            for t, ks in ((0, (0, 2, 4, 6, 8, 10)), (1, (1, 3, 5, 7, 9, 11)))}
+    solver = pk.AdmmSolver(B, N)
+    scratch = torch.empty(lib.pnpadmm_host_scratch_bytes(B, N), dtype=torch.uint8, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    want = {}
+    for t in (0, 1):
+        for i, im in enumerate(sets[t]):
+            hx = torch.empty((B, N, N), dtype=torch.float32).pin_memory()
+            _abi.check(lib.pnpadmm_reconstruct_host_f32(im.data_ptr(), masks[(i + t) % 3].data_ptr(), noise.data_ptr(), hx.data_ptr(),
+                                                        B, N, _abi.PROX_CNC, P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'],
+                                                        _abi.KERNEL_AUTO, scratch.data_ptr(), scratch.numel(), solver.ws.data_ptr(),
+                                                        solver.ws_bytes, st))
+            torch.cuda.synchronize()
+            want[(t, i)] = hx.clone()
+    got, errs = {}, []
+
+    def worker(t):
+        try:
+            torch.cuda.set_device(0)
+            pipe = pk.HostPipeline(B, N, n_slots=2)
+            hx = [torch.empty((B, N, N), dtype=torch.float32).pin_memory() for _ in range(2)]
+            n = len(sets[t])
+            for i in range(n):
+                if i >= 2:
+                    pipe.wait(i & 1)
+                    got[(t, i - 2)] = hx[i & 1].clone()
+                pipe.submit(i & 1, sets[t][i], masks[(i + t) % 3], noise, hx[i & 1], prox='cnc', **P)
+            for i in (n - 2, n - 1):
+                pipe.wait(i & 1)
+                got[(t, i)] = hx[i & 1].clone()
+            pipe.close()
+        except Exception as e:          # surfaced in the main thread
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in (0, 1)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for k, v in want.items():
+        assert torch.equal(got[k], v), k
 
 
 def test_hybrid_schedule_parity(pk, cs_inputs, monkeypatch):

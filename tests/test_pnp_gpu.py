@@ -107,7 +107,7 @@ def test_bf16_denoiser_single_call_error(env):
         assert err < 2e-2
 
 
-def test_drop_in_entry_points(env, cs_inputs, ref_out, tmp_path, monkeypatch):
+def test_drop_in_entry_points(env, cs_inputs, ref_out, tmp_path, monkeypatch, capsys):
     """Same names / kwargs / return contract as the reference functions (S1:29, S4:31, S6:372)."""
     pk, img, m, nz = env
     from pnp_admm_cnc_mri_b200 import reference_api as api
@@ -117,6 +117,7 @@ def test_drop_in_entry_points(env, cs_inputs, ref_out, tmp_path, monkeypatch):
     cv2.imwrite('testsets/Set1/05.png', cs_inputs['images'][4])
     mask64 = m.astype(np.float64)
     out = api.ADMM_L1(mask64, nz, iter_num=50, lambda1=0.1, reo=0.015)
+    assert 'zero-filling psnr = 20.6451' in capsys.readouterr().out           # S1:101 prints it per image
     assert isinstance(out, list) and len(out) == 22 and out[1].dtype == np.uint8 and out[1].shape == (256, 256)
     assert out[0].dtype == np.float64 and rel(out[0], ref_out['l1']) < 1e-4
     assert os.path.exists('results/Set1_dn_ADMM_L1/05_PDG L1.png')
@@ -133,6 +134,11 @@ def test_drop_in_entry_points(env, cs_inputs, ref_out, tmp_path, monkeypatch):
     assert len(out) == 21 and len(psnr1) == 22 and out[0].dtype == np.float32 and psnr1[0] > 15
     out = api.PNP_ADMM_L1_D('drunet_gray', mask64, nz, iter_num=2, reo=0.26, save_E=False)
     assert len(out) == 22 and out[0].shape == (256, 256)
+    # keyword-only extras: the fp64 validation build behind the same entry point, and the slot check before the batch is launched
+    out = api.ADMM_L1(mask64, nz, iter_num=50, lambda1=0.1, reo=0.015, dtype='float64', save_E=False)
+    assert rel(out[0], ref_out['l1']) < 1e-10
+    with pytest.raises(IndexError):
+        api.ADMM_CNC(mask64, nz, images=[cs_inputs['images'][0]] * 23, save_E=False)
     s = api.soft(np.array([-2.0, -0.5, 0.0, 0.5, 2.0]), 1.0)
     assert np.array_equal(s, orc.soft(np.array([-2.0, -0.5, 0.0, 0.5, 2.0]), 1.0))
     ns = api.analyze_parse_ADMM_CNC(0.45, 50, 0.5, 0.05, 64, argv=['--iter_num', '7'])
@@ -160,3 +166,108 @@ def test_pnp_cnc_with_tensor_core_denoiser_tracks_fp32_denoiser():
     for k in range(B):
         err = np.linalg.norm(x16[k] - x32[k]) / np.linalg.norm(x32[k])
         assert err < 2e-2, (k, err)
+
+
+# ---------------------------------------------------------------------------------------------
+# Full preset depth (50 iterations) against outputs of the UNMODIFIED scripts S3 / S6 with the same seeded weights
+# (tests/golden/pnp_golden_50it.npz, oracle/make_golden_pnp50.py).  The denoiser runs in float32 on both sides; what
+# differs is cuDNN on the GPU against oneDNN on the CPU (summation order, ~1e-6 per forward) and how far 50 iterations of
+# a random-weight network amplify that.  The generator records the same sensitivity on the CPU alone (the restatement,
+# driven by this package's Denoiser, against the script: `diff_vals`): residual DnCNN / FDnCNN / IRCNN / FFDNet-L1 loops
+# contract (<= 2e-6), the random-weight DRUNet loops do not (max|diff| 0.1-0.8, rel-L2 ~ 8e-3), FFDNet-CNC sits in
+# between (1.4e-3).  Gates follow that: 1e-4 rel-L2 where the loop is stable, a reported bound where it is not.
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def gold50():
+    return np.load(os.path.join(GOLD, 'pnp_golden_50it.npz'))
+
+
+def _img(cs_inputs, name):
+    names = cs_inputs['image_names']
+    return orc.preprocess_uint8(cs_inputs['images'][names.index(name)])
+
+
+def _ircnn_sets(seed0):
+    from pnp_admm_cnc_mri_b200 import denoisers as dn
+    return {str(k): dn.build_model('ircnn_gray', seed=seed0 + k).state_dict() for k in range(25)}
+
+
+STABLE_TOL, CHAOTIC_TOL = 1e-4, 5e-2
+
+
+@pytest.mark.parametrize('key,name,tol', [('l1_dncnn', 'dncnn_15', STABLE_TOL), ('l1_fdncnn', 'fdncnn_gray', STABLE_TOL),
+                                          ('l1_ffdnet', 'ffdnet_gray', STABLE_TOL), ('l1_ircnn', 'ircnn_gray', STABLE_TOL)])
+def test_pnp_l1_presets_50_iterations_vs_unmodified_s3(env, cs_inputs, gold50, key, name, tol):
+    """S3 presets (S3:339-346) of the denoisers its driver does not reach, through the script's own PNP_ADMM_L1_D."""
+    pk, _, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_l1
+    from pnp_admm_cnc_mri_b200.denoisers import Denoiser
+    it, reo = int(gold50[key + '_params'][0]), float(gold50[key + '_params'][1])
+    assert it == 50
+    kw = dict(ircnn_weights=_ircnn_sets(int(gold50['ircnn_seed0']))) if 'ircnn' in name else {}
+    D = Denoiser(name, iter_num=it, x8=False, noises=nz, dtype=torch.float32, seed=0, **kw)
+    x = pnp_admm_l1(_img(cs_inputs, str(gold50['single_image'])), m, nz, D, iter_num=it, reo=reo)
+    e = rel(x, gold50[key])
+    print(f'{key}: 50 iterations, rel-L2 vs unmodified S3 {e:.2e}, max|diff| {np.abs(x - gold50[key]).max():.2e}')
+    assert e < tol
+
+
+@pytest.mark.parametrize('key,name,tol', [('cnc_fdncnn', 'fdncnn_gray', STABLE_TOL), ('cnc_ircnn', 'ircnn_gray', STABLE_TOL),
+                                          ('cnc_ffdnet', 'ffdnet_gray', CHAOTIC_TOL)])
+def test_pnp_cnc_presets_50_iterations_vs_unmodified_s6(env, cs_inputs, gold50, key, name, tol):
+    """S6 presets (S6:569-575) through the script's own PNP_ADMM_CNC_D."""
+    pk, _, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_cnc
+    from pnp_admm_cnc_mri_b200.denoisers import Denoiser
+    a, it, lam, reo, b = (float(v) for v in gold50[key + '_params'])
+    assert it == 50
+    kw = dict(ircnn_weights=_ircnn_sets(int(gold50['ircnn_seed0']))) if 'ircnn' in name else {}
+    D = Denoiser(name, iter_num=int(it), x8=False, noises=nz, dtype=torch.float32, seed=0, **kw)
+    x = pnp_admm_cnc(_img(cs_inputs, str(gold50['single_image'])), m, nz, D, None, alpha=a, iter_num=int(it), lambda1=lam, reo=reo, b=b)
+    e = rel(x, gold50[key])
+    print(f'{key}: 50 iterations, rel-L2 vs unmodified S6 {e:.2e}, max|diff| {np.abs(x - gold50[key]).max():.2e}')
+    assert e < tol
+
+
+def test_pnp_cnc_dncnn_pair_50_iterations_three_images(env, cs_inputs, gold50):
+    """BASELINE config 3's loop at its preset depth: PNP_ADMM_CNC_DnCNN (S6:571: 1.2, 50, 4, 0.45, 0.3) on 05 / 01 / 10.png as
+    ONE batch, float32 denoiser, against the unmodified script; then the same loop with the DnCNN on the tcgen05 kernels
+    (bf16 operands): reported, and bounded at bf16-denoiser accuracy."""
+    pk, _, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_cnc
+    names = [str(s) for s in gold50['images3']]
+    imgs = np.stack([_img(cs_inputs, n) for n in names])
+    P = dict(alpha=1.2, iter_num=50, lambda1=4, reo=0.45, b=0.3)
+    D = _D('dncnn_25', 50, False, nz)
+    x = pnp_admm_cnc(imgs, m, nz, D, D, **P)
+    for k, n in enumerate(names):
+        e = rel(x[k], gold50['cnc_dncnn'][k])
+        print(f'cnc_dncnn {n}: 50 iterations, fp32 denoiser, rel-L2 vs unmodified S6 {e:.2e}')
+        assert e < STABLE_TOL, (n, e)
+    D16 = _D('dncnn_25', 50, False, nz, torch.bfloat16)
+    assert D16.fused is not None
+    x16 = pnp_admm_cnc(imgs, m, nz, D16, D16, **P)
+    for k, n in enumerate(names):
+        e = rel(x16[k], gold50['cnc_dncnn'][k])
+        print(f'cnc_dncnn {n}: 50 iterations, K5 (bf16 tcgen05) denoiser, rel-L2 vs unmodified S6 {e:.2e}')
+        assert e < CHAOTIC_TOL, (n, e)
+
+
+def test_pnp_drunet_50_iterations_three_images(env, cs_inputs, gold50):
+    """S3's own driver (PnP-ADMM-L1, DRUNet, x8 schedule; BASELINE config 4's loop at 256x256) and S6's (PnP-ADMM-CNC, DRUNet) at 50
+    iterations on three images.  A random-weight DRUNet inside the loop amplifies rounding differences (see the header of this
+    block), so the agreement is reported and bounded, not gated at 1e-4; the 3-iteration goldens above gate the same code at 1e-4."""
+    pk, _, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_cnc, pnp_admm_l1
+    names = [str(s) for s in gold50['images3']]
+    imgs = np.stack([_img(cs_inputs, n) for n in names])
+    x = pnp_admm_l1(imgs, m, nz, _D('drunet_gray', 50, True, nz), iter_num=50, reo=0.26)
+    for k, n in enumerate(names):
+        e = rel(x[k], gold50['l1_drunet'][k])
+        print(f'l1_drunet {n}: 50 iterations, rel-L2 vs unmodified S3 {e:.2e}')
+        assert e < CHAOTIC_TOL, (n, e)
+    x = pnp_admm_cnc(imgs, m, nz, _D('drunet_gray', 50, False, nz), None, alpha=1, iter_num=50, lambda1=0.8, reo=0.8, b=0.45)
+    for k, n in enumerate(names):
+        e = rel(x[k], gold50['cnc_drunet'][k])
+        print(f'cnc_drunet {n}: 50 iterations, rel-L2 vs unmodified S6 {e:.2e}')
+        assert e < CHAOTIC_TOL, (n, e)

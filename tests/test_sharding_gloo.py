@@ -43,13 +43,15 @@ def _worker(rank, world, port, B, q):
     def solve(shard, lo, hi):
         return torch.from_numpy(np.stack([orc.admm_cnc(a.numpy(), mask, nz, 0.45, 5, 0.5, 0.05, 64) for a in shard]))
 
-    full = reconstruct_sharded(imgs.double(), solve)
+    # the images arrive as float32 while solve() returns float64: a rank with an empty shard (B < world) must still
+    # contribute a float64 buffer (it used to take the input's dtype and the all_gather failed)
+    full = reconstruct_sharded(imgs.float(), solve, out_dtype=torch.float64, out_device='cpu')
     if rank == 0:
         q.put(full.numpy())
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('B', [5, 8])
+@pytest.mark.parametrize('B', [1, 5, 8])
 def test_world2_gather_equals_single_process(B):
     from oracle import reference_numpy as orc
     from pnp_admm_cnc_mri_b200 import data
@@ -67,5 +69,5 @@ def test_world2_gather_equals_single_process(B):
     imgs = data.phantoms(B, N, seed0=3)
     mask = data.make_mask('random', N, seed=1).astype(np.float64)
     nz = data.make_noise(N, seed=2)
-    want = np.stack([orc.admm_cnc(a.astype(np.float64), mask, nz, 0.45, 5, 0.5, 0.05, 64) for a in imgs])
+    want = np.stack([orc.admm_cnc(a.astype(np.float32), mask, nz, 0.45, 5, 0.5, 0.05, 64) for a in imgs])
     assert got.shape == want.shape and np.array_equal(got, want)
