@@ -8,7 +8,7 @@ alpha 0.45, 50 iterations, lambda 0.5, reo 0.05, b 64) on 64 synthetic 256x256 p
 with one 30 % sampling mask (cartesian / radial / random cycling step by step) and complex
 Gaussian noise.  metric = ADMM iterations/s = images x iter_num / time (whole job, all ranks).
 
-  value     : device-resident images -> acquisition + zero-fill + prepare + 50 iterations, CUDA events
+  value     : device-resident images -> pnpadmm_reconstruct_f32 (acquisition + zero-fill + data term + 50 iterations), CUDA events
   e2e       : same through the host-buffer pipeline (pnp_admm_cnc_mri_b200.HostPipeline over
               pnpadmm_reconstruct_host_pipelined_f32): pinned host uint8 images in, float32
               reconstructions out, copies inside the timed region
@@ -249,8 +249,8 @@ def run_ours(args):
         return float(t.item())
 
     def step_device(i):
-        y = solver.acquire(d_imgs, d_masks[i % 3], d_noise)
-        return solver.solve(y, d_masks[i % 3], 'cnc', CNC['iter_num'], CNC['lambda1'], CNC['reo'], CNC['alpha'], CNC['b'])
+        return solver.reconstruct(d_imgs, d_masks[i % 3], d_noise, 'cnc', CNC['iter_num'], CNC['lambda1'], CNC['reo'], CNC['alpha'],
+                                  CNC['b'])
 
     def step_host(i):
         st = torch.cuda.current_stream().cuda_stream
@@ -335,6 +335,13 @@ def run_ours(args):
     ms_e2e, _ = timed_pipelined(args.steps, args.warmup)
     enq_us = 1e6 * float(np.median(enq_s)) if enq_s else None
     clocks = sampler.stop() if rank == 0 else None
+    # the step per mask kind (the headline cycles through the three): cartesian masks run on the row-separable kernel K3
+    per_mask = {}
+    if full:
+        for mi, kind in enumerate(MASK_KINDS):
+            n_k = max(6, args.steps // 2)
+            per_mask[kind] = timed(lambda i, mi=mi: solver.reconstruct(d_imgs, d_masks[mi], d_noise, 'cnc', CNC['iter_num'], CNC['lambda1'],
+                                                                      CNC['reo'], CNC['alpha'], CNC['b']), n_k, 3) / n_k
 
     sustained = None
     if full:
@@ -393,8 +400,7 @@ def run_ours(args):
             s5 = pk.AdmmSolver(B5, N5)
 
             def solve5():
-                y5 = s5.acquire(im5, m5, n5)
-                return s5.solve(y5, m5, 'cnc', CNC['iter_num'], CNC['lambda1'], CNC['reo'], CNC['alpha'], CNC['b'])
+                return s5.reconstruct(im5, m5, n5, 'cnc', CNC['iter_num'], CNC['lambda1'], CNC['reo'], CNC['alpha'], CNC['b'])
             barrier()
             c5[N5] = dict(B=B5, ms=max_over_ranks(ev_time(solve5, 2, 1)))
             del s5, im5, m5, n5
@@ -469,8 +475,8 @@ def run_ours(args):
     _abi.check(lib.pnpadmm_measure_fp32_peak(fl, None))
     sm, ncl = ctypes.c_int(), ctypes.c_int()
     _abi.check(lib.pnpadmm_device_info(sm, ncl, None, None))
-    pc, ps, ch, la, ls = (ctypes.c_int() for _ in range(5))
-    _abi.check(lib.pnpadmm_plan_info(B, N, 0, CNC['iter_num'], _abi.KERNEL_AUTO, pc, ps, ch, la, ls))
+    pc, ps, ch, la, ls, lr = (ctypes.c_int() for _ in range(6))
+    _abi.check(lib.pnpadmm_plan_info(B, N, 0, CNC['iter_num'], _abi.KERNEL_AUTO, pc, ps, ch, la, ls, lr))
 
     if rank == 0:
         its_step = world * B * CNC['iter_num']
@@ -486,15 +492,17 @@ def run_ours(args):
         nominal_peak = sm.value * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
         cores = os.cpu_count() or 1
         cpu_v, cpu_dt = cpu_throughput(8, 1) if world == 1 else (None, None)
-        launches_dev = la.value + ls.value
+        launches_dev = lr.value
         line = {
             'metric': 'admm_cnc_iterations_per_s', 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'images_per_s': value / CNC['iter_num'],
             'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'iter_num': CNC['iter_num'],
-                       'kernel': f'hybrid: cluster256 (K1, 16-CTA clusters, 2 CTAs/SM) on {pc.value} of the {pc.value + ps.value} packed planes + '
-                                 f'K2 rows2/cols2 for the other {ps.value} on the SMs K1 cannot use; acquisition / zero-fill: K2',
+                       'kernel': f'radial / random steps: hybrid, cluster256 (K1, 16-CTA clusters, 2 CTAs/SM) on {pc.value} of the {pc.value + ps.value} packed '
+                                 f'planes + K2 rows2/cols2 for the other {ps.value} on the SMs K1 cannot use; acquisition / zero-fill / data term fused into '
+                                 'the K1 prologue.  cartesian steps (full k-space lines): rowsep256 (K3), every image row solved on its own, '
+                                 'picked by AdmmSolver.reconstruct / the host entry points when the mask is row-separable',
                        'l2': 'flushed (256 MiB fill) between timed steps', 'sharding': f'batch x{world}, no collective'},
             'e2e': {'value': e2e, 'unit': 'iterations/s', 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(h_img.numel() + h_masks[0].numel() + h_noise.numel() * 4),
@@ -507,11 +515,12 @@ def run_ours(args):
                                   'api': 'pnpadmm_reconstruct_host_f32: one stream, host synchronises after every step '
                                          '(copies not overlapped; single-call latency)'}},
             'gpu_launches': launches_dev * args.steps,
-            'launches_per_step': {'device': launches_dev, 'e2e': launches_dev + 1,
-                                  'source': 'pnpadmm_plan_info (the library reports the launches of acquire + solve for this plan); e2e adds u8_to_unit',
-                                  'kernels': f'acquire {la.value}: rows2<FWD_IMG>, cols2<FWD_ACQ>; solve {ls.value}: cols2<INV>, rows2<INV_ABS>, copy_zero, '
-                                             f'write_cf, prepare, pack_mcode, cluster256 x1 ({pc.value} planes, {ch.value} chunk(s)), and for the K2 share of '
-                                             f'{ps.value} planes rows2<FWD_ZW> x1 + (cols2<BLEND> + rows2<PROX>) x50'},
+            'launches_per_step': {'device': launches_dev, 'e2e': launches_dev + (1 if ps.value else 0),
+                                  'source': 'pnpadmm_plan_info (the library reports the launches of pnpadmm_reconstruct_f32 for this plan)',
+                                  'kernels': f'prepare_shared x1, cluster256 x1 ({pc.value} planes, {ch.value} chunk(s); acquisition, zero-fill and data term fused '
+                                             f'into its prologue); K2 share of {ps.value} planes on the side stream: rows2<FWD_IMG>, cols2<FWD_ACQ>, cols2<INV>, '
+                                             f'rows2<INV_ABS>, copy_zero, prepare, rows2<FWD_ZW> + (cols2<BLEND> + rows2<PROX>) x50 (+ u8_to_unit for its images in e2e); '
+                                             f'unfused acquire + solve would be {la.value} + {ls.value}'},
             'roofline': {'bound': 'fp32', 'kernel': 'cluster256_kernel<16>', 'achieved': achieved, 'peak': nominal_peak,
                          'unit': 'TFLOP/s', 'frac': achieved / nominal_peak, 'traffic': None,
                          'peak_source': f'nominal non-tensor FP32: {sm.value} SMs x 128 lanes x 2 x {sm_max:.0f} MHz '
@@ -531,6 +540,10 @@ def run_ours(args):
                                      'the clusters; same FLOP model, all 148 SMs'}},
             'clocks': clocks,
         }
+        if per_mask:
+            line['step_ms_by_mask'] = dict(per_mask, what='the device step with one mask kind throughout (ms per 64-image x 50-iteration step): cartesian = K3 '
+                                                          'rowsep256 (no column transforms, no transposes; executes about half the nominal FFT work), radial / '
+                                                          'random = K1 + K2 hybrid with the fused prologue')
         if sustained:
             line['sustained'] = {
                 'device': {'value': its_step * sustained['device_steps'] / (sustained['device_ms'] * 1e-3),

@@ -52,6 +52,12 @@ extern "C" {
 #define PNPADMM_KERNEL_AUTO       0    /* cluster kernel when N == 256 && f32, else streaming        */
 #define PNPADMM_KERNEL_CLUSTER    1    /* K1: 8-CTA cluster, state resident in DSMEM (N == 256, f32) */
 #define PNPADMM_KERNEL_STREAMING  2    /* K2: two passes per iteration through L2 / HBM              */
+#define PNPADMM_KERNEL_ROWSEP     3    /* K3 (pnpadmm_reconstruct_f32 / host entry points, N == 256): the caller asserts a
+                                          ROW-SEPARABLE mask, mask[kr][kc] == mask[0][kc] for all kr (full k-space lines, e.g.
+                                          CS_MRI/Q_Cartesian30).  The blend then commutes with the column transforms and every
+                                          image row is solved on its own: no column FFTs, no transposes.  The assertion is
+                                          verified on the device; a mask that violates it yields NaN in x, z, w.  The host
+                                          entry points test h_mask themselves and pick this kernel under KERNEL_AUTO.        */
 
 typedef void* pnpadmm_stream_t;        /* cudaStream_t */
 
@@ -65,9 +71,10 @@ int pnpadmm_device_info(int* sm_count, int* max_clusters_256, int* cc_major, int
 /* How a reconstruction of (B, N, iters) is scheduled on the current device and how many kernels it launches
  * (introspection for benchmarks; nothing is enqueued): packed planes given to the cluster kernel and to the
  * streaming kernels (hybrid schedule at N == 256), chunks of the cluster schedule, kernel launches of one
- * pnpadmm_acquire_f32 and of one pnpadmm_solve_f32.  Any out pointer may be NULL. */
+ * pnpadmm_acquire_f32, one pnpadmm_solve_f32 and one pnpadmm_reconstruct_f32.  Any out pointer may be NULL. */
 int pnpadmm_plan_info(int B, int N, int mask_batched, int iters, int kernel, int* planes_cluster,
-                      int* planes_streaming, int* chunks, int* launches_acquire, int* launches_solve);
+                      int* planes_streaming, int* chunks, int* launches_acquire, int* launches_solve,
+                      int* launches_reconstruct);
 
 /* Bytes of device workspace needed by every call below for (B, N, precision, mask layout). */
 size_t pnpadmm_workspace_bytes(int B, int N, int is_f64, int mask_batched);
@@ -142,6 +149,23 @@ int pnpadmm_solve_f64(const double* y, const uint8_t* mask, double* x, double* z
                       int B, int N, int mask_batched,
                       int prox, int iters, double lambda1, double reo, double alpha, double b,
                       int kernel, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+
+/* Whole reconstruction from IMAGES on the device: what the body of the reference's `for img in L_paths` loop does
+ * (S1:97-132 / S4:101-138), batched:  y = fft2(img) * mask + noises;  x = |ifft2(y)|; z = x; w = 0;  `iters` iterations.
+ *   img [B][N][N] real in [0,1], or (img == NULL) img8 [B][N][N] uint8 gray levels, divided by 255 on the device like
+ *   utils_image.uint2single (utils_image.py:181);  mask, noise as for pnpadmm_acquire_*;  outputs x, z, w [B][N][N].
+ * For N == 256 in f32 with one mask and one noise array for the batch, acquisition, zero-filled start and the data term run
+ * INSIDE the cluster kernel (one preparation launch + one kernel for the whole reconstruction; y is never materialised);
+ * otherwise this is pnpadmm_acquire_* into the workspace followed by pnpadmm_solve_*.  The f64 entry rounds the spectrum
+ * like NumPy >= 2 does for the reference's float32 image (spectrum_f32 = 1 of pnpadmm_acquire_f64). */
+int pnpadmm_reconstruct_f32(const float* img, const uint8_t* img8, const uint8_t* mask, const float* noise,
+                            float* x, float* z, float* w, int B, int N, int mask_batched, int noise_batched,
+                            int prox, int iters, double lambda1, double reo, double alpha, double b,
+                            int kernel, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
+int pnpadmm_reconstruct_f64(const double* img, const uint8_t* img8, const uint8_t* mask, const double* noise,
+                            double* x, double* z, double* w, int B, int N, int mask_batched, int noise_batched,
+                            int prox, int iters, double lambda1, double reo, double alpha, double b,
+                            int kernel, void* ws, size_t ws_bytes, pnpadmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Reference-facing convenience with HOST buffers (what `ADMM_L1(mask, noises, **opts)` /

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(PKG, 'libpnpadmm.so')
 
 OK, ERR_BAD_ARG, ERR_BAD_SIZE, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 PROX_L1, PROX_CNC = 0, 1
-KERNEL_AUTO, KERNEL_CLUSTER, KERNEL_STREAMING = 0, 1, 2
+KERNEL_AUTO, KERNEL_CLUSTER, KERNEL_STREAMING, KERNEL_ROWSEP = 0, 1, 2, 3
 ABI_VERSION = 2
 
 # every symbol include/pnpadmm.h declares (tests check the .so exports all of them)
@@ -20,6 +20,7 @@ SYMBOLS = [
     'pnpadmm_acquire_f32', 'pnpadmm_acquire_f64', 'pnpadmm_zero_filled_f32', 'pnpadmm_zero_filled_f64',
     'pnpadmm_prepare_f32', 'pnpadmm_prepare_f64', 'pnpadmm_xupdate_f32', 'pnpadmm_xupdate_f64',
     'pnpadmm_iterate_f32', 'pnpadmm_iterate_f64', 'pnpadmm_solve_f32', 'pnpadmm_solve_f64',
+    'pnpadmm_reconstruct_f32', 'pnpadmm_reconstruct_f64',
     'pnpadmm_host_scratch_bytes', 'pnpadmm_reconstruct_host_f32',
     'pnpadmm_pipeline_create', 'pnpadmm_pipeline_destroy',
     'pnpadmm_host_pipeline_scratch_bytes', 'pnpadmm_reconstruct_host_pipelined_f32', 'pnpadmm_reconstruct_host_wait',
@@ -54,7 +55,7 @@ def load() -> ctypes.CDLL:
     lib.pnpadmm_device_info.restype = i
     lib.pnpadmm_device_info.argtypes = [POINTER(c_int)] * 4
     lib.pnpadmm_plan_info.restype = i
-    lib.pnpadmm_plan_info.argtypes = [i, i, i, i, i] + [POINTER(c_int)] * 5
+    lib.pnpadmm_plan_info.argtypes = [i, i, i, i, i] + [POINTER(c_int)] * 6
     lib.pnpadmm_workspace_bytes.restype = z
     lib.pnpadmm_workspace_bytes.argtypes = [i, i, i, i]
     lib.pnpadmm_host_scratch_bytes.restype = z
@@ -72,6 +73,8 @@ def load() -> ctypes.CDLL:
         f.argtypes = [p, p, p, i, i, i, i, i, d, d, d, d, i, p, z, p]
         f = getattr(lib, 'pnpadmm_solve_' + sfx); f.restype = i
         f.argtypes = [p, p, p, p, p, i, i, i, i, i, d, d, d, d, i, p, z, p]
+        f = getattr(lib, 'pnpadmm_reconstruct_' + sfx); f.restype = i
+        f.argtypes = [p, p, p, p, p, p, p, i, i, i, i, i, i, d, d, d, d, i, p, z, p]
         f = getattr(lib, 'pnpadmm_soft_' + sfx); f.restype = i
         f.argtypes = [p, p, d, z, p]
         f = getattr(lib, 'pnpadmm_cnc_combine_' + sfx); f.restype = i

@@ -173,6 +173,15 @@ struct ClusterParams {
     int* progress;         // [P][16], zeroed before the launch
     int* queue;            // next unclaimed task, zeroed before the launch
     int dbg;               // timing experiments only (results invalid): 1 = no transposes, 2 = no G staging
+    // Fused prologue (cluster256_core.cuh): the first chunk of a plane starts from the IMAGES instead of (z_in, w_in):
+    // acquisition, zero-filled start and the data term G (written to `Gw` = G, this cluster's own tiles) inside the launch.
+    int fused;
+    const float* img; const uint8_t* img8;   // [B][256][256], one of the two (uint8 gray levels are divided by 255 on load)
+    cf32* Gw;              // writable alias of G
+    const cf32* tiles;     // [3][256][256] NcS, nH, nA in tile order (prepare_shared_kernel)
+    const uint32_t* mhere; // [16][256] m[k] bits of each column-phase thread's 16 bins
+    float cf1v, cf2v;      // residual coefficients by value
+    int no_memset;         // the hand-off counters + task queue were zeroed by the preparation launch
     int rot;               // rotate the transpose destinations per rank (PNPADMM_K1_ROT, default 0)
     int spin;              // polls of a tile barrier before the waiting warp goes to sleep (PNPADMM_K1_SPIN, default 0)
 };
@@ -183,6 +192,18 @@ __global__ void pack_mcode_k1_kernel(const uint8_t* __restrict__ mcode, uint32_t
     if (i >= planes * 16 * kN) return;
     const int plane = i / (16 * kN), r = i - plane * 16 * kN;
     mpack[i] = pack_codes(mcode + (size_t)plane * kN * kN, r / kN, r % kN);
+}
+
+// (mask, noise, reo) -> noise-term tiles + packed codes + m[k] bits for the fused prologue: 4096 threads, one per word.
+__global__ void prepare_shared_kernel(const uint8_t* __restrict__ mask, const cf32* __restrict__ noise, int R, float g_over_n2,
+                                      cf32* __restrict__ tiles, uint32_t* __restrict__ mpack, uint32_t* __restrict__ mhere,
+                                      uint8_t* __restrict__ mcode, int* __restrict__ zero_ints, int n_zero,
+                                      float* __restrict__ cf_out, float c1, float c2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = i; k < n_zero; k += gridDim.x * blockDim.x) zero_ints[k] = 0;   // hand-off counters + task queue of the launch that follows
+    if (i == 0) { cf_out[0] = 0.f; cf_out[1] = c1; cf_out[2] = c2; }             // coefficient table of the streaming kernels
+    if (i >= 16 * kN) return;
+    prepare_shared_word(mask, noise, R, g_over_n2, i / kN, i % kN, tiles, mpack, mhere, mcode);
 }
 
 // Cluster shape comes from the launch attribute (cudaLaunchAttributeClusterDimension = CL).
@@ -219,7 +240,7 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
 #else
     constexpr int dbg = 0;
 #endif
-    const float cf1 = p.cf[1], cf2 = p.cf[2];
+    const float cf1 = p.fused ? p.cf1v : p.cf[1], cf2 = p.fused ? p.cf2v : p.cf[2];
     uint32_t nFull1 = 0, nFull2 = 0, nG = 0, nFree1 = 0, nFree2 = 0;   // completed uses (phase parity)
     ThreadState s;
     const size_t nn = (size_t)kN * kN;
@@ -290,8 +311,76 @@ __global__ void __launch_bounds__(Geo<CL>::kThreads, Geo<CL>::kCtasPerSm) cluste
             ++nFree2;
         };
 
-        // ---- prologue: first forward row FFT of z - w
-        row_load_state(c, s, io);
+        if (p.fused && chunk == 0) {
+            // ---- fused prologue: acquisition, zero-filled start and G from the images (see cluster256_core.cuh)
+            const float hb = has_b ? 1.f : 0.f;
+            cf32* Gw = p.Gw + plane * nn + (size_t)c.rank * (kTileBytes / 8);
+            const cf32* tl = p.tiles + (size_t)c.rank * (kTileBytes / 8);
+            cf32* Fsave = c.Zs();                          // idle until z exists
+            // R0: packed image rows -> forward row FFT -> transpose
+            row_load_image(c, s, p.img ? p.img + ia * nn : nullptr, (p.img && has_b) ? p.img + (ia + 1) * nn : nullptr,
+                           p.img8 ? p.img8 + ia * nn : nullptr, (p.img8 && has_b) ? p.img8 + (ia + 1) * nn : nullptr);
+            row_step1_write<false>(c, s);
+            __syncwarp();
+            row_read_step2<false>(c, s);
+            wait_free2();
+            row_store_remote(c, s, R);
+            // C0: F = column FFT; save F, write G, inverse column FFT of the ms branch -> transpose
+            const int wi = c.ct() * kN + kRows * c.rank + c.cc();
+            const uint32_t codes0 = mpack[wi], here0 = p.mhere[wi];
+            if (threadIdx.x == 0) mbar_arm_tx(bFull2, kTileBytes);
+            mbar_wait(bFull2, nFull2 & 1); ++nFull2;
+            col_load(c, s);
+            __syncthreads();
+            col_step1_write<false>(c, s);
+            __syncthreads();
+            col_read_step2<false>(c, s);
+            col_acquire_ms(c, s, Fsave, Gw, tl, tl + nn, codes0, cf1, cf2, hb);
+            asm volatile("fence.proxy.async;" ::: "memory");   // G (generic stores) is read back by bulk copies (async proxy)
+            __syncthreads();
+            if (threadIdx.x < kCluster) mbar_arrive_remote(mapa(bFree1, threadIdx.x));   // R0 is over: this CTA's B1 is free
+            col_step1_write<true>(c, s);
+            __syncthreads();
+            col_read_step2<true>(c, s);
+            mbar_wait(bFree1, nFree1 & 1); ++nFree1;       // (no FREE2 signal: B2 stays this CTA's scratch through C1)
+            col_store_remote(c, s, R);
+            // R1: T1 = inverse row FFT, kept in the dual's registers
+            if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
+            mbar_wait(bFull1, nFull1 & 1); ++nFull1;
+            row_load(c, s);
+            __syncwarp();
+            row_step1_write<true>(c, s);
+            __syncwarp();
+            row_read_step2<true>(c, s);
+            row_stash_t1(s);
+            // C1: inverse column FFT of the ma branch -> transpose
+            __syncthreads();                               // every warp has left R1: B1 is free again
+            if (threadIdx.x < kCluster) mbar_arrive_remote(mapa(bFree1, threadIdx.x));
+            col_acquire_ma(c, s, Fsave, tl + 2 * nn, codes0, here0, hb);
+            col_step1_write<true>(c, s);
+            __syncthreads();
+            col_read_step2<true>(c, s);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane < kCluster) mbar_arrive_remote(mapa(bFree2, lane));   // this warp no longer reads B2
+            mbar_wait(bFree1, nFree1 & 1); ++nFree1;
+            col_store_remote(c, s, R);
+            // R2: T2 = inverse row FFT; z = x0 = |ifft2(y)|, w = 0; then the loop's first forward row FFT
+            if (threadIdx.x == 0) mbar_arm_tx(bFull1, kTileBytes);
+            mbar_wait(bFull1, nFull1 & 1); ++nFull1;
+            row_load(c, s);
+            __syncwarp();
+            row_step1_write<true>(c, s);
+            __syncwarp();
+            row_read_step2<true>(c, s);
+            __syncthreads();                               // F (in Zs) was last read in C1 by every warp before this point
+            row_zero_fill(c, s, 1.0f / (float)(kN * kN), has_b);
+        } else {
+            // ---- prologue: state from the caller (or from the cluster that ran the previous chunk)
+            row_load_state(c, s, io);
+        }
+        // first forward row FFT of z - w
+        __syncwarp();
         row_step1_write<false>(c, s);
         __syncwarp();
         row_read_step2<false>(c, s);

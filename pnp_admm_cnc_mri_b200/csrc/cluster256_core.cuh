@@ -346,6 +346,206 @@ PNP_HD void col_store_remote(const Ctx<CL>& c, const ThreadState& s, const Remot
 // With tid = 16 row + t (row phases) = 16 t + c (column phases) every access below is `base + 256 j + tid`: a warp
 // touches 256 contiguous bytes.  A warp's row-FFT scratch is its own 16 input chunks (256 B in each peer block).
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Fused prologue: acquisition (S1:99), zero-filled start (S1:100-105) and the data term of the blend, inside the solve.
+// With F = fft2(a + i b) of the two real images of a plane, m' the mirrored mask, ms = (m + m') / 2, ma = (m - m') / 2
+// and the noise split into its Hermitian / anti-Hermitian parts nH = (n[k] + conj n[-k]) / 2, nA = (n[k] - conj n[-k]) / 2:
+//     G  = cf .* F + (1 + i) NcS,  NcS = g / N^2 * (m n[k] + m' conj n[-k]) / 2        (the term prepare_kernel builds from y)
+//     T1 = ifft2_unnormalised(ms .* F + (1 + i) nH) = (Re ifft2 y_a) + i (Re ifft2 y_b)
+//     T2 = ifft2_unnormalised(ma .* F + (1 + i) nA) = -(Im ifft2 y_b) + i (Im ifft2 y_a)
+//     x0_a = |Re T1 + i Im T2| / N^2,   x0_b = |Im T1 - i Re T2| / N^2                  (= |ifft2(y)|, y never materialised)
+// because a real image times a symmetric (antisymmetric) real mask has a real (imaginary) inverse transform.  NcS, nH, nA
+// depend on (mask, noise, reo) only and come from prepare_shared_kernel in this kernel's tile order.  A plane with one
+// image (odd batch) uses (1 + 0 i) instead of (1 + i): its imaginary slot stays exactly zero.
+// Phases: R0 image rows -> row FFT -> transpose;  C0 col FFT = F, save F (in the idle Zs tile), write G, col IFFT of the
+// ms branch -> transpose;  R1 row IFFT = T1, stashed in the dual's registers;  C1 reload F, col IFFT of the ma branch ->
+// transpose;  R2 row IFFT = T2, z = x0, w = 0, then the first forward row FFT of the loop.
+// ---------------------------------------------------------------------------------------------
+PNP_HD float unit_from_u8(uint8_t v) { return (float)v / 255.0f; }   // utils_image.uint2single: np.float32(img / 255.)
+
+template <int CL>
+PNP_HD void row_load_image(const Ctx<CL>& c, ThreadState& s, const float* fa, const float* fb, const uint8_t* ua, const uint8_t* ub) {
+    const int row = c.row(), t = c.rt();
+    const int g0 = (Geo<CL>::kRows * c.rank + row) * kN;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int n = g0 + t + 16 * j;
+        const float a = fa ? fa[n] : unit_from_u8(ua[n]);
+        const float b = fb ? fb[n] : (ub ? unit_from_u8(ub[n]) : 0.f);
+        s.a[j] = mk<float>(a, b);
+    }
+}
+
+// tile-order index of this thread's j-th point in a column phase (G / noise-term tiles, F save area)
+template <int CL> PNP_HD int col_tile_index(const Ctx<CL>& c, int j) { return c.ct() * Geo<CL>::kRows + c.cc() + 16 * j * Geo<CL>::kRows; }
+
+// C0: s.a holds F.  hb = 1 if the plane has a second image, else 0.
+template <int CL>
+PNP_HD void col_acquire_ms(const Ctx<CL>& c, ThreadState& s, cf32* Fsave, cf32* Gtile, const cf32* NcS, const cf32* nH,
+                           uint32_t codes, float cf1, float cf2, float hb) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int i = col_tile_index(c, j);
+        const cf32 F = s.a[j];
+        Fsave[i] = F;
+        const uint32_t code = (codes >> (2 * j)) & 3u;
+        const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
+        const cf32 nc = NcS[i], nh = nH[i];
+        Gtile[i] = mk<float>(cf * F.re + (nc.re - hb * nc.im), cf * F.im + (nc.im + hb * nc.re));
+        const float ms = 0.5f * (float)code;
+        s.a[j] = mk<float>(ms * F.re + (nh.re - hb * nh.im), ms * F.im + (nh.im + hb * nh.re));
+    }
+}
+
+// C1: reload F; ma = m[k] - (m[k] + m[-k]) / 2;  `here` bit j = m[k] of the thread's j-th bin
+template <int CL>
+PNP_HD void col_acquire_ma(const Ctx<CL>& c, ThreadState& s, const cf32* Fsave, const cf32* nA, uint32_t codes, uint32_t here, float hb) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int i = col_tile_index(c, j);
+        const cf32 F = Fsave[i];
+        const uint32_t code = (codes >> (2 * j)) & 3u;
+        const float ma = (float)((here >> j) & 1u) - 0.5f * (float)code;
+        const cf32 na = nA[i];
+        s.a[j] = mk<float>(ma * F.re + (na.re - hb * na.im), ma * F.im + (na.im + hb * na.re));
+    }
+}
+
+// R1: T1 -> the dual's registers (w is zero until the loop starts)
+PNP_HD void row_stash_t1(ThreadState& s) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { s.w[2 * j] = s.a[j].re; s.w[2 * j + 1] = s.a[j].im; }
+}
+
+// R2: s.a = T2.  z = x0 = |ifft2(y)|, w = 0, a = z - w
+template <int CL>
+PNP_HD void row_zero_fill(const Ctx<CL>& c, ThreadState& s, float inv_n2, bool has_b) {
+    cf32* Zs = c.Zs() + c.row() * kN;
+    const int t = c.rt();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float t1r = s.w[2 * j], t1i = s.w[2 * j + 1];
+        const float xa = psqrt(t1r * t1r + s.a[j].im * s.a[j].im) * inv_n2;
+        const float xb = has_b ? psqrt(t1i * t1i + s.a[j].re * s.a[j].re) * inv_n2 : 0.f;
+        const cf32 z = mk<float>(xa, xb);
+        Zs[t + 16 * j] = z;
+        s.w[2 * j] = 0.f; s.w[2 * j + 1] = 0.f;
+        s.a[j] = z;
+    }
+}
+
+// (mask, noise, reo) -> the three noise-term tiles, packed codes and the m[k] bits, one thread per (t, kc) word.
+// tiles: [3][rank][kr][c] (NcS, nH, nA);  mpack / mhere: [16][256] words.
+PNP_HD void prepare_shared_word(const uint8_t* mask, const cf32* noise, int R, float g_over_n2, int t, int kc, cf32* tiles,
+                                uint32_t* mpack, uint32_t* mhere, uint8_t* mcode) {
+    uint32_t codes = 0, here = 0;
+    const int mkc = (kN - kc) & (kN - 1);
+    for (int j = 0; j < 16; ++j) {
+        const int kr = t + 16 * j, mkr = (kN - kr) & (kN - 1);
+        const int bin = kr * kN + kc, mbin = mkr * kN + mkc;
+        const float m1 = mask[bin] ? 1.f : 0.f, m2 = mask[mbin] ? 1.f : 0.f;
+        const cf32 n1 = noise[bin], n2 = noise[mbin];
+        const uint32_t code = (uint32_t)(m1 + m2);
+        codes |= code << (2 * j);
+        here |= (uint32_t)m1 << j;
+        if (mcode) mcode[bin] = (uint8_t)code;
+        const int i = g_tiled_elem(R, kr, kc);
+        tiles[i] = mk<float>(g_over_n2 * 0.5f * (m1 * n1.re + m2 * n2.re), g_over_n2 * 0.5f * (m1 * n1.im - m2 * n2.im));
+        tiles[kN * kN + i] = mk<float>(0.5f * (n1.re + n2.re), 0.5f * (n1.im - n2.im));
+        tiles[2 * kN * kN + i] = mk<float>(0.5f * (n1.re - n2.re), 0.5f * (n1.im + n2.im));
+    }
+    mpack[t * kN + kc] = codes;
+    mhere[t * kN + kc] = here;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-separable masks (K3, rowsep256.cuh): when the sampling pattern consists of full k-space lines, m[kr][kc] = m(kc)
+// (CS_MRI/Q_Cartesian30: 76 full columns), the blend coefficient depends on kc only and therefore commutes with the
+// column transforms:   ifft2(G - cf .* fft2 V) = rowIFFT( colIFFT(G) - N cf(kc) .* rowFFT(V) ).
+// Every image row then is an independent 1-D problem for the whole solve: no column FFTs, no transposes, no cluster.  The
+// same holds for the fused prologue (ms, ma depend on kc only and colIFFT(colFFT(.)) = N):
+//     G'  = colIFFT(G)  = N cf(kc) A0 + (1 + i hb) NcS',    A0 = rowFFT(image row pair),   X' = colIFFT_unnormalised(X)
+//     T1  = rowIFFT(N ms(kc) A0 + (1 + i hb) nH'),  T2 = rowIFFT(N ma(kc) A0 + (1 + i hb) nA'),  x0 as in the fused prologue / N^2
+// A CTA of 256 threads owns 16 consecutive rows of a plane and reuses the row-phase code above with the Geo<16> shared
+// memory layout: Zs = z rows, B1 = exchange scratch, B2 = the rows of G' ([16][256], resident for the whole solve).
+// Thread (row, t) handles kc = t + 16 j: its 16 codes / m[k] bits are one word each (rcodes[t], rhere[t]).
+// ---------------------------------------------------------------------------------------------
+// prologue after A0 = rowFFT(image rows): keep A0 (in Zs), write G' (B2), leave the ms branch in s.a
+PNP_HD void rsep_acquire_ms(const Ctx<16>& c, ThreadState& s, const cf32* NcSp, const cf32* nHp, uint32_t codes, float ncf1, float ncf2,
+                            float hb) {
+    const int row = c.row(), t = c.rt();
+    cf32* A0 = c.Zs() + row * kN;
+    cf32* Gp = c.B2() + row * kN;
+    const int g0 = (16 * c.rank + row) * kN;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int n = t + 16 * j;
+        const cf32 F = s.a[j];
+        A0[n] = F;
+        const uint32_t code = (codes >> (2 * j)) & 3u;
+        const float cf = code == 0 ? 0.f : (code == 1 ? ncf1 : ncf2);
+        const cf32 nc = NcSp[g0 + n], nh = nHp[g0 + n];
+        Gp[n] = mk<float>(cf * F.re + (nc.re - hb * nc.im), cf * F.im + (nc.im + hb * nc.re));
+        const float ms = (0.5f * (float)kN) * (float)code;
+        s.a[j] = mk<float>(ms * F.re + (nh.re - hb * nh.im), ms * F.im + (nh.im + hb * nh.re));
+    }
+}
+
+PNP_HD void rsep_acquire_ma(const Ctx<16>& c, ThreadState& s, const cf32* nAp, uint32_t codes, uint32_t here, float hb) {
+    const int row = c.row(), t = c.rt();
+    const cf32* A0 = c.Zs() + row * kN;
+    const int g0 = (16 * c.rank + row) * kN;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int n = t + 16 * j;
+        const cf32 F = A0[n];
+        const uint32_t code = (codes >> (2 * j)) & 3u;
+        const float ma = (float)kN * ((float)((here >> j) & 1u) - 0.5f * (float)code);
+        const cf32 na = nAp[g0 + n];
+        s.a[j] = mk<float>(ma * F.re + (na.re - hb * na.im), ma * F.im + (na.im + hb * na.re));
+    }
+}
+
+// the residual blend of a row: a = G' - N cf(kc) a
+PNP_HD void rsep_blend(const Ctx<16>& c, ThreadState& s, uint32_t codes, float ncf1, float ncf2) {
+    const cf32* Gp = c.B2() + c.row() * kN + c.rt();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const cf32 gg = Gp[16 * j];
+        const uint32_t code = (codes >> (2 * j)) & 3u;
+        const float cf = code == 0 ? 0.f : (code == 1 ? ncf1 : ncf2);
+        s.a[j] = mk<float>(gg.re - cf * s.a[j].re, gg.im - cf * s.a[j].im);
+    }
+}
+
+// Preparation for K3, thread kc of 256: is the mask the same on every k-space row?  codes / m[k] words of the 16 row-phase
+// thread classes, and the noise-term planes in ROW-major order [3][256][256] (input of the column inverse transform).
+PNP_HD bool rsep_column_is_constant(const uint8_t* mask, int kc) {
+    const bool m0 = mask[kc] != 0;
+    for (int kr = 1; kr < kN; ++kr)
+        if ((mask[kr * kN + kc] != 0) != m0) return false;
+    return true;
+}
+PNP_HD void rsep_words(const uint8_t* mask, int t, uint32_t* codes, uint32_t* here) {
+    uint32_t cw = 0, hw = 0;
+    for (int j = 0; j < 16; ++j) {
+        const int kc = t + 16 * j, mkc = (kN - kc) & (kN - 1);
+        const uint32_t m1 = mask[kc] ? 1u : 0u, m2 = mask[mkc] ? 1u : 0u;     // row 0 speaks for every row (checked separately)
+        cw |= (m1 + m2) << (2 * j);
+        hw |= m1 << j;
+    }
+    *codes = cw; *here = hw;
+}
+PNP_HD void rsep_noise_terms(const uint8_t* mask, const cf32* noise, float g_over_n2, int bin, cf32* planes) {
+    const int kr = bin / kN, kc = bin % kN;
+    const int mbin = ((kN - kr) & (kN - 1)) * kN + ((kN - kc) & (kN - 1));
+    const float m1 = mask[bin] ? 1.f : 0.f, m2 = mask[mbin] ? 1.f : 0.f;
+    const cf32 n1 = noise[bin], n2 = noise[mbin];
+    planes[bin] = mk<float>(g_over_n2 * 0.5f * (m1 * n1.re + m2 * n2.re), g_over_n2 * 0.5f * (m1 * n1.im - m2 * n2.im));
+    planes[kN * kN + bin] = mk<float>(0.5f * (n1.re + n2.re), 0.5f * (n1.im - n2.im));
+    planes[2 * kN * kN + bin] = mk<float>(0.5f * (n1.re - n2.re), 0.5f * (n1.im + n2.im));
+}
+
 #if defined(__CUDA_ARCH__)
 PNP_D cf32 ld_g(const cf32* p) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return mk<float>(v.x, v.y); }
 #else

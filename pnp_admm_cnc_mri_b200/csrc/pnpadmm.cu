@@ -13,6 +13,7 @@
 
 #include "../../include/pnpadmm.h"
 #include "cluster256.cuh"
+#include "rowsep256.cuh"
 #include "streaming.cuh"
 #include "stream2.cuh"
 #include "metrics.cuh"
@@ -59,6 +60,12 @@ struct DeviceState {
     cudaStream_t side = nullptr;  // hybrid schedule: the K2 share of a batch runs here, beside K1
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;   // fork / join of the hybrid schedule (created once, with the side stream)
     std::mutex mu;                // guards the side stream's fork/join pairs and this device's K2 graph cache
+    // timing model of the hybrid schedule, measured once per device by calibrate_hybrid() (literals = fallback, round-1 B200 fit)
+    double tau1_us = 10.1;        // K1: one plane-iteration of one cluster, all clusters busy
+    double k2_a_us = 11.0;        // K2 on the SMs outside the clusters, beside a running K1: per iteration, fixed part ...
+    double k2_b_us = 2.7;         // ... and per plane
+    double k2_pro_us = 45.0;      // K2 share of a fused reconstruct: its own acquisition / zero-fill / prepare launches
+    bool calibrated = false;
 };
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
@@ -251,6 +258,8 @@ int probe_clusters(int sm_count) {
     return ncl;
 }
 
+void calibrate_hybrid(DeviceState* d);
+
 int ensure_device(DeviceState** out) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -282,6 +291,7 @@ int ensure_device(DeviceState** out) {
         CUDA_TRY(set_stream_attrs<float>());
         CUDA_TRY(set_stream_attrs<double>());
         CUDA_TRY(S2<float>::set_attrs());
+        CUDA_TRY(cudaFuncSetAttribute(k3::rowsep256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1::Geo<16>::kSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(metrics_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(tc::conv64_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
@@ -305,6 +315,7 @@ int ensure_device(DeviceState** out) {
         CUDA_TRY(cudaEventCreateWithFlags(&d.fork_ev, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&d.join_ev, cudaEventDisableTiming));
         d.ready = true;
+        calibrate_hybrid(&d);     // best effort: the literals stay if it cannot run
     }
     *out = &d;
     return PNPADMM_OK;
@@ -323,6 +334,10 @@ struct Workspace {
     uint32_t* mpack;  // N == 256 only: [16][256] or [P][16][256] packed codes for the cluster kernel
     cx<T>* Gt;        // N == 256 fp32 only: G in the cluster kernel's tile order [P][rank][256][R]
     int* progress;    // [P][8] hand-off counters of the chunked cluster schedule
+    cx<T>* Y;         // [B][N][N] measurements of the reconstruct entry points (acquisition output when it is not fused away)
+    cx<T>* tiles;     // N == 256 fp32 only: [6][N][N]: noise-term tiles of the fused prologue (NcS, nH, nA); K3 uses [0,3) as the
+                      // row-major terms and [3,6) as their column inverse transforms
+    uint32_t* mhere;  // N == 256 fp32 only: [16][256] m[k] bits; K3: rcodes [16] | rhere [16] | separability count
     int P, solo;
 };
 
@@ -337,6 +352,8 @@ size_t ws_bytes_impl(int B, int N, size_t elt, int mask_batched) {
     s += align_up((mask_batched ? P : 1) * nn / 4);   // packed codes (2 bits per bin, 32-bit words)
     s += align_up((P * 16 + 16) * sizeof(int));       // progress counters [P][<=16 ranks] + task queue
     if (N == 256 && elt == 4) s += align_up(P * nn * 2 * elt);   // Gt (cluster kernel)
+    s += align_up((size_t)B * nn * 2 * elt);                     // Y
+    if (N == 256 && elt == 4) s += align_up(6 * nn * 2 * elt) + align_up(16 * 256 * sizeof(uint32_t));   // fused prologue / K3
     return s;
 }
 
@@ -360,6 +377,15 @@ int carve(void* ws, size_t ws_bytes, int B, int N, int mask_batched, Workspace<T
     out->mpack = (uint32_t*)p; p += align_up((mask_batched ? P : 1) * nn / 4);
     out->progress = (int*)p; p += align_up((P * 16 + 16) * sizeof(int));
     out->Gt = (N == 256 && sizeof(T) == 4) ? (cx<T>*)p : nullptr;
+    if (out->Gt) p += align_up(P * nn * 2 * sizeof(T));
+    out->Y = nullptr; out->tiles = nullptr; out->mhere = nullptr;
+    if (!scratch_only) {
+        out->Y = (cx<T>*)p; p += align_up((size_t)B * nn * 2 * sizeof(T));
+        if (N == 256 && sizeof(T) == 4) {
+            out->tiles = (cx<T>*)p; p += align_up(6 * nn * 2 * sizeof(T));
+            out->mhere = (uint32_t*)p;
+        }
+    }
     out->P = (int)P;
     out->solo = mask_batched ? 1 : 0;
     return PNPADMM_OK;
@@ -496,7 +522,14 @@ int prepare_impl(const T* y, const uint8_t* mask, int B, int N, int mask_batched
     return PNPADMM_OK;
 }
 
-int pick_kernel(int kernel, int N, bool f64, const DeviceState* d, bool* use_cluster) {
+int pick_kernel(int kernel, int N, bool f64, const DeviceState* d, bool* use_cluster, bool allow_rowsep = false) {
+    if (kernel == PNPADMM_KERNEL_ROWSEP) {
+        if (!allow_rowsep || N != 256 || f64)
+            return fail(PNPADMM_ERR_UNSUPPORTED, "the row-separable kernel serves pnpadmm_reconstruct_f32 / the host entry points at N == 256 "
+                        "with one mask and one noise array for the batch (N=%d, f64=%d)", N, (int)f64);
+        *use_cluster = false;
+        return PNPADMM_OK;
+    }
     if (kernel != PNPADMM_KERNEL_AUTO && kernel != PNPADMM_KERNEL_CLUSTER && kernel != PNPADMM_KERNEL_STREAMING)
         return fail(PNPADMM_ERR_BAD_ARG, "unknown kernel selector %d", kernel);
     const bool can = (N == 256) && !f64 && d->max_clusters_256 > 0;
@@ -507,11 +540,16 @@ int pick_kernel(int kernel, int N, bool f64, const DeviceState* d, bool* use_clu
     return PNPADMM_OK;
 }
 
+// What a chunk boundary costs, in iteration-times: the plane's z, w go through L2, the pipeline of phases drains and refills
+// (state reload + first row FFT + first transposes).  Round 2, B200: 29 planes in 10 chunks on 14 clusters take 1.236 ms
+// = 21 steps x (5 + 1.0) x 9.82 us; the round-1 value 0.35 made the planner prefer such schedules to whole rounds.
+constexpr double kChunkHandoff = 1.0;
+
 // Pick the chunking of the static cluster schedule: minimise ceil(P n / ncl) * (ceil(iters / n) + hand-off).
 void plan_chunks(int P, int iters, int max_clusters, int* chunk, int* n_chunks) {
     *chunk = iters; *n_chunks = 1;
     if (P <= max_clusters || P % max_clusters == 0 || iters < 2) return;
-    const double handoff = 0.35;   // iterations' worth of time to spill + reload a plane's z, w through L2
+    const double handoff = kChunkHandoff;   // iterations' worth of time a chunk boundary costs
     double best = 1e30;
     for (int n = 1; n <= 10 && n <= iters; ++n) {
         const int c = (iters + n - 1) / n, nn = (iters + c - 1) / c;
@@ -536,7 +574,7 @@ int launch_cluster_t(k1::ClusterParams& cp, int max_clusters, cudaStream_t st) {
         const int n = atoi(e);
         if (n >= 1 && n <= cp.iters) { cp.chunk = (cp.iters + n - 1) / n; cp.n_chunks = (cp.iters + cp.chunk - 1) / cp.chunk; }
     }
-    CUDA_TRY(cudaMemsetAsync(cp.progress, 0, sizeof(int) * (cp.P * 16 + 16), st));   // hand-off counters + task queue
+    if (!cp.no_memset) CUDA_TRY(cudaMemsetAsync(cp.progress, 0, sizeof(int) * (cp.P * 16 + 16), st));   // hand-off counters + task queue
     cp.queue = cp.progress + cp.P * 16;
     const long ntasks = (long)cp.P * cp.n_chunks;
     int ncl = ntasks < max_clusters ? (int)ntasks : max_clusters;
@@ -731,7 +769,7 @@ int stream2_iterate(const Workspace<T>& w, T* x, T* z, T* wv, int B, int N, cons
 // on the SMs K1 leaves free.  Returns P1 (== P: no split).  Model (fitted on B200, tools/k1_bench.py sweeps in
 // profiles/r1_experiments.txt): K1 takes tau1 = 10.1 us per plane-iteration and cluster; K2 on the leftover
 // SMs takes 11 + 2.7 p2 us per iteration for p2 planes (one wave of `cap` planes has a 21 us latency floor).
-int plan_hybrid(const DeviceState* d, int P, int iters) {
+int plan_hybrid(const DeviceState* d, int P, int iters, bool fused = false) {
     static const char* off = getenv("PNPADMM_NO_HYBRID");
     if (off && atoi(off) != 0) return P;
     const int ncl = d->max_clusters_256;
@@ -742,18 +780,84 @@ int plan_hybrid(const DeviceState* d, int P, int iters) {
         const int p2 = atoi(e);
         return (p2 >= 0 && p2 < P) ? P - p2 : P;
     }
-    const double tau1 = 10.1, handoff = 0.35, scale = (double)cap / 4.0;   // constants measured with 36 SMs left (cap = 4)
+    // per-device constants (calibrate_hybrid); a fused reconstruct adds the prologue to both shares: ~1.5 iteration-times per plane
+    // on K1 (three extra row phases, two column phases), a handful of small launches on the K2 side
+    const double tau1 = d->tau1_us, handoff = kChunkHandoff;
     double best = 1e30; int best_p2 = 0;
     for (int p2 = 0; p2 <= P - ncl && p2 <= P / 3; ++p2) {
         const int p1 = P - p2;
         int chunk, nch; plan_chunks(p1, iters, ncl, &chunk, &nch);
         const long steps = ((long)p1 * nch + ncl - 1) / ncl;
-        const double t1 = steps * (chunk + (nch > 1 ? handoff : 0.0)) * tau1;
-        const double t2 = p2 ? (double)iters * (11.0 + 2.7 * p2 / scale) : 0.0;
+        const long rounds = ((long)p1 + ncl - 1) / ncl;
+        const double t1 = (steps * (chunk + (nch > 1 ? handoff : 0.0)) + (fused ? 1.5 * rounds : 0.0)) * tau1;
+        const double t2 = p2 ? (double)iters * (d->k2_a_us + d->k2_b_us * p2) + (fused ? d->k2_pro_us : 0.0) : 0.0;
         const double t = t1 > t2 ? t1 : t2;
         if (t < best - 1e-9) { best = t; best_p2 = p2; }
     }
     return P - best_p2;
+}
+
+// Measure the constants of the hybrid planner on this device (first use of the library on it; PNPADMM_NO_CALIBRATE=1 keeps the
+// literals): K1's time per plane-iteration with every resident cluster busy (two run lengths, the difference removes the launch
+// and the prologue), and K2's time per iteration for `cap` and 2 `cap` planes on the SMs outside the clusters WHILE a long K1 run
+// occupies the rest (the situation the planner models).  Zero-filled scratch problem: the kernels' timing does not depend on data.
+void calibrate_hybrid(DeviceState* d) {
+    static const bool off = [] { const char* e = getenv("PNPADMM_NO_CALIBRATE"); return e && atoi(e) != 0; }();
+    const int ncl = d->max_clusters_256, left = d->sm_count - 8 * ncl, cap = left / 8;
+    if (off || ncl <= 0 || cap < 1) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(cudaStreamPerThread, &cs) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    const int N = k1::kN, P = ncl + 2 * cap, B = 2 * P;
+    const size_t nn = (size_t)N * N, wsb = ws_bytes_impl(B, N, 4, 0), sb = (size_t)B * nn * 4;
+    unsigned char* buf = nullptr;
+    cudaStream_t sa = nullptr, sbm = nullptr;
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ok = cudaMalloc(&buf, wsb + 3 * sb) == cudaSuccess && cudaMemset(buf, 0, wsb + 3 * sb) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&sbm, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&e[i]) == cudaSuccess;
+    Workspace<float> w;
+    ok = ok && carve<float>(buf, wsb, B, N, 0, &w) == PNPADMM_OK;
+    if (ok) {
+        float* x = reinterpret_cast<float*>(buf + wsb); float* z = x + (size_t)B * nn; float* wv = z + (size_t)B * nn;
+        const ProxParams<float> pp = make_prox<float>(PROX_CNC, 0.5, 0.05, 0.45, 64.0);
+        auto k1_run = [&](int planes, int iters, cudaStream_t st) {
+            Workspace<float> w1 = w; w1.P = planes;
+            return ClusterDispatch<float>::run(w1, z, wv, x, z, wv, nullptr, 2 * planes, iters, pp, d, st);
+        };
+        auto ms = [&](cudaEvent_t a, cudaEvent_t b) { float t = 0.f; return cudaEventElapsedTime(&t, a, b) == cudaSuccess ? (double)t : -1.0; };
+        // K1: ncl planes (one per cluster), 8 and 24 iterations
+        ok = k1_run(ncl, 8, sa) == PNPADMM_OK;                                         // warm-up
+        double t8 = -1, t24 = -1;
+        if (ok) { cudaEventRecord(e[0], sa); ok = k1_run(ncl, 8, sa) == PNPADMM_OK; cudaEventRecord(e[1], sa); }
+        if (ok) { cudaEventRecord(e[2], sa); ok = k1_run(ncl, 24, sa) == PNPADMM_OK; cudaEventRecord(e[3], sa); }
+        if (ok && cudaStreamSynchronize(sa) == cudaSuccess) { t8 = ms(e[0], e[1]); t24 = ms(e[2], e[3]); }
+        const double tau1 = (t24 - t8) * 1e3 / 16.0;
+        // K2 beside a running K1: planes [ncl, ncl + cap) and [ncl, ncl + 2 cap), 16 iterations each
+        double ta = -1, tb = -1;
+        if (ok && S2<float>::ok(N)) {
+            StreamParams<float> p = base_params(w, B, N);
+            const size_t o = (size_t)ncl * nn, ob = 2 * o;
+            p.K = w.K + o; p.G = w.G + o; p.z = z + ob; p.w = wv + ob; p.x = x + ob; p.prox = pp;
+            ok = k1_run(ncl, 400, sa) == PNPADMM_OK;                                   // ~4 ms of K1 to run beside
+            stream2_launch_sequence<float>(p, cap, w.mpack, 4, left, sbm);              // warm-up
+            cudaEventRecord(e[0], sbm); stream2_launch_sequence<float>(p, cap, w.mpack, 16, left, sbm); cudaEventRecord(e[1], sbm);
+            cudaEventRecord(e[2], sbm); stream2_launch_sequence<float>(p, 2 * cap, w.mpack, 16, left, sbm); cudaEventRecord(e[3], sbm);
+            if (ok && cudaStreamSynchronize(sbm) == cudaSuccess && cudaStreamSynchronize(sa) == cudaSuccess) { ta = ms(e[0], e[1]); tb = ms(e[2], e[3]); }
+        }
+        if (tau1 > 2.0 && tau1 < 50.0) d->tau1_us = tau1;
+        if (ta > 0 && tb > ta) {
+            const double a_it = ta * 1e3 / 16.0, b_it = tb * 1e3 / 16.0, per_plane = (b_it - a_it) / cap, fixed = a_it - per_plane * cap;
+            if (per_plane > 0.2 && per_plane < 20.0 && fixed > 0.0 && fixed < 100.0) { d->k2_b_us = per_plane; d->k2_a_us = fixed; }
+        }
+        d->calibrated = true;
+    }
+    (void)cudaDeviceSynchronize();
+    for (int i = 0; i < 4; ++i) if (e[i]) (void)cudaEventDestroy(e[i]);
+    if (sa) (void)cudaStreamDestroy(sa);
+    if (sbm) (void)cudaStreamDestroy(sbm);
+    if (buf) (void)cudaFree(buf);
+    (void)cudaGetLastError();
 }
 
 template <typename T>
@@ -862,6 +966,148 @@ int solve_impl(const T* y, const uint8_t* mask, T* x, T* z, T* wv, int B, int N,
     LAUNCH_CHECK("copy_zero_kernel");
     rc = prepare_impl<T>(y, mask, B, N, mask_batched, reo, ws, ws_bytes, st); if (rc) return rc;
     return iterate_impl<T>(x, z, wv, B, N, mask_batched, prox, iters, lambda1, reo, alpha, b, kernel, ws, ws_bytes, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Whole reconstruction from IMAGES (what the reference's functions do per image, S1:97-132 / S4:101-138): acquisition,
+// zero-filled start, data term, iterations.  For N == 256, fp32, one mask and one noise array for the batch, all of it runs
+// inside the cluster kernel (fused prologue, cluster256_core.cuh) after ONE small preparation launch; the planes the hybrid
+// schedule gives to the streaming kernels go through acquisition / zero-fill / prepare on the side stream, concurrently.
+// Everything else: acquisition into the workspace's Y region, then solve.  img or img8 (uint8 gray levels, / 255) is given.
+// ------------------------------------------------------------------------------------------
+template <typename T> struct FusedDispatch {
+    static bool run(int*, const Workspace<T>&, const T*, const uint8_t*, const uint8_t*, const T*, T*, T*, T*, int, int, int, int,
+                    double, double, double, double, int, DeviceState*, cudaStream_t) { return false; }
+};
+template <> struct FusedDispatch<float> {
+    // K3: row-separable mask (full k-space lines): preparation + column inverse transform of the three noise-term planes + ONE kernel
+    static int run_rowsep(const Workspace<float>& w, const float* img, const uint8_t* img8, const uint8_t* mask, const float* noise,
+                          float* x, float* z, float* wv, int B, int prox, int iters, double lambda1, double reo, double alpha, double b,
+                          DeviceState* d, cudaStream_t st) {
+        const int N = k1::kN;
+        const size_t nn = (size_t)N * N;
+        if (!w.tiles || w.solo) return fail(PNPADMM_ERR_UNSUPPORTED, "row-separable kernel: one mask for the batch, fp32, N == 256");
+        if (iters < 1) return fail(PNPADMM_ERR_BAD_ARG, "row-separable kernel: iters=%d < 1", iters);
+        const double La2 = 1.0 / 2.0 / reo, g = 1.0 / (1.0 + La2), n2 = (double)nn;
+        uint32_t* rcodes = w.mhere; uint32_t* rhere = w.mhere + 16; int* sep = reinterpret_cast<int*>(w.mhere + 32);
+        k3::prepare_rowsep_kernel<<<(unsigned)(nn / 256), 256, 0, st>>>(mask, reinterpret_cast<const k1::cf32*>(noise), (float)(g / n2),
+                                                                       reinterpret_cast<k1::cf32*>(w.tiles), rcodes, rhere, sep);
+        LAUNCH_CHECK("prepare_rowsep_kernel");
+        StreamParams<float> sp = base_params(w, 3, N);
+        sp.cin = w.tiles; sp.cout = w.tiles + 3 * nn;
+        S2<float>::template cols<CM_INV>(sp, 3, nullptr, d->sm_count, st);
+        LAUNCH_CHECK("cols2_kernel<INV> (noise terms)");
+        k3::RowSepParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.B = B; rp.P = (B + 1) / 2; rp.iters = iters;
+        rp.img = img; rp.img8 = img ? nullptr : img8;
+        rp.x = x; rp.z = z; rp.w = wv;
+        rp.planes = reinterpret_cast<const k1::cf32*>(w.tiles + 3 * nn);
+        rp.rcodes = rcodes; rp.rhere = rhere; rp.sep = sep;
+        rp.ncf1 = (float)(0.5 * g / N); rp.ncf2 = (float)(g / N);
+        rp.prox = make_prox<float>(prox, lambda1, reo, alpha, b);
+        const int tasks = rp.P * 16, cap = 2 * d->sm_count;
+        k3::rowsep256_kernel<<<tasks < cap ? tasks : cap, 256, k1::Geo<16>::kSmemBytes, st>>>(rp);
+        LAUNCH_CHECK("rowsep256_kernel");
+        return PNPADMM_OK;
+    }
+    // returns true if it handled the call (*rc holds the status)
+    static bool run(int* rc, const Workspace<float>& w, const float* img, const uint8_t* img8, const uint8_t* mask, const float* noise,
+                    float* x, float* z, float* wv, int B, int N, int prox, int iters, double lambda1, double reo, double alpha,
+                    double b, int kernel, DeviceState* d, cudaStream_t st) {
+        if (kernel == PNPADMM_KERNEL_ROWSEP) { *rc = run_rowsep(w, img, img8, mask, noise, x, z, wv, B, prox, iters, lambda1, reo, alpha, b, d, st); return true; }
+        static const bool off = [] { const char* e = getenv("PNPADMM_NO_FUSED_PROLOGUE"); return e && atoi(e) != 0; }();
+        if (off || N != k1::kN || iters < 1 || w.solo || kernel == PNPADMM_KERNEL_STREAMING || d->max_clusters_256 <= 0 || !w.tiles ||
+            !aligned16(x) || !aligned16(z) || !aligned16(wv) || (img && !aligned16(img)) || !aligned16(noise))
+            return false;
+        const size_t nn = (size_t)N * N;
+        const double La2 = 1.0 / 2.0 / reo, g = 1.0 / (1.0 + La2), n2 = (double)nn;
+        const ProxParams<float> pp = make_prox<float>(prox, lambda1, reo, alpha, b);
+        const int P1 = (kernel == PNPADMM_KERNEL_AUTO && S2<float>::ok(N)) ? plan_hybrid(d, w.P, iters, true) : w.P;
+        const int B1 = (2 * P1 < B) ? 2 * P1 : B;
+        // one launch: noise-term tiles, packed mask codes (K1 and K2 share the words), m[k] bits, mcode bytes, cf table,
+        // and the zeroed hand-off counters + task queue of the cluster launch
+        k1::prepare_shared_kernel<<<16, 256, 0, st>>>(mask, reinterpret_cast<const k1::cf32*>(noise), k1::kN / d->k1_cluster,
+                                                      (float)(g / n2), reinterpret_cast<k1::cf32*>(w.tiles), w.mpack, w.mhere, w.mcode,
+                                                      w.progress, w.P * 16 + 16, w.cf, (float)(0.5 * g / n2), (float)(g / n2));
+        if (cudaGetLastError() != cudaSuccess) { *rc = fail(PNPADMM_ERR_CUDA, "launch of prepare_shared_kernel failed"); return true; }
+        k1::ClusterParams cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.B = B1; cp.P = P1; cp.solo = 0; cp.iters = iters;
+        cp.x = x; cp.z = z; cp.w = wv;
+        cp.G = reinterpret_cast<const k1::cf32*>(w.Gt); cp.Gw = reinterpret_cast<k1::cf32*>(w.Gt);
+        cp.mpack = w.mpack; cp.mcode_batched = 0; cp.progress = w.progress; cp.cf = w.cf; cp.prox = pp;
+        cp.fused = 1; cp.img = img; cp.img8 = img ? nullptr : img8;
+        cp.tiles = reinterpret_cast<const k1::cf32*>(w.tiles); cp.mhere = w.mhere;
+        cp.cf1v = (float)(0.5 * g / n2); cp.cf2v = (float)(g / n2);
+        cp.no_memset = 1;
+        if (P1 == w.P) { *rc = launch_cluster(cp, d, st); return true; }
+        // hybrid: planes [P1, P) = images [B1, B) on the streaming kernels in the side stream, prologue included
+        const int B2 = B - B1, P2 = w.P - P1;
+        std::lock_guard<std::mutex> lk(d->mu);
+        if (cudaEventRecord(d->fork_ev, st) != cudaSuccess || cudaStreamWaitEvent(d->side, d->fork_ev, 0) != cudaSuccess) {
+            *rc = fail(PNPADMM_ERR_CUDA, "fork of the hybrid schedule failed: %s", cudaGetErrorString(cudaGetLastError())); return true;
+        }
+        *rc = launch_cluster(cp, d, st);
+        if (*rc) return true;
+        cudaStream_t s2 = d->side;
+        const int sms = d->sm_count - 8 * d->max_clusters_256;
+        float* x2 = x + (size_t)B1 * nn; float* z2 = z + (size_t)B1 * nn; float* w2v = wv + (size_t)B1 * nn;
+        const float* img2 = img ? img + (size_t)B1 * nn : nullptr;
+        if (!img2) {   // uint8 input: the streaming kernels want float images; x2 is free until the iterations write it
+            u8_to_unit_kernel<float><<<grid_1d((size_t)B2 * nn, sms), 256, 0, s2>>>(img8 + (size_t)B1 * nn, x2, (size_t)B2 * nn);
+            img2 = x2;
+        }
+        StreamParams<float> p = base_params(w, B2, N);
+        p.P = P2;
+        cx<float>* T1 = w.T1 + (size_t)B1 * nn; cx<float>* Y2 = w.Y + (size_t)B1 * nn;
+        p.img = img2; p.cout = T1;
+        S2<float>::template rows<RM_FWD_IMG>(p, B2, s2);
+        p.cin = T1; p.cout = Y2; p.mask = mask; p.mask_batched = 0;
+        p.noise = reinterpret_cast<const cx<float>*>(noise); p.noise_batched = 0;
+        S2<float>::template cols<CM_FWD_ACQ>(p, B2, nullptr, sms, s2);
+        p.cin = Y2; p.cout = T1;
+        S2<float>::template cols<CM_INV>(p, B2, nullptr, sms, s2);
+        p.cin = T1; p.x = z2;
+        S2<float>::template rows<RM_INV_ABS>(p, B2, s2);
+        copy_zero_kernel<float><<<grid_1d((size_t)B2 * nn, sms), 256, 0, s2>>>(z2, nullptr, w2v, (size_t)B2 * nn);
+        const size_t total = (size_t)P2 * nn;
+        prepare_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, s2>>>(Y2, mask, w.G + (size_t)P1 * nn, nullptr, B2, P2, N, 0, 0,
+                                                                            (float)(g / n2), nullptr, 0);
+        if (cudaGetLastError() != cudaSuccess) { *rc = fail(PNPADMM_ERR_CUDA, "launch of the streaming prologue failed"); return true; }
+        Workspace<float> w2 = w;
+        w2.P = P2; w2.K = w.K + (size_t)P1 * nn; w2.G = w.G + (size_t)P1 * nn;
+        *rc = stream2_iterate<float>(w2, x2, z2, w2v, B2, N, pp, iters, sms, s2, /*locked=*/true);
+        if (cudaEventRecord(d->join_ev, s2) != cudaSuccess || cudaStreamWaitEvent(st, d->join_ev, 0) != cudaSuccess)
+            *rc = fail(PNPADMM_ERR_CUDA, "join of the hybrid schedule failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return true;
+    }
+};
+
+template <typename T>
+int reconstruct_impl(const T* img, const uint8_t* img8, const uint8_t* mask, const T* noise, T* x, T* z, T* wv, int B, int N,
+                     int mask_batched, int noise_batched, int prox, int iters, double lambda1, double reo, double alpha, double b,
+                     int kernel, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if ((!img && !img8) || !mask || !noise || !x || !z || !wv || B <= 0) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct: NULL pointer or B <= 0");
+    int rc = check_n(N, sizeof(T) == 8); if (rc) return rc;
+    rc = check_prox(prox, iters, reo, b); if (rc) return rc;
+    DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
+    Workspace<T> w; rc = carve<T>(ws, ws_bytes, B, N, mask_batched, &w); if (rc) return rc;
+    bool use_cluster; rc = pick_kernel(kernel, N, sizeof(T) == 8, d, &use_cluster, true); if (rc) return rc;
+    if (kernel == PNPADMM_KERNEL_ROWSEP && (mask_batched || noise_batched))
+        return fail(PNPADMM_ERR_UNSUPPORTED, "the row-separable kernel needs one mask and one noise array for the batch");
+    if ((use_cluster || kernel == PNPADMM_KERNEL_ROWSEP) && !mask_batched && !noise_batched &&
+        FusedDispatch<T>::run(&rc, w, img, img8, mask, noise, x, z, wv, B, N, prox, iters, lambda1, reo, alpha, b, kernel, d, st))
+        return rc;
+    const size_t n = (size_t)B * N * N;
+    if (!img) {   // uint8 gray levels -> unit scale; x is free until the solve writes it
+        u8_to_unit_kernel<T><<<grid_1d(n, d->sm_count), 256, 0, st>>>(img8, x, n);
+        LAUNCH_CHECK("u8_to_unit_kernel");
+        img = x;
+    }
+    T* y = reinterpret_cast<T*>(w.Y);
+    rc = acquire_impl<T>(img, mask, noise, y, B, N, mask_batched, noise_batched, sizeof(T) == 8 ? 1 : 0, ws, ws_bytes, st); if (rc) return rc;
+    return solve_impl<T>(y, mask, x, z, wv, B, N, mask_batched, prox, iters, lambda1, reo, alpha, b, kernel, ws, ws_bytes, st);
 }
 
 template <typename T>
@@ -1015,7 +1261,7 @@ int pnpadmm_device_info(int* sm_count, int* max_clusters_256, int* cc_major, int
 //   acquire: rows<FWD_IMG> + cols<FWD_ACQ>;  zero_filled: cols<INV> + rows<INV_ABS>;  solve adds copy_zero, write_cf,
 //   prepare, pack_mcode (fp32, N in {256, 512, 1024}), then the iteration kernels.
 int pnpadmm_plan_info(int B, int N, int mask_batched, int iters, int kernel, int* planes_cluster, int* planes_streaming,
-                      int* chunks, int* launches_acquire, int* launches_solve) {
+                      int* chunks, int* launches_acquire, int* launches_solve, int* launches_reconstruct) {
     if (B <= 0 || iters < 0) return fail(PNPADMM_ERR_BAD_ARG, "plan_info: B <= 0 or iters < 0");
     int rc = check_n(N, false); if (rc) return rc;
     DeviceState* d; rc = ensure_device(&d); if (rc) return rc;
@@ -1023,7 +1269,7 @@ int pnpadmm_plan_info(int B, int N, int mask_batched, int iters, int kernel, int
     const int P = mask_batched ? B : (B + 1) / 2;
     int p1 = 0, p2 = P, nch = 1;
     if (use_cluster) {
-        p1 = (kernel == PNPADMM_KERNEL_AUTO && S2<float>::ok(N)) ? plan_hybrid(d, P, iters) : P;
+        p1 = (kernel == PNPADMM_KERNEL_AUTO && S2<float>::ok(N)) ? plan_hybrid(d, P, iters, !mask_batched && iters >= 1) : P;
         p2 = P - p1;
         int chunk; plan_chunks(p1, iters, d->max_clusters_256, &chunk, &nch);
     }
@@ -1034,7 +1280,14 @@ int pnpadmm_plan_info(int B, int N, int mask_batched, int iters, int kernel, int
     if (planes_streaming) *planes_streaming = p2;
     if (chunks) *chunks = nch;
     if (launches_acquire) *launches_acquire = 2;
-    if (launches_solve) *launches_solve = 2 /* zero-fill */ + 1 /* copy_zero */ + 2 /* write_cf, prepare */ + (s2 ? 1 : 0) /* pack */ + it_launches;
+    const int solve = 2 /* zero-fill */ + 1 /* copy_zero */ + 2 /* write_cf, prepare */ + (s2 ? 1 : 0) /* pack */ + it_launches;
+    if (launches_solve) *launches_solve = solve;
+    if (launches_reconstruct) {
+        // fused prologue (N == 256, fp32, shared mask and noise): prepare_shared + the cluster kernel; the streaming share of
+        // the hybrid schedule adds rows<FWD_IMG>, cols<FWD_ACQ>, cols<INV>, rows<INV_ABS>, copy_zero, prepare + its iterations
+        const bool fused = use_cluster && !mask_batched && iters >= 1 && getenv("PNPADMM_NO_FUSED_PROLOGUE") == nullptr;
+        *launches_reconstruct = fused ? 1 + (p1 > 0 ? 1 : 0) + (p2 > 0 ? 6 + 1 + 2 * iters : 0) : 2 + solve;
+    }
     return PNPADMM_OK;
 }
 
@@ -1095,6 +1348,31 @@ int pnpadmm_solve_f64(const double* y, const uint8_t* mask, double* x, double* z
     return solve_impl<double>(y, mask, x, z, w, B, N, mb, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, ST(s));
 }
 
+int pnpadmm_reconstruct_f32(const float* img, const uint8_t* img8, const uint8_t* mask, const float* noise, float* x, float* z,
+                            float* w, int B, int N, int mb, int nb, int prox, int iters, double lambda1, double reo, double alpha,
+                            double b, int kernel, void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return reconstruct_impl<float>(img, img8, mask, noise, x, z, w, B, N, mb, nb, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, ST(s));
+}
+int pnpadmm_reconstruct_f64(const double* img, const uint8_t* img8, const uint8_t* mask, const double* noise, double* x, double* z,
+                            double* w, int B, int N, int mb, int nb, int prox, int iters, double lambda1, double reo, double alpha,
+                            double b, int kernel, void* ws, size_t wsb, pnpadmm_stream_t s) {
+    return reconstruct_impl<double>(img, img8, mask, noise, x, z, w, B, N, mb, nb, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, ST(s));
+}
+
+namespace {
+// full k-space lines?  (host mask of the *_host entry points: 255 row compares of N bytes)
+bool host_mask_row_separable(const uint8_t* m, int N) {
+    for (int r = 1; r < N; ++r)
+        for (int c = 0; c < N; ++c)
+            if ((m[(size_t)r * N + c] != 0) != (m[c] != 0)) return false;
+    return true;
+}
+int host_auto_kernel(int kernel, const uint8_t* h_mask, int N) {
+    static const bool off = [] { const char* e = getenv("PNPADMM_NO_ROWSEP"); return e && atoi(e) != 0; }();
+    return (!off && kernel == PNPADMM_KERNEL_AUTO && N == 256 && host_mask_row_separable(h_mask, N)) ? PNPADMM_KERNEL_ROWSEP : kernel;
+}
+}  // namespace
+
 size_t pnpadmm_host_scratch_bytes(int B, int N) {
     if (B <= 0 || N <= 0) return 0;
     const size_t nn = (size_t)N * N, n = (size_t)B * nn;
@@ -1126,10 +1404,10 @@ int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, co
     CUDA_TRY(cudaMemcpyAsync(d_img8, h_img, n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_mask, h_mask, nn, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_noise, h_noise, nn * 8, cudaMemcpyHostToDevice, st));
-    u8_to_unit_kernel<float><<<grid_1d(n, d->sm_count), 256, 0, st>>>(d_img8, d_img, n);
-    LAUNCH_CHECK("u8_to_unit_kernel");
-    rc = acquire_impl<float>(d_img, d_mask, d_noise, d_y, B, N, 0, 0, 0, ws, wsb, st); if (rc) return rc;
-    rc = solve_impl<float>(d_y, d_mask, d_x, d_z, d_w, B, N, 0, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, st);
+    (void)d_img; (void)d_y;   // kept in the scratch layout; the reconstruct path reads the uint8 images directly
+    kernel = host_auto_kernel(kernel, h_mask, N);
+    rc = reconstruct_impl<float>(nullptr, d_img8, d_mask, d_noise, d_x, d_z, d_w, B, N, 0, 0, prox, iters, lambda1, reo, alpha, b, kernel,
+                                 ws, wsb, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(h_x, d_x, n * 4, cudaMemcpyDeviceToHost, st));
     return PNPADMM_OK;
@@ -1233,6 +1511,7 @@ int pnpadmm_reconstruct_host_pipelined_f32(pnpadmm_pipeline_t pipe, const uint8_
     int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
     if (dev != pipe->dev) return fail(PNPADMM_ERR_BAD_ARG, "reconstruct_host_pipelined: pipeline belongs to device %d, current device is %d", pipe->dev, dev);
     cudaStream_t sc = ST(compute), si = ST(h2d), so = ST(d2h);
+    kernel = host_auto_kernel(kernel, h_mask, N);
     const size_t nn = (size_t)N * N, n = (size_t)B * nn;
     unsigned char* p = (unsigned char*)d_scratch;
     uint8_t* d_img8[PNPADMM_PIPELINE_MAX_SLOTS]; uint8_t* d_mask[PNPADMM_PIPELINE_MAX_SLOTS];
@@ -1257,11 +1536,10 @@ int pnpadmm_reconstruct_host_pipelined_f32(pnpadmm_pipeline_t pipe, const uint8_
     // compute: needs the inputs, and the slot's output buffer drained by the previous D2H
     CUDA_TRY(cudaStreamWaitEvent(sc, pipe->in_ready[slot], 0));
     if (pipe->used[slot]) CUDA_TRY(cudaStreamWaitEvent(sc, pipe->out_done[slot], 0));
+    (void)d_img; (void)d_y;
     auto enqueue_compute = [&]() -> int {
-        u8_to_unit_kernel<float><<<grid_1d(n, d->sm_count), 256, 0, sc>>>(d_img8[slot], d_img, n);
-        LAUNCH_CHECK("u8_to_unit_kernel");
-        int r = acquire_impl<float>(d_img, d_mask[slot], d_noise[slot], d_y, B, N, 0, 0, 0, ws, wsb, sc); if (r) return r;
-        return solve_impl<float>(d_y, d_mask[slot], d_x[slot], d_z, d_w, B, N, 0, prox, iters, lambda1, reo, alpha, b, kernel, ws, wsb, sc);
+        return reconstruct_impl<float>(nullptr, d_img8[slot], d_mask[slot], d_noise[slot], d_x[slot], d_z, d_w, B, N, 0, 0, prox, iters,
+                                       lambda1, reo, alpha, b, kernel, ws, wsb, sc);
     };
     // The compute section has fixed arguments per (slot, parameters): replay it as one graph from the second sighting on.
     static const char* nograph = getenv("PNPADMM_NO_GRAPH");
@@ -1390,6 +1668,14 @@ int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H
                                const float* b_head, const void* w_mid, const float* b_mid, const void* w_tail,
                                const float* b_tail, int residual, void* act0, void* act1, pnpadmm_stream_t s) {
     return dncnn_forward_impl(x, out, B, cin, H, W, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, residual, act0, act1, ST(s));
+}
+
+// debug only (not part of include/pnpadmm.h): the planner's per-device constants
+int pnpadmm_debug_plan_constants(double* out4, int* calibrated) {
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    out4[0] = d->tau1_us; out4[1] = d->k2_a_us; out4[2] = d->k2_b_us; out4[3] = d->k2_pro_us;
+    if (calibrated) *calibrated = d->calibrated ? 1 : 0;
+    return PNPADMM_OK;
 }
 
 // debug only (not part of include/pnpadmm.h): read and clear the wait-time counters of conv64_tc_kernel (PNPADMM_TC_DEBUG bit 256)

@@ -324,6 +324,7 @@ __global__ void prepare_kernel(const cx<T>* __restrict__ y, const uint8_t* __res
     G[idx] = gv;
     // N = 256 fp32: second copy in the cluster kernel's tile order [plane][rank][kr][c] (cluster256_core.cuh)
     if (Gt) Gt[(size_t)plane * nn + (size_t)(c / tileR) * ((size_t)N * tileR) + (size_t)r * tileR + (c % tileR)] = gv;
+    if (!mcode) return;                      // codes already written (fused prologue's preparation launch)
     if (!mask_batched) {
         if (plane == 0) mcode[bin] = (uint8_t)((m[bin] ? 1 : 0) + (m[mbin] ? 1 : 0));
     } else {

@@ -10,6 +10,7 @@ iterations, returns the last x-update.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple, Union
 
 import numpy as np
@@ -20,7 +21,26 @@ from . import _abi
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
 _PROX = {'l1': _abi.PROX_L1, 'cnc': _abi.PROX_CNC}
-_KERNEL = {'auto': _abi.KERNEL_AUTO, 'cluster': _abi.KERNEL_CLUSTER, 'streaming': _abi.KERNEL_STREAMING}
+_KERNEL = {'auto': _abi.KERNEL_AUTO, 'cluster': _abi.KERNEL_CLUSTER, 'streaming': _abi.KERNEL_STREAMING, 'rowsep': _abi.KERNEL_ROWSEP}
+_ROWSEP_CACHE = {}
+
+
+def mask_is_row_separable(mask) -> bool:
+    """True if the sampling mask consists of full k-space lines, mask[kr, kc] == mask[0, kc] (Cartesian undersampling such as
+    CS_MRI/Q_Cartesian30): the reconstruction then runs on the row-separable kernel (kernel='rowsep').  Host arrays are tested
+    directly; a CUDA tensor is tested once per (storage, version) with one device reduction and remembered."""
+    if os.environ.get('PNPADMM_NO_ROWSEP'):
+        return False
+    if isinstance(mask, torch.Tensor) and mask.is_cuda:
+        key = (mask.data_ptr(), mask._version, tuple(mask.shape))
+        hit = _ROWSEP_CACHE.get(key)
+        if hit is None:
+            if len(_ROWSEP_CACHE) > 64:
+                _ROWSEP_CACHE.clear()
+            hit = _ROWSEP_CACHE[key] = bool(((mask != 0) == (mask[:1] != 0)).all().item()) if mask.ndim == 2 else False
+        return hit
+    m = np.asarray(mask.cpu() if isinstance(mask, torch.Tensor) else mask)
+    return bool(m.ndim == 2 and ((m != 0) == (m[:1] != 0)).all())
 
 
 def _require_cuda(device=None) -> torch.device:
@@ -179,6 +199,36 @@ class AdmmSolver:
         self._prepared_reo = float(reo)
         return x, z, w
 
+    def reconstruct(self, img: ArrayLike, mask: ArrayLike, noises: ArrayLike, prox: str, iter_num: int, lambda1: float, reo: float,
+                    alpha: float = 0.0, b: float = 1.0, kernel: str = 'auto') -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """From images to reconstructions in one call (S1:97-132 / S4:101-138 per image): acquisition, zero-filled start,
+        data term and `iter_num` iterations.  `img`: (B,N,N) real in [0,1], or uint8 gray levels (divided by 255 on the device).
+        At N = 256 in float32 with one mask / noise for the batch all of it runs inside the cluster kernel.  Returns (x, z, w)."""
+        if prox not in _PROX:
+            raise ValueError("prox must be 'l1' or 'cnc'")
+        t = torch.as_tensor(img)
+        if t.shape != (self.B, self.N, self.N):
+            raise ValueError(f'img must have shape {(self.B, self.N, self.N)}, got {tuple(t.shape)}')
+        if t.dtype == torch.uint8:
+            img8, imgf = t.to(self.device).contiguous(), None
+        else:
+            img8, imgf = None, t.to(device=self.device, dtype=self.rdtype).contiguous()
+        if (kernel == 'auto' and self.N == 256 and not self.f64 and not self.mask_batched and iter_num >= 1
+                and mask_is_row_separable(mask)):
+            kernel = 'rowsep'                  # full k-space lines: every image row is solved on its own (K3)
+        m = self._mask(mask)
+        nz, nb = _noise_arg(self, noises)
+        if kernel == 'rowsep' and nb:
+            kernel = 'auto'
+        x, z, w = self.new(), self.new(), self.new()
+        with torch.cuda.device(self.device):
+            _abi.check(self._fn('reconstruct')(_ptr(imgf), _ptr(img8), m.data_ptr(), nz.data_ptr(), x.data_ptr(), z.data_ptr(),
+                                               w.data_ptr(), self.B, self.N, int(self.mask_batched), nb, _PROX[prox], int(iter_num),
+                                               float(lambda1), float(reo), float(alpha), float(b), _KERNEL[kernel],
+                                               self.ws.data_ptr(), self.ws_bytes, _stream_ptr()))
+        self._prepared_reo = None          # the fused path does not leave a prepared data term for xupdate / iterate
+        return x, z, w
+
 
 class HostPipeline:
     """Back-to-back reconstructions from HOST buffers (the drop-in functions' situation: uint8 images on the host in,
@@ -248,6 +298,15 @@ class HostPipeline:
             pass
 
 
+def _noise_arg(solver, noises):
+    nz = torch.as_tensor(noises).to(device=solver.device, dtype=solver.cdtype).contiguous()
+    if nz.shape == (solver.N, solver.N):
+        return nz, 0
+    if nz.shape == (solver.B, solver.N, solver.N):
+        return nz, 1
+    raise ValueError(f'noises must be (N,N) or (B,N,N), got {tuple(nz.shape)}')
+
+
 def admm_solve(images: ArrayLike, mask: ArrayLike, noises: ArrayLike, *, prox: str = 'l1', iter_num: int = 50,
                lambda1: float = 0.1, reo: float = 0.015, alpha: float = 0.45, b: float = 64.0,
                dtype: str = 'float32', kernel: str = 'auto', return_state: bool = False, device=None):
@@ -270,8 +329,13 @@ def admm_solve(images: ArrayLike, mask: ArrayLike, noises: ArrayLike, *, prox: s
     B, N = int(img.shape[0]), int(img.shape[1])
     m = torch.as_tensor(mask)
     solver = AdmmSolver(B, N, dtype=dtype, mask_batched=(m.ndim == 3), device=device)
-    y = solver.acquire(img, m, noises)
-    x, z, w = solver.solve(y, m, prox, iter_num, lambda1, reo, alpha, b, kernel=kernel)
+    if dtype == 'float32' and not return_state:
+        # one call from images to reconstructions (acquisition fused into the cluster kernel where it applies)
+        x, z, w = solver.reconstruct(img, m, noises, prox, iter_num, lambda1, reo, alpha, b, kernel=kernel)
+        y = None
+    else:
+        y = solver.acquire(img, m, noises)
+        x, z, w = solver.solve(y, m, prox, iter_num, lambda1, reo, alpha, b, kernel=kernel)
 
     def out(t):
         t = t[0] if single else t

@@ -119,3 +119,22 @@ def test_ircnn_sigma_indexed_weight_switch():
                      ircnn_weights=[sets[str(k)] for k in range(25)])
     for i in (0, 17, 49):
         assert torch.equal(D2(x, i), D(x, i)) and torch.equal(D3(x, i), D(x, i))
+
+
+@pytest.mark.parametrize('key,name', [('l1_ircnn', 'ircnn_gray'), ('l1_dncnn', 'dncnn_15')])
+def test_oracle_pnp_50_iterations_matches_unmodified_s3(cs_inputs, key, name):
+    """The PnP restatement at the presets' full depth against outputs of the UNMODIFIED S3 function
+    (tests/golden/pnp_golden_50it.npz, oracle/make_golden_pnp50.py): the IRCNN preset exercises the 25-set weight switch
+    inside the reference's own loop (S3:280-288, run with the `np.int` alias restored), DnCNN-15 the plain residual branch."""
+    g = np.load(os.path.join(GOLD, 'pnp_golden_50it.npz'))
+    it, reo = int(g[key + '_params'][0]), float(g[key + '_params'][1])
+    assert it == 50
+    names = cs_inputs['image_names']
+    img = orc.preprocess_uint8(cs_inputs['images'][names.index(str(g['single_image']))])
+    kw = {}
+    if 'ircnn' in name:
+        kw['ircnn_weights'] = {str(k): dn.build_model('ircnn_gray', seed=int(g['ircnn_seed0']) + k).state_dict() for k in range(25)}
+    D = dn.Denoiser(name, iter_num=it, x8=False, noises=cs_inputs['noises'], dtype=torch.float32, device='cpu', seed=0, **kw)
+    f = lambda a, i: D(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))[None, None], i)[0, 0].numpy()
+    x = orc.pnp_admm_l1(img, cs_inputs['masks'][0].astype(np.float64), cs_inputs['noises'], f, iter_num=it, reo=reo)
+    assert np.abs(x - g[key]).max() < 2e-5

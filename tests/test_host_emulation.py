@@ -88,6 +88,74 @@ def test_k1_emulated_solve_matches_oracle(emu, cs_inputs, prox, P, cluster):
         assert abs(p - kat.PSNR[('Q_Radial30', prox)][i]) < 0.01
 
 
+@pytest.mark.parametrize('cluster', [8, 16])
+@pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
+def test_k1_emulated_fused_prologue_matches_oracle(emu, cs_inputs, prox, P, cluster):
+    """The fused prologue (acquisition, zero-filled start and data term inside the cluster kernel: packed F = fft2(a + i b),
+    G = cf F + noise term, |ifft2(y)| from the symmetric / antisymmetric mask branches) followed by the loop, from the uint8 images."""
+    idx = [4, 0, 7]                                      # odd count: the last plane's imaginary slot must stay zero
+    m = cs_inputs['masks'][2]
+    nz = cs_inputs['noises']
+    u8 = np.ascontiguousarray(cs_inputs['images'][idx])
+    noise = np.ascontiguousarray(nz.astype(np.complex64)).view(np.float32)
+    B = len(idx)
+    x, z, w = (np.zeros((B, 256, 256), np.float32) for _ in range(3))
+    a, l, reo, b = P.get('alpha', 0.), P['lambda1'], P['reo'], P.get('b', 1.)
+    f = ctypes.c_float
+    U8 = ctypes.POINTER(ctypes.c_uint8)
+    mask = np.ascontiguousarray(m.astype(np.uint8))
+    for it in (0, P['iter_num']):
+        emu.k1_emulate_fused(None, u8.ctypes.data_as(U8), mask.ctypes.data_as(U8), noise.ctypes.data_as(FP), f(reo),
+                             x.ctypes.data_as(FP), z.ctypes.data_as(FP), w.ctypes.data_as(FP), B, max(it, 1), 0 if prox == 'l1' else 1,
+                             f(reo * l), f(1 / b), f(1 - a), f(a), f(a * reo * l * b), f(a * reo * l), cluster)
+        if it == 0:
+            continue
+        fn = orc.admm_l1 if prox == 'l1' else orc.admm_cnc
+        for k, i in enumerate(idx):
+            xr, zr, wr, _ = fn(orc.preprocess_uint8(cs_inputs['images'][i]), m.astype(np.float64), nz, return_state=True, **P)
+            assert np.linalg.norm(x[k] - xr) / np.linalg.norm(xr) < 1e-4
+            assert np.linalg.norm(z[k] - zr) / np.linalg.norm(zr) < 1e-4
+            p = orc.calculate_psnr(x[k].astype(np.float64) * 255, cs_inputs['images'][i])
+            assert abs(p - kat.PSNR[('Q_Cartesian30', prox)][i]) < 0.01
+
+
+@pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
+def test_k3_emulated_rowsep_solve_matches_oracle(emu, cs_inputs, prox, P):
+    """K3 (rowsep256.cuh): under the reference's Q_Cartesian30 mask (76 full columns) the blend commutes with the column
+    transforms and every image row is solved on its own.  Same per-thread code as the device kernel, from the uint8 images."""
+    idx = [4, 0, 7]
+    m = cs_inputs['masks'][2]
+    assert cs_inputs['mask_names'][2] == 'Q_Cartesian30' and (m == m[:1]).all()
+    nz = cs_inputs['noises']
+    u8 = np.ascontiguousarray(cs_inputs['images'][idx])
+    noise = np.ascontiguousarray(nz.astype(np.complex64)).view(np.float32)
+    mask = np.ascontiguousarray(m.astype(np.uint8))
+    B = len(idx)
+    a, l, reo, b = P.get('alpha', 0.), P['lambda1'], P['reo'], P.get('b', 1.)
+    g = 1 / (1 + 1 / (2 * reo))
+    f = ctypes.c_float
+    U8 = ctypes.POINTER(ctypes.c_uint8)
+    planes = np.zeros((3, 256, 256), np.complex64)
+    emu.k3_noise_terms(mask.ctypes.data_as(U8), noise.ctypes.data_as(FP), f(g / 65536.), planes.view(np.float32).ctypes.data_as(FP))
+    planes = np.ascontiguousarray((np.fft.ifft(planes.astype(np.complex128), axis=1) * 256).astype(np.complex64))   # column IFFT, unnormalised
+    x, z, w = (np.zeros((B, 256, 256), np.float32) for _ in range(3))
+    rc = emu.k3_emulate(None, u8.ctypes.data_as(U8), mask.ctypes.data_as(U8), planes.view(np.float32).ctypes.data_as(FP), f(reo),
+                        x.ctypes.data_as(FP), z.ctypes.data_as(FP), w.ctypes.data_as(FP), B, P['iter_num'], 0 if prox == 'l1' else 1,
+                        f(reo * l), f(1 / b), f(1 - a), f(a), f(a * reo * l * b), f(a * reo * l))
+    assert rc == 0
+    fn = orc.admm_l1 if prox == 'l1' else orc.admm_cnc
+    for k, i in enumerate(idx):
+        xr, zr, wr, _ = fn(orc.preprocess_uint8(cs_inputs['images'][i]), m.astype(np.float64), nz, return_state=True, **P)
+        assert np.linalg.norm(x[k] - xr) / np.linalg.norm(xr) < 1e-4
+        assert np.linalg.norm(z[k] - zr) / np.linalg.norm(zr) < 1e-4
+        p = orc.calculate_psnr(x[k].astype(np.float64) * 255, cs_inputs['images'][i])
+        assert abs(p - kat.PSNR[('Q_Cartesian30', prox)][i]) < 0.01
+    # a mask that is not made of full lines is refused
+    assert emu.k3_emulate(None, u8.ctypes.data_as(U8), np.ascontiguousarray(cs_inputs['masks'][0].astype(np.uint8)).ctypes.data_as(U8),
+                          planes.view(np.float32).ctypes.data_as(FP), f(reo), x.ctypes.data_as(FP), z.ctypes.data_as(FP),
+                          w.ctypes.data_as(FP), B, 1, 0, f(0), f(1), f(1), f(0), f(0), f(0)) == 1
+
+
 # ---------------------------------------------------------------------------------------------
 # K2 streaming kernels: the per-thread FFT stages (stream2_core.cuh) against a naive double DFT
 # ---------------------------------------------------------------------------------------------

@@ -585,3 +585,134 @@ def test_k2_column_pass_variants_bit_identical(tmp_path):
         results.append(np.load(f))
     assert np.array_equal(results[0], results[1])
     assert np.array_equal(results[0], results[2])
+
+
+# ---------------------------------------------------------------------------------------------
+# pnpadmm_reconstruct_*: images -> reconstructions in one call; at N = 256 (fp32, shared mask + noise) acquisition,
+# zero-filled start and the data term run inside the cluster kernel (fused prologue)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
+@pytest.mark.parametrize('mask_i', [0, 1, 2])
+def test_fused_prologue_matches_oracle_and_unfused_path(pk, cs_inputs, prox, P, mask_i):
+    idx = list(range(15))
+    u8 = np.ascontiguousarray(cs_inputs['images'][idx])
+    imgs = _imgs(cs_inputs, idx)
+    m, nz = cs_inputs['masks'][mask_i], cs_inputs['noises']
+    s = pk.AdmmSolver(15, 256)
+    args = (prox, P['iter_num'], P['lambda1'], P['reo'], P.get('alpha', 0.0), P.get('b', 1.0))
+    xf, zf, wf = (t.cpu().numpy() for t in s.reconstruct(imgs, m, nz, *args, kernel='cluster'))     # float images
+    x8, z8, w8 = (t.cpu().numpy() for t in s.reconstruct(u8, m, nz, *args, kernel='cluster'))       # uint8 gray levels
+    assert np.array_equal(xf, x8) and np.array_equal(zf, z8) and np.array_equal(wf, w8)
+    y = s.acquire(imgs, m, nz)
+    xo, zo, wo = (t.cpu().numpy() for t in s.solve(y, m, *args, kernel='cluster'))                  # unfused: acquire + solve
+    xr, zr, wr, _ = oracle_batch(imgs, m, nz, prox, P)
+    name = cs_inputs['mask_names'][mask_i]
+    for k in range(15):
+        assert rel(xf[k], xr[k]) < TOL32 and rel(zf[k], zr[k]) < TOL32, (name, prox, k)
+        assert rel(xf[k], xo[k].astype(np.float64)) < TOL32          # two fp32 paths, each ~1e-5 from the oracle under CNC
+        p = orc.calculate_psnr(xf[k].astype(np.float64) * 255, cs_inputs['images'][k])
+        assert abs(p - kat.PSNR[(name, prox)][k]) < TOL_PSNR, (name, prox, k, p)
+    # the dual: same accuracy as the unfused path reaches against the oracle (a few pixels sit on a threshold)
+    ew_f, ew_o = rel(wf, wr), rel(wo, wr)
+    print(f'{name} {prox}: dual w rel-L2 vs oracle: fused {ew_f:.2e}, unfused {ew_o:.2e}')
+    assert ew_f < max(3 * ew_o, 1e-4)
+
+
+def test_fused_prologue_hybrid_split_and_fallbacks(pk, cs_inputs, monkeypatch):
+    """The fused call under the hybrid schedule (streaming share does its own acquisition on the side stream, from float and
+    from uint8 images), and the cases that fall back to acquisition + solve: N != 256, per-image masks, float64."""
+    from pnp_admm_cnc_mri_b200 import data
+    B = 45
+    idx = [i % 15 for i in range(B)]
+    u8 = np.ascontiguousarray(cs_inputs['images'][idx])
+    imgs = _imgs(cs_inputs, idx)
+    m, nz = cs_inputs['masks'][0], cs_inputs['noises']
+    P = kat.CNC_DEFAULTS
+    args = ('cnc', P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'])
+    ref = {i: orc.admm_cnc(imgs[i], m.astype(np.float64), nz, **P) for i in range(15)}
+    s = pk.AdmmSolver(B, 256)
+    pure = s.reconstruct(imgs, m, nz, *args, kernel='cluster')[0].cpu().numpy()
+    for p2 in ('5', None):
+        if p2 is None:
+            monkeypatch.delenv('PNPADMM_HYBRID_P2', raising=False)
+        else:
+            monkeypatch.setenv('PNPADMM_HYBRID_P2', p2)
+        for src in (imgs, u8):
+            x = s.reconstruct(src, m, nz, *args, kernel='auto')[0].cpu().numpy()
+            for k in range(B):
+                assert rel(x[k], ref[idx[k]]) < TOL32, (p2, k)
+            if p2 is not None:
+                n1 = 2 * (23 - int(p2))
+                assert np.array_equal(x[:n1], pure[:n1])             # the K1 share is the pure cluster run, bit for bit
+    monkeypatch.delenv('PNPADMM_HYBRID_P2', raising=False)
+    # fallbacks
+    N2 = 512
+    im2 = data.phantoms(3, N2, seed0=3)
+    m2, n2 = data.make_mask('radial', N2, seed=1), data.make_noise(N2, seed=2)
+    Pq = dict(P, iter_num=8)
+    aq = ('cnc', 8, P['lambda1'], P['reo'], P['alpha'], P['b'])
+    x = pk.AdmmSolver(3, N2).reconstruct(np.uint8((im2 * 255).round()), m2, n2, *aq)[0].cpu().numpy()
+    xr = oracle_batch(np.float32(np.uint8((im2 * 255).round()) / 255.), m2, n2, 'cnc', Pq)[0]
+    assert rel(x, xr) < TOL32
+    masks = np.stack([cs_inputs['masks'][k % 3] for k in range(4)])
+    x = pk.AdmmSolver(4, 256, mask_batched=True).reconstruct(imgs[:4], masks, nz, *aq)[0].cpu().numpy()
+    xr = oracle_batch(imgs[:4], masks, nz, 'cnc', Pq)[0]
+    assert rel(x, xr) < TOL32
+    x = pk.AdmmSolver(2, 256, dtype='float64').reconstruct(imgs[:2], m, nz, *aq)[0].cpu().numpy()
+    xr = oracle_batch(imgs[:2], m, nz, 'cnc', Pq)[0]
+    assert rel(x, xr) < TOL64
+
+
+# ---------------------------------------------------------------------------------------------
+# K3: row-separable masks (full k-space lines, the reference's Q_Cartesian30): every image row is solved on its own
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('prox,P', [('l1', kat.L1_DEFAULTS), ('cnc', kat.CNC_DEFAULTS)])
+def test_rowsep_kernel_kat_table_cartesian(pk, cs_inputs, prox, P):
+    """All 15 set images under Q_Cartesian30 on the row-separable kernel (explicitly, and picked by kernel='auto'), float and
+    uint8 images, against the oracle, the reference's log table and the general cluster kernel."""
+    m, nz = cs_inputs['masks'][2], cs_inputs['noises']
+    assert cs_inputs['mask_names'][2] == 'Q_Cartesian30' and pk.mask_is_row_separable(m)
+    assert not pk.mask_is_row_separable(cs_inputs['masks'][0]) and not pk.mask_is_row_separable(cs_inputs['masks'][1])
+    imgs = _imgs(cs_inputs, range(15))
+    u8 = np.ascontiguousarray(cs_inputs['images'][:15])
+    s = pk.AdmmSolver(15, 256)
+    args = (prox, P['iter_num'], P['lambda1'], P['reo'], P.get('alpha', 0.0), P.get('b', 1.0))
+    x, z, w = (t.cpu().numpy() for t in s.reconstruct(imgs, m, nz, *args, kernel='rowsep'))
+    xa = s.reconstruct(u8, torch.as_tensor(m).cuda(), nz, *args, kernel='auto')[0].cpu().numpy()     # device mask: tested once, cached
+    assert np.array_equal(x, xa)
+    xc = s.reconstruct(imgs, m, nz, *args, kernel='cluster')[0].cpu().numpy()
+    xr, zr, wr, _ = oracle_batch(imgs, m, nz, prox, P)
+    for k in range(15):
+        assert rel(x[k], xr[k]) < TOL32 and rel(z[k], zr[k]) < TOL32, (prox, k)
+        assert rel(x[k], xc[k].astype(np.float64)) < TOL32
+        p = orc.calculate_psnr(x[k].astype(np.float64) * 255, cs_inputs['images'][k])
+        assert abs(p - kat.PSNR[('Q_Cartesian30', prox)][k]) < TOL_PSNR, (prox, k, p)
+    print(f'rowsep {prox}: worst rel-L2 vs oracle {max(rel(x[k], xr[k]) for k in range(15)):.2e}')
+    # admm_solve picks it for a separable mask; results identical
+    assert np.array_equal(pk.admm_solve(imgs, m, nz, prox=prox, **P), x)
+
+
+def test_rowsep_kernel_refuses_other_masks_and_covers_batches(pk, cs_inputs):
+    from pnp_admm_cnc_mri_b200 import data
+    nz = cs_inputs['noises']
+    imgs = _imgs(cs_inputs, range(3))
+    P = kat.CNC_DEFAULTS
+    args = ('cnc', P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'])
+    # asserted separability is verified on the device: a radial mask yields NaN, not a wrong reconstruction
+    x, z, w = pk.AdmmSolver(3, 256).reconstruct(imgs, cs_inputs['masks'][1], nz, *args, kernel='rowsep')
+    assert torch.isnan(x).all() and torch.isnan(z).all() and torch.isnan(w).all()
+    with pytest.raises(pk.PnpAdmmError):
+        pk.AdmmSolver(2, 512).reconstruct(data.phantoms(2, 512, 0), data.make_mask('cartesian', 512, 0), data.make_noise(512, 1), *args,
+                                          kernel='rowsep')
+    # a synthetic Cartesian mask, a batch larger than one wave of CTAs (2 x 148 SMs x 16 rows), odd count
+    B = 75
+    m = data.make_mask('cartesian', 256, seed=7)
+    assert pk.mask_is_row_separable(m)
+    base = data.phantoms(5, 256, seed0=9)
+    big = np.concatenate([base] * 15)[:B]
+    x = pk.AdmmSolver(B, 256).reconstruct(big, m, nz, *args)[0].cpu().numpy()
+    xr = oracle_batch(base, m, nz, 'cnc', P)[0]
+    for k in range(B):
+        assert rel(x[k], xr[k % 5]) < TOL32, k
+    reps = x[:70].reshape(7, 10, 256, 256)                                    # period 10: same pair slot, same partner image
+    assert np.array_equal(reps, np.broadcast_to(reps[:1], reps.shape))        # rows are independent: such copies are bit-identical

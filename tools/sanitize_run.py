@@ -36,6 +36,18 @@ if which in ('all', 'hybrid'):
     B = 2 * (int(os.environ.get('SAN_NCL', '14')) + 3)  # more planes than resident clusters, so the split is live
     imgs = np.concatenate([data.phantoms(4, N, seed0=1)] * (B // 4 + 1))[:B]
     check(pk.admm_solve(imgs, m, nz, prox='cnc', kernel='auto', **P), imgs, m, nz, f'hybrid B={B}')
+if which in ('all', 'fused'):
+    # images -> reconstruction in one call: fused prologue inside the cluster kernel, from uint8 images, hybrid split live
+    os.environ['PNPADMM_HYBRID_P2'] = '2'
+    B = 2 * (int(os.environ.get('SAN_NCL', '14')) + 3) + 1      # odd: the last plane has an empty slot
+    imgs = np.concatenate([data.phantoms(4, N, seed0=1)] * (B // 4 + 1))[:B]
+    u8 = np.uint8((imgs * 255).round())
+    s = pk.AdmmSolver(B, N)
+    x = s.reconstruct(u8, m, nz, 'cnc', P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'])[0].cpu().numpy()
+    check(x, np.float32(u8 / 255.), m, nz, f'fused reconstruct B={B}')
+    x = s.reconstruct(u8, m, nz, 'cnc', P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'], kernel='cluster')[0].cpu().numpy()
+    check(x, np.float32(u8 / 255.), m, nz, f'fused reconstruct, cluster only, B={B}')
+    del os.environ['PNPADMM_HYBRID_P2']
 if which in ('all', 'k2'):
     N2 = 512
     m2 = data.make_mask('radial', N2, seed=1)
