@@ -280,7 +280,7 @@ def run_ours(args):
     h_xs = [torch.empty((B, N, N), dtype=torch.float32).pin_memory() for _ in range(SLOTS)]
     enq_s = []                                            # host time spent enqueueing one step (diagnostic)
 
-    def timed_pipelined(steps, warmup, min_seconds=0.0):
+    def timed_pipelined(steps, warmup, min_seconds=0.0, pipe=pipe, h_xs=h_xs):
         def enqueue(i):
             t0 = time.perf_counter()
             pipe.submit(i % SLOTS, h_img, h_masks[i % 3], h_noise, h_xs[i % SLOTS], prox='cnc', **CNC)
@@ -335,6 +335,12 @@ def run_ours(args):
     ms_e2e, _ = timed_pipelined(args.steps, args.warmup)
     enq_us = 1e6 * float(np.median(enq_s)) if enq_s else None
     clocks = sampler.stop() if rank == 0 else None
+    ms_e2e_u8 = None
+    if full:   # same pipeline copying back img_E (uint8, what the reference saves, S1:133-138) instead of float32 x: 4x fewer D2H bytes
+        pipe8 = pk.HostPipeline(B, N, n_slots=SLOTS, output='uint8')
+        h_x8 = [torch.empty((B, N, N), dtype=torch.uint8).pin_memory() for _ in range(SLOTS)]
+        ms_e2e_u8, _ = timed_pipelined(args.steps, args.warmup, pipe=pipe8, h_xs=h_x8)
+        pipe8.close()
     # the step per mask kind (the headline cycles through the three): cartesian masks run on the row-separable kernel K3
     per_mask = {}
     if full:
@@ -511,6 +517,12 @@ def run_ours(args):
                     'api': f'pnp_admm_cnc_mri_b200.HostPipeline.submit / wait (pnpadmm_reconstruct_host_pipelined_f32): pinned host buffers in '
                            f'and out every step; H2D / kernels / D2H on three streams, {SLOTS} device slots, the compute section of a step '
                            'replayed as one CUDA graph; every result is waited for and read on the host inside the timed region',
+                    'uint8_output': None if ms_e2e_u8 is None else {
+                        'value': its_step * args.steps / (ms_e2e_u8 * 1e-3), 'ms_per_step': ms_e2e_u8 / args.steps,
+                        'd2h_bytes_per_step': int(h_x.numel()),
+                        'what': "HostPipeline(output='uint8'): the D2H read is img_E = uint8(round(255 x)) as the reference saves it (S1:133-138) instead "
+                                'of the float32 x; shown because the float32 read makes the 8-GPU e2e run D2H-bound on this box (aggregate pinned D2H '
+                                'saturates at 71-94 GB/s for 2-8 GPUs, tools/pcie_probe.py, profiles/r2_pcie_probe.txt)'},
                     'sync_call': {'value': its_step * args.steps / (ms_e2e_sync * 1e-3), 'ms_per_step': ms_e2e_sync / args.steps,
                                   'api': 'pnpadmm_reconstruct_host_f32: one stream, host synchronises after every step '
                                          '(copies not overlapped; single-call latency)'}},

@@ -197,6 +197,12 @@ int pnpadmm_reconstruct_host_f32(const uint8_t* h_img, const uint8_t* h_mask, co
 typedef struct pnpadmm_pipeline_s* pnpadmm_pipeline_t;
 int pnpadmm_pipeline_create(pnpadmm_pipeline_t* out, int n_slots);     /* on the current device */
 int pnpadmm_pipeline_destroy(pnpadmm_pipeline_t pipe);                 /* after the streams have drained */
+/* What a pipeline copies back: PNPADMM_OUT_F32 (default) = the reconstructions x as float32 [B][N][N] (what the reference
+ * stores in out[n], S1:132); PNPADMM_OUT_U8 = img_E as the reference SAVES it (S1:133-138: uint8(round(255 x)), saturated),
+ * 4x fewer bytes over the host link - h_x then points to B*N*N bytes.  Set between batches, not while a call is in flight. */
+#define PNPADMM_OUT_F32 0
+#define PNPADMM_OUT_U8  1
+int pnpadmm_pipeline_set_output(pnpadmm_pipeline_t pipe, int format);
 size_t pnpadmm_host_pipeline_scratch_bytes(int B, int N, int n_slots);
 int pnpadmm_reconstruct_host_pipelined_f32(pnpadmm_pipeline_t pipe,
                                            const uint8_t* h_img, const uint8_t* h_mask, const float* h_noise,

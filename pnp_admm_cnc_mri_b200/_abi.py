@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(PKG, 'libpnpadmm.so')
 OK, ERR_BAD_ARG, ERR_BAD_SIZE, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 PROX_L1, PROX_CNC = 0, 1
 KERNEL_AUTO, KERNEL_CLUSTER, KERNEL_STREAMING, KERNEL_ROWSEP = 0, 1, 2, 3
+OUT_F32, OUT_U8 = 0, 1
 ABI_VERSION = 2
 
 # every symbol include/pnpadmm.h declares (tests check the .so exports all of them)
@@ -22,7 +23,7 @@ SYMBOLS = [
     'pnpadmm_iterate_f32', 'pnpadmm_iterate_f64', 'pnpadmm_solve_f32', 'pnpadmm_solve_f64',
     'pnpadmm_reconstruct_f32', 'pnpadmm_reconstruct_f64',
     'pnpadmm_host_scratch_bytes', 'pnpadmm_reconstruct_host_f32',
-    'pnpadmm_pipeline_create', 'pnpadmm_pipeline_destroy',
+    'pnpadmm_pipeline_create', 'pnpadmm_pipeline_destroy', 'pnpadmm_pipeline_set_output',
     'pnpadmm_host_pipeline_scratch_bytes', 'pnpadmm_reconstruct_host_pipelined_f32', 'pnpadmm_reconstruct_host_wait',
     'pnpadmm_soft_f32', 'pnpadmm_soft_f64', 'pnpadmm_cnc_combine_f32', 'pnpadmm_cnc_combine_f64',
     'pnpadmm_dual_update_f32', 'pnpadmm_dual_update_f64', 'pnpadmm_measure_fp32_peak',
@@ -92,6 +93,8 @@ def load() -> ctypes.CDLL:
     lib.pnpadmm_host_pipeline_scratch_bytes.argtypes = [i, i, i]
     lib.pnpadmm_pipeline_create.restype = i
     lib.pnpadmm_pipeline_create.argtypes = [POINTER(c_void_p), i]
+    lib.pnpadmm_pipeline_set_output.restype = i
+    lib.pnpadmm_pipeline_set_output.argtypes = [p, i]
     lib.pnpadmm_pipeline_destroy.restype = i
     lib.pnpadmm_pipeline_destroy.argtypes = [p]
     lib.pnpadmm_reconstruct_host_pipelined_f32.restype = i

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/pnpadmm.h"
@@ -58,7 +59,8 @@ struct DeviceState {
     int max_cl8 = 0, max_cl16 = 0;  // co-resident clusters of the 8-CTA / 16-CTA variants of K1
     int k1_cluster = 8;           // geometry used by default
     cudaStream_t side = nullptr;  // hybrid schedule: the K2 share of a batch runs here, beside K1
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;   // fork / join of the hybrid schedule (created once, with the side stream)
+    cudaStream_t side2 = nullptr; // second half of the K2 share
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, join_ev2 = nullptr;   // fork / join of the hybrid schedule (created once, with the side streams)
     std::mutex mu;                // guards the side stream's fork/join pairs and this device's K2 graph cache
     // timing model of the hybrid schedule, measured once per device by calibrate_hybrid() (literals = fallback, round-1 B200 fit)
     double tau1_us = 10.1;        // K1: one plane-iteration of one cluster, all clusters busy
@@ -181,10 +183,28 @@ template <> struct S2<float> {
         e = set_attrs_n<512>(); if (e != cudaSuccess) return e;
         return set_attrs_n<1024>();
     }
+    // The passes of the iteration are launched with programmatic stream serialisation: a pass may be scheduled while the
+    // previous one drains and waits (griddepcontrol.wait) right before it first touches the data (PNPADMM_NO_PDL=1: plain launches).
+    static bool pdl_enabled() {
+        static const bool on = [] { const char* e = getenv("PNPADMM_NO_PDL"); return !(e && atoi(e) != 0); }();
+        return on;
+    }
+    template <typename... KArgs, typename... Args>
+    static void launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+        (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    }
     // `planes`: packed planes, or images for the per-image modes (FWD_IMG, INV_ABS, FWD_ACQ, INV)
     template <int N, int MODE> static void rows_n(const StreamParams<float>& p, int planes, cudaStream_t st) {
         typedef s2::RowsGeo<N> G;
-        s2::rows2_kernel<N, MODE><<<planes * (N / G::L), s2::kRowsThreads, G::kSmemBytes, st>>>(p);
+        constexpr bool kIter = (MODE == RM_INV_PROX_FWD);
+        launch(s2::rows2_kernel<N, MODE>, (unsigned)(planes * (N / G::L)), s2::kRowsThreads, G::kSmemBytes, st, kIter, p);
     }
     template <int MODE> static int rows(const StreamParams<float>& p, int planes, cudaStream_t st) {
         switch (p.N) {
@@ -205,8 +225,8 @@ template <> struct S2<float> {
             if (!lsu && plane_tensor_map(&tmK, p.K, planes, N, G::C) && plane_tensor_map(&tmG, p.G, planes, N, G::C)) {
                 static const bool tma_store = getenv("PNPADMM_COLS_TMA_STORE") != nullptr;   // experiment: measured 1 % slower
                 const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
-                if (tma_store) s2::cols2_tma_kernel<N, true><<<grid, G::kThreads, G::kSmemBytes + 32, st>>>(p, mpack, tmK, tmG);
-                else s2::cols2_tma_kernel<N, false><<<grid, G::kThreads, G::kSmemBytes + 32, st>>>(p, mpack, tmK, tmG);
+                if (tma_store) launch(s2::cols2_tma_kernel<N, true>, grid, G::kThreads, G::kSmemBytes + 32, st, true, p, mpack, tmK, tmG);
+                else launch(s2::cols2_tma_kernel<N, false>, grid, G::kThreads, G::kSmemBytes + 32, st, true, p, mpack, tmK, tmG);
                 return;
             }
         }
@@ -314,6 +334,8 @@ int ensure_device(DeviceState** out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&d.fork_ev, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&d.join_ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.side2, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.join_ev2, cudaEventDisableTiming));
         d.ready = true;
         calibrate_hybrid(&d);     // best effort: the literals stay if it cannot run
     }
@@ -860,6 +882,8 @@ void calibrate_hybrid(DeviceState* d) {
     (void)cudaGetLastError();
 }
 
+bool k2_split_enabled();
+
 template <typename T>
 int xupdate_impl(const T* z, const T* wv, T* x, T* xpw, int B, int N, int mask_batched, int kernel, void* ws,
                  size_t ws_bytes, cudaStream_t st) {
@@ -921,13 +945,31 @@ int iterate_impl(T* x, T* z, T* wv, int B, int N, int mask_batched, int prox, in
         // launch order) is not interleaved with another host thread's: the device mutex.
         std::lock_guard<std::mutex> lk(d->mu);
         CUDA_TRY(cudaEventRecord(d->fork_ev, st));
-        CUDA_TRY(cudaStreamWaitEvent(d->side, d->fork_ev, 0));
         rc = ClusterDispatch<T>::run(w1, z, wv, x, z, wv, nullptr, B1, iters, pp, d, st);
-        if (rc == PNPADMM_OK)
-            rc = stream2_iterate<T>(w2, x + (size_t)B1 * nn, z + (size_t)B1 * nn, wv + (size_t)B1 * nn, B - B1, N, pp, iters,
-                                    d->sm_count - 8 * d->max_clusters_256, d->side, /*locked=*/true);
-        CUDA_TRY(cudaEventRecord(d->join_ev, d->side));
-        CUDA_TRY(cudaStreamWaitEvent(st, d->join_ev, 0));
+        if (rc) return rc;
+        const int sms = d->sm_count - 8 * d->max_clusters_256;
+        auto share = [&](int pa, int pb, cudaStream_t s2, cudaEvent_t join) -> int {   // planes [pa, pb) on the streaming kernels in s2
+            const int ba = w.solo ? pa : 2 * pa, bb0 = w.solo ? pb : 2 * pb, bb = bb0 < B ? bb0 : B;
+            Workspace<T> ws2 = w;
+            ws2.P = pb - pa;
+            ws2.K = w.K + (size_t)pa * nn; ws2.G = w.G + (size_t)pa * nn;
+            if (w.solo) { ws2.mcode = w.mcode + (size_t)pa * nn; ws2.mpack = w.mpack + (size_t)pa * (nn / 16); }
+            CUDA_TRY(cudaStreamWaitEvent(s2, d->fork_ev, 0));
+            const int r = stream2_iterate<T>(ws2, x + (size_t)ba * nn, z + (size_t)ba * nn, wv + (size_t)ba * nn, bb - ba, N, pp, iters, sms,
+                                             s2, /*locked=*/true);
+            if (r) return r;
+            CUDA_TRY(cudaEventRecord(join, s2));
+            CUDA_TRY(cudaStreamWaitEvent(st, join, 0));
+            return PNPADMM_OK;
+        };
+        const int P2 = w.P - P1;
+        if (k2_split_enabled() && P2 >= 2) {
+            const int pm = P1 + (P2 + 1) / 2;
+            rc = share(P1, pm, d->side, d->join_ev);
+            if (rc == PNPADMM_OK) rc = share(pm, w.P, d->side2, d->join_ev2);
+        } else {
+            rc = share(P1, w.P, d->side, d->join_ev);
+        }
         return rc;
     }
 
@@ -975,6 +1017,13 @@ int solve_impl(const T* y, const uint8_t* mask, T* x, T* z, T* wv, int B, int N,
 // schedule gives to the streaming kernels go through acquisition / zero-fill / prepare on the side stream, concurrently.
 // Everything else: acquisition into the workspace's Y region, then solve.  img or img8 (uint8 gray levels, / 255) is given.
 // ------------------------------------------------------------------------------------------
+// Experiment knob PNPADMM_K2_SPLIT=1: the K2 share of the hybrid schedule in two halves on two side streams (measured in round 2:
+// within run-to-run noise of the single stream, so it stays off).
+bool k2_split_enabled() {
+    static const bool on = [] { const char* e = getenv("PNPADMM_K2_SPLIT"); return e ? atoi(e) != 0 : false; }();
+    return on;
+}
+
 template <typename T> struct FusedDispatch {
     static bool run(int*, const Workspace<T>&, const T*, const uint8_t*, const uint8_t*, const T*, T*, T*, T*, int, int, int, int,
                     double, double, double, double, int, DeviceState*, cudaStream_t) { return false; }
@@ -1042,44 +1091,56 @@ template <> struct FusedDispatch<float> {
         cp.cf1v = (float)(0.5 * g / n2); cp.cf2v = (float)(g / n2);
         cp.no_memset = 1;
         if (P1 == w.P) { *rc = launch_cluster(cp, d, st); return true; }
-        // hybrid: planes [P1, P) = images [B1, B) on the streaming kernels in the side stream, prologue included
-        const int B2 = B - B1, P2 = w.P - P1;
+        // hybrid: planes [P1, P) = images [B1, B) on the streaming kernels, prologue included, in the side stream
         std::lock_guard<std::mutex> lk(d->mu);
-        if (cudaEventRecord(d->fork_ev, st) != cudaSuccess || cudaStreamWaitEvent(d->side, d->fork_ev, 0) != cudaSuccess) {
+        if (cudaEventRecord(d->fork_ev, st) != cudaSuccess) {
             *rc = fail(PNPADMM_ERR_CUDA, "fork of the hybrid schedule failed: %s", cudaGetErrorString(cudaGetLastError())); return true;
         }
         *rc = launch_cluster(cp, d, st);
         if (*rc) return true;
-        cudaStream_t s2 = d->side;
         const int sms = d->sm_count - 8 * d->max_clusters_256;
-        float* x2 = x + (size_t)B1 * nn; float* z2 = z + (size_t)B1 * nn; float* w2v = wv + (size_t)B1 * nn;
-        const float* img2 = img ? img + (size_t)B1 * nn : nullptr;
-        if (!img2) {   // uint8 input: the streaming kernels want float images; x2 is free until the iterations write it
-            u8_to_unit_kernel<float><<<grid_1d((size_t)B2 * nn, sms), 256, 0, s2>>>(img8 + (size_t)B1 * nn, x2, (size_t)B2 * nn);
-            img2 = x2;
+        auto share = [&](int pa, int pb, cudaStream_t s2, cudaEvent_t join) -> int {
+            const int ba = 2 * pa, bb = (2 * pb < B) ? 2 * pb : B, B2 = bb - ba, P2 = pb - pa;
+            CUDA_TRY(cudaStreamWaitEvent(s2, d->fork_ev, 0));
+            float* x2 = x + (size_t)ba * nn; float* z2 = z + (size_t)ba * nn; float* w2v = wv + (size_t)ba * nn;
+            const float* img2 = img ? img + (size_t)ba * nn : nullptr;
+            if (!img2) {   // uint8 input: the streaming kernels want float images; x2 is free until the iterations write it
+                u8_to_unit_kernel<float><<<grid_1d((size_t)B2 * nn, sms), 256, 0, s2>>>(img8 + (size_t)ba * nn, x2, (size_t)B2 * nn);
+                img2 = x2;
+            }
+            StreamParams<float> p = base_params(w, B2, N);
+            p.P = P2;
+            cx<float>* T1 = w.T1 + (size_t)ba * nn; cx<float>* Y2 = w.Y + (size_t)ba * nn;
+            p.img = img2; p.cout = T1;
+            S2<float>::template rows<RM_FWD_IMG>(p, B2, s2);
+            p.cin = T1; p.cout = Y2; p.mask = mask; p.mask_batched = 0;
+            p.noise = reinterpret_cast<const cx<float>*>(noise); p.noise_batched = 0;
+            S2<float>::template cols<CM_FWD_ACQ>(p, B2, nullptr, sms, s2);
+            p.cin = Y2; p.cout = T1;
+            S2<float>::template cols<CM_INV>(p, B2, nullptr, sms, s2);
+            p.cin = T1; p.x = z2;
+            S2<float>::template rows<RM_INV_ABS>(p, B2, s2);
+            copy_zero_kernel<float><<<grid_1d((size_t)B2 * nn, sms), 256, 0, s2>>>(z2, nullptr, w2v, (size_t)B2 * nn);
+            const size_t total = (size_t)P2 * nn;
+            prepare_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, s2>>>(Y2, mask, w.G + (size_t)pa * nn, nullptr, B2, P2, N, 0, 0,
+                                                                                (float)(g / n2), nullptr, 0);
+            LAUNCH_CHECK("streaming prologue of the hybrid share");
+            Workspace<float> w2 = w;
+            w2.P = P2; w2.K = w.K + (size_t)pa * nn; w2.G = w.G + (size_t)pa * nn;
+            const int r = stream2_iterate<float>(w2, x2, z2, w2v, B2, N, pp, iters, sms, s2, /*locked=*/true);
+            if (r) return r;
+            CUDA_TRY(cudaEventRecord(join, s2));
+            CUDA_TRY(cudaStreamWaitEvent(st, join, 0));
+            return PNPADMM_OK;
+        };
+        const int P2 = w.P - P1;
+        if (k2_split_enabled() && P2 >= 2) {
+            const int pm = P1 + (P2 + 1) / 2;
+            *rc = share(P1, pm, d->side, d->join_ev);
+            if (*rc == PNPADMM_OK) *rc = share(pm, w.P, d->side2, d->join_ev2);
+        } else {
+            *rc = share(P1, w.P, d->side, d->join_ev);
         }
-        StreamParams<float> p = base_params(w, B2, N);
-        p.P = P2;
-        cx<float>* T1 = w.T1 + (size_t)B1 * nn; cx<float>* Y2 = w.Y + (size_t)B1 * nn;
-        p.img = img2; p.cout = T1;
-        S2<float>::template rows<RM_FWD_IMG>(p, B2, s2);
-        p.cin = T1; p.cout = Y2; p.mask = mask; p.mask_batched = 0;
-        p.noise = reinterpret_cast<const cx<float>*>(noise); p.noise_batched = 0;
-        S2<float>::template cols<CM_FWD_ACQ>(p, B2, nullptr, sms, s2);
-        p.cin = Y2; p.cout = T1;
-        S2<float>::template cols<CM_INV>(p, B2, nullptr, sms, s2);
-        p.cin = T1; p.x = z2;
-        S2<float>::template rows<RM_INV_ABS>(p, B2, s2);
-        copy_zero_kernel<float><<<grid_1d((size_t)B2 * nn, sms), 256, 0, s2>>>(z2, nullptr, w2v, (size_t)B2 * nn);
-        const size_t total = (size_t)P2 * nn;
-        prepare_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, s2>>>(Y2, mask, w.G + (size_t)P1 * nn, nullptr, B2, P2, N, 0, 0,
-                                                                            (float)(g / n2), nullptr, 0);
-        if (cudaGetLastError() != cudaSuccess) { *rc = fail(PNPADMM_ERR_CUDA, "launch of the streaming prologue failed"); return true; }
-        Workspace<float> w2 = w;
-        w2.P = P2; w2.K = w.K + (size_t)P1 * nn; w2.G = w.G + (size_t)P1 * nn;
-        *rc = stream2_iterate<float>(w2, x2, z2, w2v, B2, N, pp, iters, sms, s2, /*locked=*/true);
-        if (cudaEventRecord(d->join_ev, s2) != cudaSuccess || cudaStreamWaitEvent(st, d->join_ev, 0) != cudaSuccess)
-            *rc = fail(PNPADMM_ERR_CUDA, "join of the hybrid schedule failed: %s", cudaGetErrorString(cudaGetLastError()));
         return true;
     }
 };
@@ -1157,6 +1218,15 @@ int metrics_impl(const T* x, const uint8_t* ref, int B, int N, int quantize, dou
     metrics_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(acc, out, B, N);
     LAUNCH_CHECK("metrics_finalize_kernel");
     return PNPADMM_OK;
+}
+
+// img_E = saturate_cast<uint8>(255 x), rounding half to even like cv2.imwrite of the reference's float image (S1:133-138)
+// and np.uint8((clip(x, 0, 1) * 255).round()) of util.single2uint (S6:315)
+__global__ void unit_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = fminf(fmaxf(rintf(255.0f * x[i]), 0.f), 255.f);
+        out[i] = (uint8_t)v;
+    }
 }
 
 // FP32 FMA throughput probe: 8 independent FMA chains per thread.
@@ -1429,7 +1499,7 @@ namespace {
 struct PipeKey {
     void* d_scratch; void* ws; size_t scratch_bytes, wsb;
     double lambda1, reo, alpha, b;
-    int B, N, prox, iters, kernel, slot, n_slots, pad;
+    int B, N, prox, iters, kernel, slot, n_slots, out_format;
 };
 struct PipeGraph {
     bool valid = false;
@@ -1445,6 +1515,7 @@ constexpr int kPipeGraphs = 8;
 // (u8 -> unit, acquisition, zero-fill, prepare, iterations: one graph launch per step instead of ~25 driver calls).
 struct pnpadmm_pipeline_s {
     int dev = 0, n_slots = 2;
+    int out_format = PNPADMM_OUT_F32;
     cudaEvent_t in_ready[PNPADMM_PIPELINE_MAX_SLOTS], done[PNPADMM_PIPELINE_MAX_SLOTS], out_done[PNPADMM_PIPELINE_MAX_SLOTS];
     bool used[PNPADMM_PIPELINE_MAX_SLOTS];
     PipeGraph graphs[kPipeGraphs];
@@ -1476,6 +1547,14 @@ int pnpadmm_pipeline_create(pnpadmm_pipeline_t* out, int n_slots) {
         }
     }
     *out = p;
+    return PNPADMM_OK;
+}
+
+int pnpadmm_pipeline_set_output(pnpadmm_pipeline_t p, int format) {
+    if (!p) return fail(PNPADMM_ERR_BAD_ARG, "pipeline_set_output: NULL pipeline");
+    if (format != PNPADMM_OUT_F32 && format != PNPADMM_OUT_U8) return fail(PNPADMM_ERR_BAD_ARG, "pipeline_set_output: unknown format %d", format);
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->out_format = format;
     return PNPADMM_OK;
 }
 
@@ -1537,9 +1616,15 @@ int pnpadmm_reconstruct_host_pipelined_f32(pnpadmm_pipeline_t pipe, const uint8_
     CUDA_TRY(cudaStreamWaitEvent(sc, pipe->in_ready[slot], 0));
     if (pipe->used[slot]) CUDA_TRY(cudaStreamWaitEvent(sc, pipe->out_done[slot], 0));
     (void)d_img; (void)d_y;
+    const bool out_u8 = pipe->out_format == PNPADMM_OUT_U8;
     auto enqueue_compute = [&]() -> int {
-        return reconstruct_impl<float>(nullptr, d_img8[slot], d_mask[slot], d_noise[slot], d_x[slot], d_z, d_w, B, N, 0, 0, prox, iters,
-                                       lambda1, reo, alpha, b, kernel, ws, wsb, sc);
+        const int r = reconstruct_impl<float>(nullptr, d_img8[slot], d_mask[slot], d_noise[slot], d_x[slot], d_z, d_w, B, N, 0, 0, prox, iters,
+                                              lambda1, reo, alpha, b, kernel, ws, wsb, sc);
+        if (r || !out_u8) return r;
+        // img_E as the reference saves it (S1:133-138): uint8 gray levels; the slot's image buffer is free after the solve
+        unit_to_u8_kernel<<<grid_1d(n, d->sm_count), 256, 0, sc>>>(d_x[slot], d_img8[slot], n);
+        LAUNCH_CHECK("unit_to_u8_kernel");
+        return PNPADMM_OK;
     };
     // The compute section has fixed arguments per (slot, parameters): replay it as one graph from the second sighting on.
     static const char* nograph = getenv("PNPADMM_NO_GRAPH");
@@ -1554,6 +1639,7 @@ int pnpadmm_reconstruct_host_pipelined_f32(pnpadmm_pipeline_t pipe, const uint8_
         key.d_scratch = d_scratch; key.ws = ws; key.scratch_bytes = scratch_bytes; key.wsb = wsb;
         key.lambda1 = lambda1; key.reo = reo; key.alpha = alpha; key.b = b;
         key.B = B; key.N = N; key.prox = prox; key.iters = iters; key.kernel = kernel; key.slot = slot; key.n_slots = S;
+        key.out_format = pipe->out_format;
         PipeGraph* victim = nullptr;
         for (int i = 0; i < kPipeGraphs; ++i) {
             PipeGraph& e = pipe->graphs[i];
@@ -1592,7 +1678,8 @@ int pnpadmm_reconstruct_host_pipelined_f32(pnpadmm_pipeline_t pipe, const uint8_
     }
     CUDA_TRY(cudaEventRecord(pipe->done[slot], sc));
     CUDA_TRY(cudaStreamWaitEvent(so, pipe->done[slot], 0));
-    CUDA_TRY(cudaMemcpyAsync(h_x, d_x[slot], n * 4, cudaMemcpyDeviceToHost, so));
+    if (out_u8) CUDA_TRY(cudaMemcpyAsync(h_x, d_img8[slot], n, cudaMemcpyDeviceToHost, so));
+    else CUDA_TRY(cudaMemcpyAsync(h_x, d_x[slot], n * 4, cudaMemcpyDeviceToHost, so));
     CUDA_TRY(cudaEventRecord(pipe->out_done[slot], so));
     pipe->used[slot] = true;
     return PNPADMM_OK;

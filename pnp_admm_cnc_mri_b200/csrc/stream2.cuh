@@ -28,6 +28,10 @@
 namespace pnp {
 namespace s2 {
 
+// programmatic dependent launch (griddepcontrol): see rows2_kernel
+PNP_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PNP_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int kRowsThreads = 128;
 
 template <int N> struct ColsGeo {
@@ -130,6 +134,11 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
         if (bytes2) k1::mbar_arm_tx(bar2, bytes2);
     }
     __syncthreads();                        // barriers initialised and armed before any copy or wait
+    // Programmatic dependent launch: everything above needs nothing from the kernel before this one in the stream; its output
+    // is complete and visible after the wait (a no-op for an ordinary launch).  The dependents may be scheduled right away: they
+    // wait at the same point.
+    pdl_wait();
+    pdl_launch_dependents();
     // Issuing a bulk copy costs its thread ~140 cycles (measured on K5), so the copies are issued by one lane of
     // each of the four warps instead of one after the other by thread 0 (the K rows, needed first, by warps 0 and 3).
     if (tid == 0) {
@@ -267,6 +276,8 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
     cf32* out = (MODE == CM_FWD_BLEND_INV) ? p.K : p.cout;
     const cf32* aux = (MODE == CM_FWD_BLEND_INV) ? p.G : p.noise;   // second streamed operand
     const bool aux_batched = (MODE == CM_FWD_BLEND_INV) ? true : (p.noise_batched != 0);
+    pdl_wait();
+    pdl_launch_dependents();
     const float cf1 = (MODE == CM_FWD_BLEND_INV) ? p.cf[1] : 0.f, cf2 = (MODE == CM_FWD_BLEND_INV) ? p.cf[2] : 0.f;
 
     // tile copy: N rows x (C * 8) bytes = N * C / 2 pieces of 16 bytes, 8 per thread
@@ -380,7 +391,6 @@ cols2_tma_kernel(const StreamParams<float> p, const uint32_t* __restrict__ mpack
     constexpr int tiles_per_plane = N / C;
     const int ntiles = p.P * tiles_per_plane;
     const size_t nn = (size_t)N * N;
-    const float cf1 = p.cf[1], cf2 = p.cf[2];
 
     if (tid == 0) {
         k1::mbar_init(bar0, 1); k1::mbar_init(bar0 + 8, 1); k1::mbar_init(bar0 + 16, 1);
@@ -392,6 +402,9 @@ cols2_tma_kernel(const StreamParams<float> p, const uint32_t* __restrict__ mpack
         TW3[q] = ld_tw(reinterpret_cast<const cf32*>(g_tw_f32) + ((q >> 8) + 1) * (q & 255) * (kTwMax / N));
     const Tw3Table tw3{TW3};
     __syncthreads();
+    pdl_wait();                    // tables and barriers are set up; the K plane of the previous pass is complete from here on
+    pdl_launch_dependents();
+    const float cf1 = p.cf[1], cf2 = p.cf[2];
 
     // one thread: expect the tile's bytes, then one box per 256 rows
     auto issue = [&](const CUtensorMap* tm, int tile, uint32_t dst, uint32_t bar) {

@@ -243,8 +243,11 @@ class HostPipeline:
 
     Host tensors should be pinned (otherwise the copies are synchronous)."""
 
-    def __init__(self, B: int, N: int, n_slots: int = 2, device=None):
+    def __init__(self, B: int, N: int, n_slots: int = 2, device=None, output: str = 'float32'):
         import ctypes
+        if output not in ('float32', 'uint8'):
+            raise ValueError("output must be 'float32' (the reconstructions x) or 'uint8' (img_E as the reference saves it)")
+        self.output = output
         self.lib = _abi.load()
         self.device = _require_cuda(device)
         self.B, self.N, self.n_slots = int(B), int(N), int(n_slots)
@@ -255,6 +258,8 @@ class HostPipeline:
             h = ctypes.c_void_p()
             _abi.check(self.lib.pnpadmm_pipeline_create(ctypes.byref(h), self.n_slots))
             self._h = h
+            if output == 'uint8':
+                _abi.check(self.lib.pnpadmm_pipeline_set_output(h, _abi.OUT_U8))
             self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.ws_bytes = self.lib.pnpadmm_workspace_bytes(self.B, self.N, 0, 0)
             self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
@@ -270,8 +275,9 @@ class HostPipeline:
             raise ValueError(f'h_mask must be a contiguous host uint8 tensor of shape {(N, N)}')
         if not (h_noise.dtype == torch.float32 and h_noise.numel() == 2 * N * N and h_noise.is_contiguous() and not h_noise.is_cuda):
             raise ValueError('h_noise must be a contiguous host float32 tensor holding (N,N) complex64 as (re, im) pairs')
-        if not (h_x.dtype == torch.float32 and tuple(h_x.shape) == (B, N, N) and h_x.is_contiguous() and not h_x.is_cuda):
-            raise ValueError(f'h_x must be a contiguous host float32 tensor of shape {(B, N, N)}')
+        want = torch.uint8 if self.output == 'uint8' else torch.float32
+        if not (h_x.dtype == want and tuple(h_x.shape) == (B, N, N) and h_x.is_contiguous() and not h_x.is_cuda):
+            raise ValueError(f'h_x must be a contiguous host {want} tensor of shape {(B, N, N)}')
         with torch.cuda.device(self.device):
             _abi.check(self.lib.pnpadmm_reconstruct_host_pipelined_f32(
                 self._h, h_img.data_ptr(), h_mask.data_ptr(), h_noise.data_ptr(), h_x.data_ptr(), B, N, _PROX[prox],

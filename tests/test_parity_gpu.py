@@ -408,6 +408,18 @@ def test_pipelined_host_call_matches_sync_call(pk, cs_inputs):
         for i in range(steps):
             assert torch.equal(got[i], want[(i % 4, i % 3)]), (S, i)
         pipe.close()
+    # uint8 output (img_E as the reference saves it, S1:133-138): the float32 result rounded half-to-even and saturated
+    pipe = pk.HostPipeline(B, N, n_slots=2, output='uint8')
+    h8 = [torch.empty((B, N, N), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for i in range(4):
+        if i >= 2:
+            pipe.wait(i & 1)
+        pipe.submit(i & 1, imgs[i % 4], masks[i % 3], noise, h8[i & 1], prox='cnc', **P)
+    for i in (2, 3):
+        pipe.wait(i & 1)
+        w32 = want[(i % 4, i % 3)].numpy()
+        assert np.array_equal(h8[i & 1].numpy(), np.uint8(np.clip(np.rint(np.float32(255.0) * w32), 0, 255))), i
+    pipe.close()
     # and against the oracle for one image of the last step
     xr = orc.admm_cnc(orc.preprocess_uint8(cs_inputs['images'][9]), cs_inputs['masks'][0].astype(np.float64), cs_inputs['noises'], **P)
     assert rel(want[(3, 0)][0].numpy(), xr) < TOL32
