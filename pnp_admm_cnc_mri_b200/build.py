@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libpnpadmm.so')
 SOURCES = ['pnpadmm.cu', 'common.cuh', 'streaming.cuh', 'stream2.cuh', 'stream2_core.cuh', 'cluster256.cuh', 'cluster256_core.cuh',
-           'metrics.cuh', 'dncnn_tc.cuh']
+           'metrics.cuh', 'dncnn_tc.cuh', 'rowsep256.cuh', 'rowsepN.cuh', 'rowsep_core.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 

@@ -29,22 +29,24 @@ struct RowSepParams {
     const cf32* planes;        // [3][256][256] row-major: colIFFT of NcS, nH, nA
     const uint32_t* rcodes;    // [16] packed codes of kc = t + 16 j
     const uint32_t* rhere;     // [16] m[kc] bits
-    const int* sep;            // number of constant mask columns (256 = separable)
+    const int* sep;            // blocks of the preparation launch that saw a mask bin differ from k-space row 0 (0 = separable)
     float ncf1, ncf2;          // N * g / (2 N^2), N * g / N^2
     ProxParams<float> prox;
 };
 
-// one block of 256 threads for the flag and the words; every block for its 256 bins of the noise-term planes
+// every thread: the noise terms of one bin, and whether its mask bin equals the bin of k-space row 0 in the same column (`bad`
+// counts the blocks that saw a difference; zeroed by the host before the launch); block 0 also writes the 2 x 16 words
 __global__ void prepare_rowsep_kernel(const uint8_t* __restrict__ mask, const cf32* __restrict__ noise, float g_over_n2,
                                       cf32* __restrict__ planes, uint32_t* __restrict__ rcodes, uint32_t* __restrict__ rhere,
-                                      int* __restrict__ sep) {
+                                      int* __restrict__ bad) {
     const int bin = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bin < kN * kN) k1::rsep_noise_terms(mask, noise, g_over_n2, bin, planes);
-    if (blockIdx.x == 0) {
-        const int n_const = __syncthreads_count(k1::rsep_column_is_constant(mask, threadIdx.x) ? 1 : 0);
-        if (threadIdx.x == 0) *sep = n_const;
-        if (threadIdx.x < 16) k1::rsep_words(mask, threadIdx.x, rcodes + threadIdx.x, rhere + threadIdx.x);
+    int differs = 0;
+    if (bin < kN * kN) {
+        k1::rsep_noise_terms(mask, noise, g_over_n2, bin, planes);
+        differs = ((mask[bin] != 0) != (mask[bin % kN] != 0)) ? 1 : 0;
     }
+    if (__syncthreads_or(differs) && threadIdx.x == 0) atomicAdd(bad, 1);
+    if (blockIdx.x == 0 && threadIdx.x < 16) k1::rsep_words(mask, threadIdx.x, rcodes + threadIdx.x, rhere + threadIdx.x);
 }
 
 __global__ void __launch_bounds__(256, 2) rowsep256_kernel(const RowSepParams p) {
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(256, 2) rowsep256_kernel(const RowSepParams p)
     c.smem = smem;
     c.rank = 0;
     const size_t nn = (size_t)kN * kN;
-    if (*p.sep != kN) {   // the mask is not made of full k-space lines: fail loudly
+    if (*p.sep != 0) {   // the mask is not made of full k-space lines: fail loudly
         const float qnan = __int_as_float(0x7fc00000);
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)p.B * nn; i += (size_t)gridDim.x * blockDim.x) {
             p.x[i] = qnan; p.z[i] = qnan; p.w[i] = qnan;

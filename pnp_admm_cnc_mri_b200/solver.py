@@ -213,7 +213,7 @@ class AdmmSolver:
             img8, imgf = t.to(self.device).contiguous(), None
         else:
             img8, imgf = None, t.to(device=self.device, dtype=self.rdtype).contiguous()
-        if (kernel == 'auto' and self.N == 256 and not self.f64 and not self.mask_batched and iter_num >= 1
+        if (kernel == 'auto' and self.N in (256, 512, 1024) and not self.f64 and not self.mask_batched and iter_num >= 1
                 and mask_is_row_separable(mask)):
             kernel = 'rowsep'                  # full k-space lines: every image row is solved on its own (K3)
         m = self._mask(mask)

@@ -164,7 +164,7 @@ def s2emu():
     so = os.path.join(EMU_DIR, 's2_emu.so')
     src = os.path.join(EMU_DIR, 's2_emu.cpp')
     deps = [src] + [os.path.join(ROOT, 'pnp_admm_cnc_mri_b200', 'csrc', f)
-                    for f in ('stream2_core.cuh', 'cluster256_core.cuh', 'common.cuh')]
+                    for f in ('stream2_core.cuh', 'cluster256_core.cuh', 'common.cuh', 'rowsep_core.cuh')]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', so, src])
     lib = ctypes.CDLL(so)
@@ -190,3 +190,35 @@ def test_k2_packed_codes(s2emu):
         for t, kc in ((0, 0), (T - 1, N - 1), (3, 17)):
             w = s2emu.s2_pack_codes(mc.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), N, t, kc)
             assert [(w >> (2 * m)) & 3 for m in range(16)] == [int(mc[t + T * m, kc]) for m in range(16)]
+
+
+@pytest.mark.parametrize('N,prox', [(256, 'cnc'), (512, 'cnc'), (512, 'l1'), (1024, 'cnc')])
+def test_k3n_emulated_rowsep_solve_matches_oracle(s2emu, N, prox):
+    """K3 on the K2 line FFT (rowsepN.cuh, N = 512 / 1024; 256 for A/B): synthetic Cartesian mask (full k-space lines), uint8 phantoms,
+    odd batch; the per-thread code of the kernel run line by line against the fp64 oracle."""
+    from pnp_admm_cnc_mri_b200 import data
+    B = 3 if N < 1024 else 1
+    P = dict(kat.L1_DEFAULTS) if prox == 'l1' else dict(kat.CNC_DEFAULTS)
+    P['iter_num'] = 50 if N <= 512 else 12
+    u8 = np.ascontiguousarray(np.uint8((data.phantoms(B, N, seed0=3) * 255).round()))
+    m = data.make_mask('cartesian', N, seed=5)
+    nz = data.make_noise(N, seed=6)
+    noise = np.ascontiguousarray(nz.astype(np.complex64)).view(np.float32)
+    mask = np.ascontiguousarray(m.astype(np.uint8))
+    a, l, reo, b = P.get('alpha', 0.), P['lambda1'], P['reo'], P.get('b', 1.)
+    g = 1 / (1 + 1 / (2 * reo))
+    f = ctypes.c_float
+    U8 = ctypes.POINTER(ctypes.c_uint8)
+    planes = np.zeros((3, N, N), np.complex64)
+    s2emu.k3n_noise_terms(mask.ctypes.data_as(U8), noise.ctypes.data_as(FP), N, f(g / (N * N)), planes.view(np.float32).ctypes.data_as(FP))
+    planes = np.ascontiguousarray((np.fft.ifft(planes.astype(np.complex128), axis=1) * N).astype(np.complex64))   # column IFFT, unnormalised
+    x, z, w = (np.zeros((B, N, N), np.float32) for _ in range(3))
+    rc = s2emu.k3n_emulate(N, u8.ctypes.data_as(U8), mask.ctypes.data_as(U8), planes.view(np.float32).ctypes.data_as(FP), f(reo),
+                           x.ctypes.data_as(FP), z.ctypes.data_as(FP), w.ctypes.data_as(FP), B, P['iter_num'], 0 if prox == 'l1' else 1,
+                           f(reo * l), f(1 / b), f(1 - a), f(a), f(a * reo * l * b), f(a * reo * l))
+    assert rc == 0
+    fn = orc.admm_l1 if prox == 'l1' else orc.admm_cnc
+    for k in range(B):
+        xr, zr, wr, _ = fn(np.float32(u8[k] / 255.), m.astype(np.float64), nz, return_state=True, **P)
+        assert np.linalg.norm(x[k] - xr) / np.linalg.norm(xr) < 1e-4, (N, prox, k)
+        assert np.linalg.norm(z[k] - zr) / np.linalg.norm(zr) < 1e-4

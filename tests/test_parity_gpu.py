@@ -713,8 +713,8 @@ def test_rowsep_kernel_refuses_other_masks_and_covers_batches(pk, cs_inputs):
     # asserted separability is verified on the device: a radial mask yields NaN, not a wrong reconstruction
     x, z, w = pk.AdmmSolver(3, 256).reconstruct(imgs, cs_inputs['masks'][1], nz, *args, kernel='rowsep')
     assert torch.isnan(x).all() and torch.isnan(z).all() and torch.isnan(w).all()
-    with pytest.raises(pk.PnpAdmmError):
-        pk.AdmmSolver(2, 512).reconstruct(data.phantoms(2, 512, 0), data.make_mask('cartesian', 512, 0), data.make_noise(512, 1), *args,
+    with pytest.raises(pk.PnpAdmmError):                  # sizes without a row-separable kernel say so
+        pk.AdmmSolver(2, 128).reconstruct(data.phantoms(2, 128, 0), data.make_mask('cartesian', 128, 0), data.make_noise(128, 1), *args,
                                           kernel='rowsep')
     # a synthetic Cartesian mask, a batch larger than one wave of CTAs (2 x 148 SMs x 16 rows), odd count
     B = 75
@@ -728,3 +728,30 @@ def test_rowsep_kernel_refuses_other_masks_and_covers_batches(pk, cs_inputs):
         assert rel(x[k], xr[k % 5]) < TOL32, k
     reps = x[:70].reshape(7, 10, 256, 256)                                    # period 10: same pair slot, same partner image
     assert np.array_equal(reps, np.broadcast_to(reps[:1], reps.shape))        # rows are independent: such copies are bit-identical
+
+
+@pytest.mark.parametrize('N,prox', [(512, 'cnc'), (512, 'l1'), (1024, 'cnc'), (1024, 'l1')])
+def test_rowsep_kernel_large_sizes(pk, N, prox):
+    """K3 on the K2 line FFT (rowsepN.cuh): Cartesian masks at N = 512 / 1024, the reference depth (50 iterations), odd batch, uint8
+    images in; picked by kernel='auto'.  Against the oracle and against the general streaming kernels."""
+    from pnp_admm_cnc_mri_b200 import data
+    B = 3
+    u8 = np.uint8((data.phantoms(B, N, seed0=80 + N // 512) * 255).round())
+    imgs = np.float32(u8 / 255.)
+    m = data.make_mask('cartesian', N, seed=6)
+    nz = data.make_noise(N, seed=10)
+    assert pk.mask_is_row_separable(m)
+    P = dict(kat.L1_DEFAULTS) if prox == 'l1' else dict(kat.CNC_DEFAULTS)
+    args = (prox, P['iter_num'], P['lambda1'], P['reo'], P.get('alpha', 0.0), P.get('b', 1.0))
+    s = pk.AdmmSolver(B, N)
+    x, z, w = (t.cpu().numpy() for t in s.reconstruct(u8, m, nz, *args))                  # auto -> rowsep
+    xs = s.reconstruct(imgs, m, nz, *args, kernel='streaming')[0].cpu().numpy()
+    xr, zr, wr, _ = oracle_batch(imgs, m, nz, prox, P, workers=B)
+    for k in range(B):
+        e = rel(x[k], xr[k])
+        print(f'rowsepN N={N} {prox} image {k}: rel-L2 vs oracle {e:.2e} (streaming kernels {rel(xs[k], xr[k]):.2e})')
+        assert e < TOL32 and rel(z[k], zr[k]) < TOL32, (N, prox, k)
+        assert rel(x[k], xs[k].astype(np.float64)) < TOL32
+    # a non-separable mask is refused loudly at these sizes too
+    bad = s.reconstruct(u8, data.make_mask('radial', N, seed=1), nz, *args, kernel='rowsep')[0]
+    assert torch.isnan(bad).all()

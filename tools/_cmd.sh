@@ -1,1 +1,3 @@
-for n in 1 2 4 8; do python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n tools/pcie_probe.py 2>/dev/null | grep ranks; done | tee gpurun_out/r2_pcie_probe.txt
+timeout 1500 python -m pytest tests/test_parity_gpu.py -q -x -s -k "rowsep" 2>&1 | grep -E "rowsep|passed|failed|Error|error|FAILED" | tail -25
+PNPADMM_K3_K1CODE=1 timeout 600 python -m pytest tests/test_parity_gpu.py -q -x -k "rowsep_kernel_kat or rowsep_kernel_refuses" 2>&1 | tail -2
+bash tools/ncu_r2.sh > gpurun_out/ncu_r2.log 2>&1; tail -3 gpurun_out/ncu_r2.log
