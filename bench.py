@@ -510,7 +510,9 @@ def run_ours(args):
         nominal_peak = sm.value * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
         cores = os.cpu_count() or 1
         cpu_v, cpu_dt = cpu_throughput(8, 1) if world == 1 else (None, None)
-        launches_dev = lr.value
+        launches_dev = lr.value                       # radial / random steps (hybrid K1 + K2, fused prologue)
+        launches_k3 = 3                               # cartesian steps: prepare_rowsepN, cols2<INV> over the noise-term planes, rowsepN
+        n_cart = len([i for i in range(args.steps) if MASK_KINDS[i % 3] == 'cartesian'])
         line = {
             'metric': 'admm_cnc_iterations_per_s', 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
@@ -538,8 +540,8 @@ def run_ours(args):
                     'sync_call': {'value': its_step * args.steps / (ms_e2e_sync * 1e-3), 'ms_per_step': ms_e2e_sync / args.steps,
                                   'api': 'pnpadmm_reconstruct_host_f32: one stream, host synchronises after every step '
                                          '(copies not overlapped; single-call latency)'}},
-            'gpu_launches': launches_dev * args.steps,
-            'launches_per_step': {'device': launches_dev, 'e2e': launches_dev + (1 if ps.value else 0),
+            'gpu_launches': launches_dev * (args.steps - n_cart) + launches_k3 * n_cart,
+            'launches_per_step': {'device': launches_dev, 'device_cartesian_step': launches_k3, 'e2e': launches_dev + (1 if ps.value else 0),
                                   'source': 'pnpadmm_plan_info (the library reports the launches of pnpadmm_reconstruct_f32 for this plan)',
                                   'kernels': f'prepare_shared x1, cluster256 x1 ({pc.value} planes, {ch.value} chunk(s); acquisition, zero-fill and data term fused '
                                              f'into its prologue); K2 share of {ps.value} planes on the side stream: rows2<FWD_IMG>, cols2<FWD_ACQ>, cols2<INV>, '
@@ -554,6 +556,12 @@ def run_ours(args):
                          'flop_model': '10 N^2 log2(N^2) = 10485760 per image-iteration (nominal radix-2 count of 2 '
                                        'complex 2-D FFTs; executed flops are lower: pair-packing + radix-16)',
                          'launch_ms': k1_ms, 'resident_clusters': ncl.value,
+                         'workload': {
+                             'achieved': value / world * FLOP_PER_IMAGE_ITER / 1e12, 'frac': value / world * FLOP_PER_IMAGE_ITER / 1e12 / nominal_peak,
+                             'what': 'SURVEY 8d convention applied to the whole timed step (value x F / FP32 peak, per GPU): nominal flops of the '
+                                     "reference's algorithm per delivered image-iteration over the three-mask workload, prologue included. It exceeds the "
+                                     'K1 kernel figure because cartesian steps run on K3, which does not execute the column transforms at all, and the '
+                                     'hybrid schedule uses all 148 SMs; `frac` above stays the K1 kernel alone'},
                          'traffic_note': 'K1 is not HBM-bound: 22 MB of DRAM reads per launch (profiles/r1_k1_cluster256_ncu_summary.txt)',
                          'hybrid_iterate': {
                              'call_ms': hyb_ms,

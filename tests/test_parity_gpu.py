@@ -755,3 +755,62 @@ def test_rowsep_kernel_large_sizes(pk, N, prox):
     # a non-separable mask is refused loudly at these sizes too
     bad = s.reconstruct(u8, data.make_mask('radial', N, seed=1), nz, *args, kernel='rowsep')[0]
     assert torch.isnan(bad).all()
+
+
+def test_plan_info_reports_the_schedule(pk):
+    """pnpadmm_plan_info (what bench.py derives gpu_launches from): planes per kernel add up, the fused reconstruct launches far
+    fewer kernels than acquire + solve, a batch that fits the resident clusters is not split."""
+    import ctypes
+    from pnp_admm_cnc_mri_b200 import _abi
+    lib = _abi.load()
+    sm, ncl = ctypes.c_int(), ctypes.c_int()
+    _abi.check(lib.pnpadmm_device_info(sm, ncl, None, None))
+    v = [ctypes.c_int() for _ in range(6)]
+    _abi.check(lib.pnpadmm_plan_info(64, 256, 0, 50, _abi.KERNEL_AUTO, *v))
+    p1, p2, chunks, la, ls, lr = (x.value for x in v)
+    assert p1 + p2 == 32 and p1 >= ncl.value and chunks >= 1 and la == 2
+    assert ls == 6 + (1 if p1 else 0) + ((1 + 100) if p2 else 0)
+    assert lr == 1 + (1 if p1 else 0) + ((7 + 100) if p2 else 0) and lr < la + ls
+    _abi.check(lib.pnpadmm_plan_info(2 * ncl.value, 256, 0, 50, _abi.KERNEL_AUTO, *v))
+    assert v[0].value == ncl.value and v[1].value == 0 and v[5].value == 2          # one preparation launch + one cluster kernel
+    _abi.check(lib.pnpadmm_plan_info(8, 1024, 0, 10, _abi.KERNEL_AUTO, *v))
+    assert v[0].value == 0 and v[1].value == 4 and v[5].value == v[3].value + v[4].value
+    assert lib.pnpadmm_plan_info(8, 100, 0, 10, _abi.KERNEL_AUTO, *v) == _abi.ERR_BAD_SIZE
+
+
+@pytest.mark.gpu
+def test_experiment_switches_keep_parity(tmp_path):
+    """The A/B switches of the kernels (read once per process, hence the subprocesses) select other code for the same
+    arithmetic: the blocked-tile / bulk-copy transposes of K1, the first row-separable kernel, the K2 share on two streams,
+    plain launches instead of programmatic dependent launch, acquisition + solve instead of the fused prologue, the literal
+    planner constants.  Each must reproduce the default build's reconstructions within the gate (bit for bit where the
+    arithmetic is literally the same code)."""
+    import subprocess
+    import sys
+    script = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "import pnp_admm_cnc_mri_b200 as pk\n"
+        "from pnp_admm_cnc_mri_b200 import data\n"
+        "out = []\n"
+        "nz = data.make_noise(256, seed=4)\n"
+        "for kind, B in (('random', 37), ('cartesian', 5)):\n"
+        "    imgs = np.concatenate([data.phantoms(5, 256, seed0=7)] * 8)[:B]\n"
+        "    x = pk.admm_solve(imgs, data.make_mask(kind, 256, seed=2), nz, prox='cnc', alpha=0.45, iter_num=12, lambda1=0.5, reo=0.05, b=64)\n"
+        "    out.append(x.ravel())\n"
+        "np.save(sys.argv[1], np.concatenate(out))\n")
+    variants = [({}, None), ({'PNPADMM_K1_BULK': '1'}, 1e-4), ({'PNPADMM_K3_K1CODE': '1'}, 1e-4), ({'PNPADMM_K2_SPLIT': '1'}, 0.0),
+                ({'PNPADMM_NO_PDL': '1'}, 0.0), ({'PNPADMM_NO_FUSED_PROLOGUE': '1', 'PNPADMM_NO_ROWSEP': '1'}, 1e-4),
+                ({'PNPADMM_NO_CALIBRATE': '1'}, 1e-4)]
+    base = None
+    for k, (env_add, tol) in enumerate(variants):
+        f = str(tmp_path / f'v{k}.npy')
+        subprocess.run([sys.executable, '-c', script, f], check=True, env=dict(os.environ, **env_add), timeout=300)
+        got = np.load(f)
+        assert np.isfinite(got).all(), env_add
+        if base is None:
+            base = got
+        elif tol == 0.0:
+            assert np.array_equal(got, base), env_add
+        else:
+            assert rel(got, base.astype(np.float64)) < tol, env_add

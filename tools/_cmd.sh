@@ -1,3 +1,4 @@
-timeout 1500 python -m pytest tests/test_parity_gpu.py -q -x -s -k "rowsep" 2>&1 | grep -E "rowsep|passed|failed|Error|error|FAILED" | tail -25
-PNPADMM_K3_K1CODE=1 timeout 600 python -m pytest tests/test_parity_gpu.py -q -x -k "rowsep_kernel_kat or rowsep_kernel_refuses" 2>&1 | tail -2
-bash tools/ncu_r2.sh > gpurun_out/ncu_r2.log 2>&1; tail -3 gpurun_out/ncu_r2.log
+timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/r2_pytest_final.log; cat gpurun_out/r2_pytest_final.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo bench rc=$?; tail -3 gpurun_out/r2_bench_final.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 | cut -c1-300

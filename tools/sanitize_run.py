@@ -48,6 +48,15 @@ if which in ('all', 'fused'):
     x = s.reconstruct(u8, m, nz, 'cnc', P['iter_num'], P['lambda1'], P['reo'], P['alpha'], P['b'], kernel='cluster')[0].cpu().numpy()
     check(x, np.float32(u8 / 255.), m, nz, f'fused reconstruct, cluster only, B={B}')
     del os.environ['PNPADMM_HYBRID_P2']
+if which in ('all', 'k3'):
+    # row-separable kernels: N = 256 (both implementations are exercised by PNPADMM_K3_K1CODE) and N = 512, odd batches, uint8 in
+    mc = data.make_mask('cartesian', N, seed=7)
+    imgs = data.phantoms(5, N, seed0=1)
+    check(pk.admm_solve(imgs, mc, nz, prox='cnc', **P), imgs, mc, nz, 'K3 rowsep N=256 B=5')
+    N3 = 512
+    mc3 = data.make_mask('cartesian', N3, seed=7); nz3 = data.make_noise(N3, seed=4)
+    im3 = data.phantoms(3, N3, seed0=2)
+    check(pk.admm_solve(im3, mc3, nz3, prox='cnc', **P), im3, mc3, nz3, 'K3 rowsepN N=512 B=3', 1)
 if which in ('all', 'k2'):
     N2 = 512
     m2 = data.make_mask('radial', N2, seed=1)
