@@ -624,7 +624,7 @@ int launch_cluster_t(k1::ClusterParams& cp, int max_clusters, cudaStream_t st) {
         cfg.numAttrs = 2;
     }
     if (const char* e = getenv("PNPADMM_K1_STAGGER")) cp.dbg = atoi(e) << 8;   // experiments: start delay of odd clusters (us)
-    if (CL == 16 && k1_bulk_enabled()) {
+    if (CL == 16 && k1_bulk_enabled() && !cp.fused) {   // the experiment kernel has no fused prologue
         CUDA_TRY(cudaLaunchKernelEx(&cfg, k1::cluster256_bk_kernel, (const k1::ClusterParams)cp));
         return PNPADMM_OK;
     }

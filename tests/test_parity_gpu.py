@@ -799,7 +799,7 @@ def test_experiment_switches_keep_parity(tmp_path):
         "    x = pk.admm_solve(imgs, data.make_mask(kind, 256, seed=2), nz, prox='cnc', alpha=0.45, iter_num=12, lambda1=0.5, reo=0.05, b=64)\n"
         "    out.append(x.ravel())\n"
         "np.save(sys.argv[1], np.concatenate(out))\n")
-    variants = [({}, None), ({'PNPADMM_K1_BULK': '1'}, 1e-4), ({'PNPADMM_K3_K1CODE': '1'}, 1e-4), ({'PNPADMM_K2_SPLIT': '1'}, 0.0),
+    variants = [({}, None), ({'PNPADMM_K1_BULK': '1', 'PNPADMM_NO_FUSED_PROLOGUE': '1'}, 1e-4), ({'PNPADMM_K1_BULK': '1'}, 0.0), ({'PNPADMM_K3_K1CODE': '1'}, 1e-4), ({'PNPADMM_K2_SPLIT': '1'}, 0.0),
                 ({'PNPADMM_NO_PDL': '1'}, 0.0), ({'PNPADMM_NO_FUSED_PROLOGUE': '1', 'PNPADMM_NO_ROWSEP': '1'}, 1e-4),
                 ({'PNPADMM_NO_CALIBRATE': '1'}, 1e-4)]
     base = None
