@@ -274,6 +274,22 @@ int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H
                                pnpadmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * a9  FFDNet denoiser forward on the same tensor-core kernels (reference models/network_ffdnet.py:31-73
+ * FFDNet.forward: replicate-pad to even size, PixelUnShuffle(2), concatenate the noise-level map, conv3x3 5->64 + ReLU,
+ * n_mid x [conv3x3 64->64 + ReLU], conv3x3 64->4, PixelShuffle(2), crop; called from denoising_step1 S3:64-66 with
+ * sigma = 15 / 255).  All convolutions run at half resolution; bf16 operands, fp32 accumulation, bias in every layer.
+ *   x      [B][H][W] f32 (one channel);  out [B][H][W] f32, 8-byte aligned
+ *   sigma  the noise level of the map (rounded to bf16 like the module's input)
+ *   w_head a w_mid-format layer whose input channels 5..63 are zero (channel c < 4: sub-pixel (c / 2, c % 2), channel 4: map);
+ *          only its first two 8-channel chunks are read (K = 16 per tap);  b_head [64] f32
+ *   w_mid, b_mid as for pnpadmm_dncnn_forward_bf16;  w_tail [kx][c_in / 8][ky][16][c_in % 8] bf16 with rows 4..15 zero, b_tail [4] f32
+ *   act0, act1: two device buffers of pnpadmm_dncnn_activation_bytes(B, ceil(H / 2), ceil(W / 2)) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+int pnpadmm_ffdnet_forward_bf16(const float* x, float* out, int B, int H, int W, float sigma, int n_mid, const void* w_head,
+                                const float* b_head, const void* w_mid, const float* b_mid, const void* w_tail,
+                                const float* b_tail, void* act0, void* act1, pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helper: runs `iters` dependent-FMA loops on every SM and returns the achieved
  * non-tensor FP32 FLOP/s in *flops (device-timed with CUDA events, synchronous).  Used by
  * bench.py as the measured denominator of the FP32 FFT roofline.

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_void_p
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, 'libpnpadmm.so')
@@ -28,7 +28,7 @@ SYMBOLS = [
     'pnpadmm_soft_f32', 'pnpadmm_soft_f64', 'pnpadmm_cnc_combine_f32', 'pnpadmm_cnc_combine_f64',
     'pnpadmm_dual_update_f32', 'pnpadmm_dual_update_f64', 'pnpadmm_measure_fp32_peak',
     'pnpadmm_metrics_scratch_bytes', 'pnpadmm_metrics_f32', 'pnpadmm_metrics_f64',
-    'pnpadmm_dncnn_activation_bytes', 'pnpadmm_conv64_bf16', 'pnpadmm_dncnn_forward_bf16',
+    'pnpadmm_dncnn_activation_bytes', 'pnpadmm_conv64_bf16', 'pnpadmm_dncnn_forward_bf16', 'pnpadmm_ffdnet_forward_bf16',
 ]
 
 _lib = None
@@ -109,6 +109,8 @@ def load() -> ctypes.CDLL:
     lib.pnpadmm_conv64_bf16.argtypes = [p, p, p, p, i, i, i, i, p]
     lib.pnpadmm_dncnn_forward_bf16.restype = i
     lib.pnpadmm_dncnn_forward_bf16.argtypes = [p, p, i, i, i, i, i, p, p, p, p, p, p, i, p, p, p]
+    lib.pnpadmm_ffdnet_forward_bf16.restype = i
+    lib.pnpadmm_ffdnet_forward_bf16.argtypes = [p, p, i, i, i, c_float, i, p, p, p, p, p, p, p, p, p]
     if lib.pnpadmm_abi_version() != ABI_VERSION:
         raise PnpAdmmError(f'ABI version mismatch: library {lib.pnpadmm_abi_version()} != binding {ABI_VERSION}; rebuild')
     _lib = lib

@@ -59,7 +59,6 @@ constexpr int kOffTmemPtr = kOffBar + 8 * kNumBars;
 constexpr int kOffBias = kOffTmemPtr + 16;
 constexpr int kOffOut = kOffBias + 64 * 4;     // staging tiles [8 chunks][128 pixels][16 B], two per epilogue group
 constexpr int kSmemBytes = kOffOut + 2 * kEpiGroups * kTileM * 128;
-constexpr int kRowTxBytes = 8 * kSlots * 16;   // bytes a staged input row receives (data + zero padding)
 
 // source of the zero padding (rows above / below the image, the pixel left / right of it)
 __device__ __align__(128) unsigned char g_zero[kSlots * 16];
@@ -74,6 +73,10 @@ struct ConvParams {
     const float* bias;          // [64] (tail: [1])
     int B, H, W, strip, xtiles, ystrips, items;
     int relu;
+    int kchunks;                // 8-channel chunks of the input that are real: 8 (64 channels) or 2 (a thin first layer, K = 16 per tap);
+                                // the input layout then is [B][H][kchunks][W][8] and a tap costs kchunks / 2 instructions
+    int cout;                   // tail (NOUT = 16): real output channels, 1 (DnCNN / FDnCNN) or 4 (FFDNet, pixel-shuffled on the way out)
+    int out_H, out_W;           // tail with cout = 4: size of the pixel-shuffled output image [B][out_H][out_W] (H = ceil(out_H / 2))
     // PNPADMM_TC_DEBUG, timing experiments only, compiled in with -DPNPADMM_TC_EXPERIMENTS (PNPADMM_NVCC_EXTRA of build.py);
     // every bit but 256 makes the results invalid: 1 = no input copies, 2 = no
     // output stores, 4 = no MMAs, 8 / 16 = no tcgen05.ld / no accumulator re-init in the epilogue, 64 = no MMA <-> epilogue
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
     for (int i = threadIdx.x; i < kWBytes / 16; i += kThreads)
         cp_async16(s0 + kOffW + 16 * i, reinterpret_cast<const unsigned char*>(p.w) + 16 * i, 16);
     cp_async_commit();
-    if (threadIdx.x < 64) bias_s[threadIdx.x] = (threadIdx.x < (NOUT == 64 ? 64 : 1)) ? p.bias[threadIdx.x] : 0.f;
+    if (threadIdx.x < 64) bias_s[threadIdx.x] = ((int)threadIdx.x < (NOUT == 64 ? 64 : p.cout)) ? p.bias[threadIdx.x] : 0.f;
     cp_async_wait<0>();
     k1::fence_proxy_async();                   // weights (generic-proxy writes) visible to the tensor core's async proxy
     if (warp == kMmaWarp) {
@@ -254,6 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                       "r"(br[8]), "r"(br[9]), "r"(br[10]), "r"(br[11]), "r"(br[12]), "r"(br[13]), "r"(br[14]), "r"(br[15])
                     : "memory");
             }
+        } else if (p.cout == 4) {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(bias_s[0])),
+                         "r"(__float_as_uint(bias_s[1])), "r"(__float_as_uint(bias_s[2])), "r"(__float_as_uint(bias_s[3]))
+                         : "memory");
         } else {
             asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(bias_s[0])) : "memory");
         }
@@ -279,7 +286,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         const int pw = warp - (kMmaWarp + 1), c0 = pw * (8 / kProdWarps);      // this warp's k-chunk planes
         if (lane == 0) {
             const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in);
-            const size_t plane = (size_t)p.W * 16, rowb = 8 * plane;
+            const size_t plane = (size_t)p.W * 16, rowb = (size_t)p.kchunks * plane;
+            const int c1 = c0 + 8 / kProdWarps < p.kchunks ? c0 + 8 / kProdWarps : p.kchunks;   // this warp's planes: [c0, c1)
+            const uint32_t row_tx = (uint32_t)p.kchunks * kSlots * 16;
             uint32_t e = 0;
             for (int item = blockIdx.x; item < ((dbg & 128) ? 0 : p.items); item += gridDim.x) {
                 const Item it = decode_item(p, item);
@@ -292,15 +301,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                     mbar_wait_t(bEmpty(st), ((e / kStages) & 1u) ^ 1u, w0, prof);
                     const uint32_t bar = bFull(st), dst0 = ring + st * kRowBytes;
                     if (dbg & 1) { if (pw == 0) mbar_arrive(bar); continue; }
-                    if (pw == 0) k1::mbar_arm_tx(bar, kRowTxBytes);       // the other producer warps' bytes may land first: fine
+                    if (pw == 0) k1::mbar_arm_tx(bar, row_tx);       // the other producer warps' bytes may land first: fine
                     const int y = it.y0 - 1 + r;
                     if (y < 0 || y >= p.H) {
-#pragma unroll
-                        for (int c = c0; c < c0 + 8 / kProdWarps; ++c) bulk_load(dst0 + c * kChunkBytes, g_zero, kSlots * 16, bar);
+#pragma unroll 4
+                        for (int c = c0; c < c1; ++c) bulk_load(dst0 + c * kChunkBytes, g_zero, kSlots * 16, bar);
                     } else {
                         const unsigned char* src = in_b + ((size_t)it.b * p.H + y) * rowb + (size_t)lo * 16;
-#pragma unroll
-                        for (int c = c0; c < c0 + 8 / kProdWarps; ++c) {
+#pragma unroll 4
+                        for (int c = c0; c < c1; ++c) {
                             const uint32_t d = dst0 + c * kChunkBytes;
                             if (nleft) bulk_load(d, g_zero, nleft * 16, bar);
                             bulk_load(d + nleft * 16, src + c * plane, nvalid * 16, bar);
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         const uint64_t desc_hi_a = ((uint64_t)(kChunkBytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
         const uint64_t b_desc0 = make_desc(s0 + kOffW, 3 * NOUT * 16, 128);
         const bool leader = elect_one();
+        const int ksteps = p.kchunks >> 1;             // K = 16 per instruction = two chunks
         // The tensor pipe queues only an instruction or two, so whatever the issuing thread does between the last MMA
         // of a row and the first of the next is a bubble.  The waits for row e + 1 (pre) and the commits of row e - 1
         // (post) are therefore placed INSIDE row e's MMA stream; nothing but loop control sits between rows.
@@ -346,13 +356,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                 const uint32_t idesc = make_idesc(n * NOUT);
                 const uint32_t d_tmem = tmem_base + b * NOUT;
                 const uint64_t b_dy = b_desc0 + (uint64_t)((dy * NOUT * 16) >> 4);
+                auto mma_ks = [&](int dx, int ks) {
+                    // start-address field += byte offset / 16 (never carries out of its 14 bits: smem < 256 KB)
+                    const uint64_t ad = a_desc0 + (uint64_t)((dx * 16 + ks * 2 * kChunkBytes) >> 4);
+                    const uint64_t bd = b_dy + (uint64_t)(((dx * 8 + ks * 2) * (3 * NOUT * 16)) >> 4);
+                    tc_mma_bf16(d_tmem, ad, bd, idesc, 1);
+                };
                 for (int dx = dx0; dx < dx1; ++dx) {
+                    if (ksteps == 4) {                       // 64 input channels: the hot path, fully unrolled
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        // start-address field += byte offset / 16 (never carries out of its 14 bits: smem < 256 KB)
-                        const uint64_t ad = a_desc0 + (uint64_t)((dx * 16 + ks * 2 * kChunkBytes) >> 4);
-                        const uint64_t bd = b_dy + (uint64_t)(((dx * 8 + ks * 2) * (3 * NOUT * 16)) >> 4);
-                        tc_mma_bf16(d_tmem, ad, bd, idesc, 1);
+                        for (int ks = 0; ks < 4; ++ks) mma_ks(dx, ks);
+                    } else {
+                        for (int ks = 0; ks < ksteps; ++ks) mma_ks(dx, ks);
                     }
                 }
                 dy += n;
@@ -462,6 +477,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                } else if (p.cout == 4) {
+                    // FFDNet tail: four output channels = the 2 x 2 sub-pixels of the full-resolution image
+                    // (F.pixel_shuffle: out[2 y + dy][2 x + dx] = conv[2 dy + dx][y][x]), cropped to out_H x out_W
+                    uint32_t v[4];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    init_block(taddr);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bTEmpty(b));
+                    if (x < p.W && !(dbg & 2)) {
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy) {
+                            const int oy = 2 * y + dy, ox = 2 * x;
+                            if (oy >= p.out_H) continue;
+                            float* o = p.out_f32 + ((size_t)it.b * p.out_H + oy) * p.out_W + ox;
+                            const float f0 = __uint_as_float(v[2 * dy]), f1 = __uint_as_float(v[2 * dy + 1]);
+                            if (!(p.out_W & 1)) *reinterpret_cast<float2*>(o) = make_float2(f0, f1);      // ox + 1 < out_W, 8-byte aligned
+                            else { o[0] = f0; if (ox + 1 < p.out_W) o[1] = f1; }
+                        }
+                    }
                 } else {
                     uint32_t v0;
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v0) : "r"(taddr));
@@ -559,6 +596,27 @@ __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict
 #pragma unroll
             for (int k = 0; k < 3; ++k) { r0[ci][k] = r1[ci][k]; r1[ci][k] = r2[ci][k]; }
     }
+}
+
+// FFDNet input (reference models/network_ffdnet.py:56-70: replicate-pad to even size, PixelUnShuffle(2), concatenate the
+// noise-level map): x [B][H][W] fp32 -> [B][H2][2 chunks][W2][8] bf16, chunk 0 = {x[2y][2x], x[2y][2x+1], x[2y+1][2x], x[2y+1][2x+1],
+// sigma, 0, 0, 0}, chunk 1 = 0 (the thin first layer reads K = 16 per tap: ConvParams::kchunks = 2).  Values are rounded to
+// bf16 like the input of a bf16 PyTorch module.
+__global__ void __launch_bounds__(256) ffdnet_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, float sigma, int B,
+                                                          int H, int W, int H2, int W2) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * H2 * W2) return;
+    const int xx = (int)(i % W2), yy = (int)((i / W2) % H2), b = (int)(i / ((size_t)W2 * H2));
+    const int y0 = 2 * yy, y1 = (2 * yy + 1 < H) ? 2 * yy + 1 : H - 1, x0 = 2 * xx, x1 = (2 * xx + 1 < W) ? 2 * xx + 1 : W - 1;
+    const float* img = x + (size_t)b * H * W;
+    uint4 o;
+    o.x = pack_bf16x2(__ldg(img + (size_t)y0 * W + x0), __ldg(img + (size_t)y0 * W + x1));
+    o.y = pack_bf16x2(__ldg(img + (size_t)y1 * W + x0), __ldg(img + (size_t)y1 * W + x1));
+    o.z = pack_bf16x2(sigma, 0.f);
+    o.w = 0u;
+    uint4* row = reinterpret_cast<uint4*>(out) + ((size_t)b * H2 + yy) * 2 * W2;
+    row[xx] = o;
+    row[W2 + xx] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 }  // namespace tc

@@ -1300,6 +1300,7 @@ int conv_geometry(tc::ConvParams& p, int B, int H, int W, const char* who) {
     if (B <= 0 || H <= 0 || W <= 0) return fail(PNPADMM_ERR_BAD_ARG, "%s: B=%d H=%d W=%d must be positive", who, B, H, W);
     if ((long long)B * H * W >= (1ll << 31)) return fail(PNPADMM_ERR_BAD_SIZE, "%s: B*H*W = %lld pixels exceeds 2^31", who, (long long)B * H * W);
     p.B = B; p.H = H; p.W = W;
+    p.kchunks = 8; p.cout = 1;
     p.strip = H < 64 ? H : 64;
     p.xtiles = (W + tc::kTileM - 1) / tc::kTileM;
     p.ystrips = (H + p.strip - 1) / p.strip;
@@ -1353,6 +1354,48 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
     p.w = w_tail; p.bias = b_tail; p.relu = 0;
     p.resid = residual ? x : nullptr;          // channel 0 of x
     p.resid_bstride = (long long)cin * H * W;
+    tc::conv64_tc_kernel<16><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    LAUNCH_CHECK("conv64_tc_kernel<16>");
+    return PNPADMM_OK;
+}
+
+// FFDNet forward (reference models/network_ffdnet.py:31-73, called from S3:64-66): pack (pad, pixel-unshuffle, noise-level map) ->
+// thin first layer (5 real input channels: K = 16 per tap) -> n_mid x conv64 -> four-channel tail with the pixel shuffle in its
+// epilogue.  All convolutions run on conv64_tc_kernel at half resolution.
+int ffdnet_forward_impl(const float* x, float* out, int B, int H, int W, float sigma, int n_mid, const void* w_head, const float* b_head,
+                        const void* w_mid, const float* b_mid, const void* w_tail, const float* b_tail, void* act0, void* act1,
+                        cudaStream_t st) {
+    if (!x || !out || !w_head || !b_head || !w_tail || !b_tail || !act0 || !act1 || (n_mid > 0 && (!w_mid || !b_mid)))
+        return fail(PNPADMM_ERR_BAD_ARG, "ffdnet_forward: NULL pointer");
+    if (n_mid < 0) return fail(PNPADMM_ERR_BAD_ARG, "ffdnet_forward: n_mid=%d", n_mid);
+    if ((((uintptr_t)act0) | ((uintptr_t)act1) | ((uintptr_t)w_head) | ((uintptr_t)w_mid) | ((uintptr_t)w_tail)) & 15)
+        return fail(PNPADMM_ERR_BAD_ARG, "ffdnet_forward: activation / weight pointers must be 16-byte aligned");
+    if (((uintptr_t)out) & 7) return fail(PNPADMM_ERR_BAD_ARG, "ffdnet_forward: out must be 8-byte aligned");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(PNPADMM_ERR_BAD_ARG, "ffdnet_forward: B=%d H=%d W=%d must be positive", B, H, W);
+    DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    tc::ConvParams p{};
+    rc = conv_geometry(p, B, H2, W2, "ffdnet_forward"); if (rc) return rc;
+    __nv_bfloat16* act[2] = {static_cast<__nv_bfloat16*>(act0), static_cast<__nv_bfloat16*>(act1)};
+    const size_t npx = (size_t)B * H2 * W2;
+    tc::ffdnet_pack_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(x, act[1], sigma, B, H, W, H2, W2);
+    LAUNCH_CHECK("ffdnet_pack_kernel");
+    const int grid = p.items < d->sm_count ? p.items : d->sm_count;
+    if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);     // timing experiments only
+    p.relu = 1;
+    p.in = act[1]; p.out = act[0]; p.w = w_head; p.bias = b_head; p.kchunks = 2;
+    tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    p.kchunks = 8;
+    for (int l = 0; l < n_mid; ++l) {
+        p.in = act[l & 1]; p.out = act[(l + 1) & 1];
+        p.w = static_cast<const unsigned char*>(w_mid) + (size_t)l * tc::kWBytesMax;
+        p.bias = b_mid + 64 * l;
+        tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    }
+    LAUNCH_CHECK("conv64_tc_kernel<64>");
+    p.in = act[n_mid & 1]; p.out = nullptr; p.out_f32 = out;
+    p.w = w_tail; p.bias = b_tail; p.relu = 0; p.resid = nullptr;
+    p.cout = 4; p.out_H = H; p.out_W = W;
     tc::conv64_tc_kernel<16><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
     LAUNCH_CHECK("conv64_tc_kernel<16>");
     return PNPADMM_OK;
@@ -1808,6 +1851,12 @@ int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H
 }
 
 // debug only (not part of include/pnpadmm.h): the planner's per-device constants
+int pnpadmm_ffdnet_forward_bf16(const float* x, float* out, int B, int H, int W, float sigma, int n_mid, const void* w_head,
+                                const float* b_head, const void* w_mid, const float* b_mid, const void* w_tail, const float* b_tail,
+                                void* act0, void* act1, pnpadmm_stream_t s) {
+    return ffdnet_forward_impl(x, out, B, H, W, sigma, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, act0, act1, ST(s));
+}
+
 int pnpadmm_debug_plan_constants(double* out4, int* calibrated) {
     DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
     out4[0] = d->tau1_us; out4[1] = d->k2_a_us; out4[2] = d->k2_b_us; out4[3] = d->k2_pro_us;

@@ -252,15 +252,17 @@ class Denoiser:
             if isinstance(sd, dict) and '0' in sd and isinstance(sd['0'], dict):
                 ircnn_weights, weights = sd, None
         net = model if model is not None else build_model(model_name, seed, weights)
-        # DnCNN / FDnCNN in bf16 on a GPU run on the hand-written tensor-core kernels (csrc/dncnn_tc.cuh) unless
-        # fused=False asks for the stock PyTorch module (the A/B baseline); other architectures stay in PyTorch.
-        can_fuse = self.arch in ('dncnn', 'fdncnn') and dtype == torch.bfloat16 and self.device.type == 'cuda'
+        # DnCNN / FDnCNN / FFDNet (all 64-channel conv3x3 chains) in bf16 on a GPU run on the hand-written tensor-core kernels
+        # (csrc/dncnn_tc.cuh) unless fused=False asks for the stock PyTorch module (the A/B baseline); IRCNN (dilated) and
+        # DRUNet stay in PyTorch.
+        can_fuse = self.arch in ('dncnn', 'fdncnn', 'ffdnet') and dtype == torch.bfloat16 and self.device.type == 'cuda'
         if fused and not can_fuse:
-            raise ValueError('fused=True needs a DnCNN / FDnCNN in bf16 on a CUDA device')
+            raise ValueError('fused=True needs a DnCNN / FDnCNN / FFDNet in bf16 on a CUDA device')
         self.fused = None
         if can_fuse and fused is not False:
-            from .dncnn_fused import FusedDnCNN
-            self.fused = FusedDnCNN(net, residual=(self.arch == 'dncnn'), device=self.device)
+            from .dncnn_fused import FusedDnCNN, FusedFFDNet
+            self.fused = (FusedFFDNet(net, device=self.device) if self.arch == 'ffdnet'
+                          else FusedDnCNN(net, residual=(self.arch == 'dncnn'), device=self.device))
         self.net = net.to(self.device, dtype).to(memory_format=torch.channels_last)
         self.sigmas = None
         self.noise_map = None
@@ -294,6 +296,8 @@ class Denoiser:
             xin = torch.cat((x, nm), 1)
             return self.fused(xin) if self.fused is not None else self._run(xin)                    # S3:26-35
         if self.arch == 'ffdnet':
+            if self.fused is not None:
+                return self.fused(x, 15 / 255.)                                                     # S3:64-66
             return self._run(x, self.ffdnet_sigma.to(self.dtype))                                   # S3:64-66
         mode = i % 8 if self.x8 else 0
         if mode:

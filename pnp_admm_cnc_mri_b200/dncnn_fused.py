@@ -1,4 +1,5 @@
-"""DnCNN / FDnCNN forward through the tensor-core kernels of the C ABI (``pnpadmm_dncnn_forward_bf16``).
+"""DnCNN / FDnCNN / FFDNet forward through the tensor-core kernels of the C ABI (``pnpadmm_dncnn_forward_bf16``,
+``pnpadmm_ffdnet_forward_bf16``).
 
 The reference runs its denoisers as stock ``torch.nn`` modules (models/network_dncnn.py:36-67, 120-141, called
 from S6:353-359 / S3:20-35).  On B200 the 64->64 layers are hand-written tcgen05 implicit GEMMs
@@ -110,6 +111,80 @@ class FusedDnCNN:
                 x.data_ptr(), out.data_ptr(), B, self.cin, H, W, self.n_mid, w['w_head'].data_ptr(), w['b_head'].data_ptr(),
                 w['w_mid'].data_ptr() if self.n_mid else None, w['b_mid'].data_ptr() if self.n_mid else None,
                 w['w_tail'].data_ptr(), w['b_tail'].data_ptr(), int(self.residual), a0.data_ptr(), a1.data_ptr(),
+                torch.cuda.current_stream().cuda_stream))
+        return out
+
+
+def pack_ffdnet(net: nn.Module, device) -> Tuple[dict, int]:
+    """Weights of an FFDNet (models/network_ffdnet.py:31-54: conv 5->64, (nb - 2) x conv 64->64, conv 64->4, all with bias)
+    in the kernels' layouts.  The first layer becomes a 64->64 image whose input channels 5..63 are zero."""
+    convs = [m for m in net.model if isinstance(m, nn.Conv2d)]
+    for k, c in enumerate(convs):
+        if c.kernel_size != (3, 3) or c.padding != (1, 1) or c.dilation != (1, 1) or c.stride != (1, 1) or c.bias is None:
+            raise ValueError(f'layer {k}: only conv3x3, stride 1, padding 1, dilation 1, with bias is supported')
+    head, mids, tail = convs[0], convs[1:-1], convs[-1]
+    if (head.in_channels, head.out_channels, tail.in_channels, tail.out_channels) != (5, 64, 64, 4) or getattr(net, 'sf', 2) != 2:
+        raise ValueError('expected the gray FFDNet: 4 sub-pixels + noise map -> 64 -> ... -> 4 sub-pixels, scale factor 2')
+    for c in mids:
+        if c.in_channels != 64 or c.out_channels != 64:
+            raise ValueError('middle layers must be 64 -> 64')
+    dev = torch.device(device)
+    bf = lambda t: t.detach().to(dev, torch.float32).to(torch.bfloat16)      # noqa: E731
+    w_head = torch.zeros((64, 64, 3, 3), dtype=torch.bfloat16, device=dev)
+    w_head[:, :5] = bf(head.weight)
+    packed = {
+        'w_head': pack_conv64(w_head),
+        'b_head': bf(head.bias).float().contiguous(),
+        'w_mid': (torch.stack([pack_conv64(bf(c.weight)) for c in mids]).contiguous() if mids
+                  else torch.zeros(0, dtype=torch.bfloat16, device=dev)),
+        'b_mid': (torch.stack([bf(c.bias).float() for c in mids]).contiguous() if mids
+                  else torch.zeros(0, dtype=torch.float32, device=dev)),
+        'w_tail': pack_conv64(bf(tail.weight), 16),
+        'b_tail': bf(tail.bias).float().contiguous(),
+    }
+    return packed, len(mids)
+
+
+class FusedFFDNet:
+    """``y = FFDNet(x, sigma)`` (reference models/network_ffdnet.py:56-73) on the tensor-core kernels: x (B, 1, H, W) float32
+    CUDA -> (B, 1, H, W) float32; ``sigma`` is the scalar level of the noise map (S3:64: 15 / 255).  Buffer ownership and
+    stream ordering as for :class:`FusedDnCNN`."""
+
+    def __init__(self, net: nn.Module, device='cuda'):
+        if not torch.cuda.is_available():
+            raise _abi.PnpAdmmError('no CUDA device visible: the tensor-core denoiser has no CPU path')
+        self.lib = _abi.load()
+        self.device = torch.device(device)
+        if self.device.type == 'cuda' and self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.w, self.n_mid = pack_ffdnet(net, self.device)
+        self._act = None
+        self._act_key = None
+
+    def _buffers(self, B, H2, W2):
+        key = (B, H2, W2)
+        if self._act_key != key:
+            n = self.lib.pnpadmm_dncnn_activation_bytes(B, H2, W2)
+            self._act = (torch.empty(n, dtype=torch.uint8, device=self.device), torch.empty(n, dtype=torch.uint8, device=self.device))
+            self._act_key = key
+        return self._act
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor, sigma: float) -> torch.Tensor:
+        if x.ndim != 4 or x.shape[1] != 1 or not x.is_cuda:
+            raise ValueError(f'expected a CUDA tensor of shape (B, 1, H, W), got {tuple(x.shape)} on {x.device}')
+        if x.device != self.w['w_head'].device:
+            raise ValueError(f'input on {x.device} but the packed weights live on {self.w["w_head"].device}')
+        x = x.float().contiguous()
+        B, _, H, W = (int(v) for v in x.shape)
+        w = self.w
+        with torch.cuda.device(x.device):
+            a0, a1 = self._buffers(B, (H + 1) // 2, (W + 1) // 2)
+            out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+            _abi.check(self.lib.pnpadmm_ffdnet_forward_bf16(
+                x.data_ptr(), out.data_ptr(), B, H, W, float(sigma), self.n_mid, w['w_head'].data_ptr(), w['b_head'].data_ptr(),
+                w['w_mid'].data_ptr() if self.n_mid else None, w['b_mid'].data_ptr() if self.n_mid else None,
+                w['w_tail'].data_ptr(), w['b_tail'].data_ptr(), a0.data_ptr(), a1.data_ptr(),
                 torch.cuda.current_stream().cuda_stream))
         return out
 

@@ -209,3 +209,77 @@ def test_denoiser_dispatch_uses_fused_gpu():
     d_ref = denoisers.build_denoiser('dncnn_25', seed=1, fused=False)
     y_ref = d_ref(x, 0)
     assert _rel(y, y_ref) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------- FFDNet on the same kernels
+def test_pack_ffdnet_layer_split():
+    """CPU: the first layer of an FFDNet becomes a 64 -> 64 image with input channels 5..63 zero; the tail keeps 4 outputs."""
+    net = denoisers.build_model('ffdnet_gray', seed=2)
+    packed, n_mid = df.pack_ffdnet(net, 'cpu')
+    assert n_mid == 13
+    convs = [m for m in net.model if isinstance(m, torch.nn.Conv2d)]
+    wh = packed['w_head'].float()                      # [kx][c_in // 8][ky][c_out][c_in % 8]
+    assert wh.shape == (3, 8, 3, 64, 8)
+    assert float(wh[:, 1:].abs().max()) == 0.0 and float(wh[:, 0, :, :, 5:].abs().max()) == 0.0
+    want = convs[0].weight.detach().to(torch.bfloat16).float()          # [64][5][3][3]
+    assert torch.equal(wh[:, 0, :, :, :5].permute(2, 3, 1, 0), want)   # -> [c_out][c_in][ky][kx]
+    wt = packed['w_tail'].float()
+    assert wt.shape == (3, 8, 3, 16, 8) and float(wt[:, :, :, 4:].abs().max()) == 0.0
+    assert packed['b_tail'].shape == (4,)
+
+
+def _ffdnet_with_bf16_rounding_points(net, x, sigma):
+    """fp32 convolutions with the roundings the kernels apply (input, map, weights, biases, activations after each ReLU)."""
+    h, w = x.shape[-2:]
+    xp = F.pad(x, (0, (-w) % 2, 0, (-h) % 2), mode='replicate')
+    t = F.pixel_unshuffle(xp.to(torch.bfloat16).float(), 2)
+    m = torch.full_like(t[:, :1], float(torch.tensor(sigma).to(torch.bfloat16)))
+    t = torch.cat((t, m), 1)
+    convs = [c for c in net.model if isinstance(c, torch.nn.Conv2d)]
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        for k, c in enumerate(convs):
+            t = F.conv2d(t, c.weight.to(torch.bfloat16).float(), c.bias.to(torch.bfloat16).float(), padding=1)
+            if k < len(convs) - 1:
+                t = F.relu(t).to(torch.bfloat16).float()
+    return F.pixel_shuffle(t, 2)[..., :h, :w]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(2, 256, 256), (3, 70, 200), (1, 65, 131), (1, 16, 16)])
+def test_ffdnet_forward_gpu(shape):
+    """FFDNet through pnpadmm_ffdnet_forward_bf16 (pack -> thin first layer -> 13 x conv64 -> shuffled four-channel tail)
+    against the fp32 module with the same bf16-representable weights, PyTorch's own bf16 forward as the yardstick, and the
+    same-rounding-points evaluation (odd sizes exercise the replicate padding and the crop)."""
+    B, H, W = shape
+    net = denoisers.build_model('ffdnet_gray', seed=4)
+    with torch.no_grad():
+        for c in net.model:
+            if isinstance(c, torch.nn.Conv2d):
+                c.weight.mul_(1.5)
+                c.weight.copy_(c.weight.to(torch.bfloat16).float())
+                c.bias.copy_(c.bias.to(torch.bfloat16).float())
+    net = net.cuda()
+    x = torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(H + W)).cuda().to(torch.bfloat16).float()
+    sigma = 15 / 255.
+    got = df.FusedFFDNet(net)(x, sigma)
+    sig = torch.full((1, 1, 1, 1), sigma, device='cuda')
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        want = net(x, sig.to(torch.bfloat16).float())
+        ref16 = net.to(torch.bfloat16)(x.to(torch.bfloat16), sig.to(torch.bfloat16)).float()
+        net = net.float()
+        same = _ffdnet_with_bf16_rounding_points(net, x, sigma)
+    assert got.shape == want.shape == (B, 1, H, W)
+    e_ours, e_torch, e_same = _rel(got, want), _rel(ref16, want), _rel(got, same)
+    print(f'FFDNet {shape}: ours vs fp32 {e_ours:.2e}, torch bf16 vs fp32 {e_torch:.2e}, ours vs same rounding points {e_same:.2e}')
+    assert e_ours < max(2.0 * e_torch, 2e-2), (e_ours, e_torch)
+    assert e_same < 5e-3, e_same
+
+
+@pytest.mark.gpu
+def test_denoiser_dispatch_ffdnet_fused_gpu():
+    d = denoisers.build_denoiser('ffdnet_gray', seed=1)
+    assert d.fused is not None
+    x = torch.rand(2, 1, 96, 64, device='cuda')
+    y = d(x, 0)
+    y_ref = denoisers.build_denoiser('ffdnet_gray', seed=1, fused=False)(x, 0)
+    assert y.shape == y_ref.shape and _rel(y, y_ref) < 2e-2

@@ -89,6 +89,24 @@ def main():
         t_l = timed(lambda: lib.pnpadmm_conv64_bf16(a.data_ptr(), out.data_ptr(), wp.data_ptr(), b.data_ptr(), B, H, W, 1, st))
         print(f'      one 64->64 layer: {t_l[0] * 1e3:.1f} us = {B * flops_mid / t_l[0] / 1e9:.0f} TFLOP/s, '
               f'{2 * a.numel() * 2 / t_l[0] / 1e6:.0f} GB/s of activations', flush=True)
+    # FFDNet-15 (half resolution, 13 x conv64 between a thin first layer and a four-channel pixel-shuffled tail)
+    fnet = denoisers.build_model('ffdnet_gray', seed=0).cuda()
+    ffused = df.FusedFFDNet(fnet)
+    fnet16 = denoisers.build_model('ffdnet_gray', seed=0).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    sig16 = torch.full((1, 1, 1, 1), 15 / 255., device='cuda', dtype=torch.bfloat16)
+    x = torch.rand(2, 1, 256, 256, device='cuda')
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        want = fnet(x, sig16.float())
+    print(f'FFDNet: ours vs fp32 {rel(ffused(x, 15 / 255.), want):.3e}, torch bf16 vs fp32 {rel(fnet16(x.to(torch.bfloat16), sig16).float(), want):.3e}',
+          flush=True)
+    for B in Bs:
+        x = torch.rand(B, 1, H, W, device='cuda')
+        x16 = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        t_ours = timed(lambda: ffused(x, 15 / 255.))
+        t_torch = timed(lambda: fnet16(x16, sig16))
+        fl = B * (H // 2) * (W // 2) * 2.0 * 9 * (13 * 64 * 64 + 5 * 64 + 64 * 4)
+        print(f'FFDNet B={B}: ours {t_ours[0]:.3f} ms (avg {t_ours[1]:.3f}) = {fl / t_ours[0] / 1e9:.0f} TFLOP/s | '
+              f'torch bf16 cuDNN {t_torch[0]:.3f} ms | speed-up {t_torch[0] / t_ours[0]:.2f}x', flush=True)
     return 0
 
 
