@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PNPADMM_ABI_VERSION 2
+#define PNPADMM_ABI_VERSION 3
 
 #define PNPADMM_OK                 0
 #define PNPADMM_ERR_BAD_ARG       -1   /* NULL pointer, B <= 0, iters < 0, unknown enum ...          */
@@ -272,6 +272,20 @@ int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H
                                const float* w_head, const float* b_head, const void* w_mid, const float* b_mid,
                                const void* w_tail, const float* b_tail, int residual, void* act0, void* act1,
                                pnpadmm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a9  IRCNN denoiser forward (reference models/network_dncnn.py:70-109 IRCNN: conv3x3 1->64, five DILATED conv3x3 64->64
+ * with dilation = padding = 2, 3, 4, 3, 2, conv3x3 64->1, ReLU between, forward = x - model(x); called from S3:52-62,
+ * S3:280-288 with one of 25 weight sets) on the same kernels: pnpadmm_dncnn_forward_bf16 with a dilation per middle layer
+ * (`dilation_mid`, n_mid host integers in 1..4; the first and last layers are undilated).  pnpadmm_conv64_dilated_bf16 is the
+ * one-layer entry of the parity tests.
+ * ------------------------------------------------------------------------------------- */
+int pnpadmm_conv64_dilated_bf16(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu,
+                                int dilation, pnpadmm_stream_t stream);
+int pnpadmm_dncnn_forward_dilated_bf16(const float* x, float* out, int B, int cin, int H, int W, int n_mid,
+                                       const int* dilation_mid, const float* w_head, const float* b_head, const void* w_mid,
+                                       const float* b_mid, const void* w_tail, const float* b_tail, int residual, void* act0,
+                                       void* act1, pnpadmm_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a9  FFDNet denoiser forward on the same tensor-core kernels (reference models/network_ffdnet.py:31-73

@@ -13,7 +13,7 @@ OK, ERR_BAD_ARG, ERR_BAD_SIZE, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1,
 PROX_L1, PROX_CNC = 0, 1
 KERNEL_AUTO, KERNEL_CLUSTER, KERNEL_STREAMING, KERNEL_ROWSEP = 0, 1, 2, 3
 OUT_F32, OUT_U8 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/pnpadmm.h declares (tests check the .so exports all of them)
 SYMBOLS = [
@@ -29,6 +29,7 @@ SYMBOLS = [
     'pnpadmm_dual_update_f32', 'pnpadmm_dual_update_f64', 'pnpadmm_measure_fp32_peak',
     'pnpadmm_metrics_scratch_bytes', 'pnpadmm_metrics_f32', 'pnpadmm_metrics_f64',
     'pnpadmm_dncnn_activation_bytes', 'pnpadmm_conv64_bf16', 'pnpadmm_dncnn_forward_bf16', 'pnpadmm_ffdnet_forward_bf16',
+    'pnpadmm_conv64_dilated_bf16', 'pnpadmm_dncnn_forward_dilated_bf16',
 ]
 
 _lib = None
@@ -109,6 +110,10 @@ def load() -> ctypes.CDLL:
     lib.pnpadmm_conv64_bf16.argtypes = [p, p, p, p, i, i, i, i, p]
     lib.pnpadmm_dncnn_forward_bf16.restype = i
     lib.pnpadmm_dncnn_forward_bf16.argtypes = [p, p, i, i, i, i, i, p, p, p, p, p, p, i, p, p, p]
+    lib.pnpadmm_conv64_dilated_bf16.restype = i
+    lib.pnpadmm_conv64_dilated_bf16.argtypes = [p, p, p, p, i, i, i, i, i, p]
+    lib.pnpadmm_dncnn_forward_dilated_bf16.restype = i
+    lib.pnpadmm_dncnn_forward_dilated_bf16.argtypes = [p, p, i, i, i, i, i, POINTER(c_int), p, p, p, p, p, p, i, p, p, p]
     lib.pnpadmm_ffdnet_forward_bf16.restype = i
     lib.pnpadmm_ffdnet_forward_bf16.argtypes = [p, p, i, i, i, c_float, i, p, p, p, p, p, p, p, p, p]
     if lib.pnpadmm_abi_version() != ABI_VERSION:

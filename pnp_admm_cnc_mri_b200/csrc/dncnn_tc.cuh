@@ -11,10 +11,11 @@
 // of 128 x 192 x 16 per input row, the three ky taps stacked along N (input-stationary schedule, see the kernel).
 // Activations are bf16 in CHUNK-PLANAR ROWS, [B][H][8 chunks][W][8 channels]: a row of the image is 8 planes of
 // W x 16 bytes.  Shared memory uses the NO-SWIZZLE K-major canonical layout (core matrix = 8 rows x 16 B = 128 B):
-//     A row buffer : [k-chunk 0..7][slot 0..130][8 c_in]   slot s <-> pixel x0 - 1 + s (1-pixel halo each side)
+//     A row buffer : [k-chunk 0..7][slot 0..128 + 2 dil)[8 c_in]   slot s <-> pixel x0 - dil + s (halo of dil = 1 pixel each side;
+//                    IRCNN's dilated layers: dil = 2, 3, 4, see ConvParams::dil)
 // so the tap shift kx is a 16-byte shift of the descriptor start address and the tap shift ky selects another row
 // buffer: the im2col matrix is never materialised, every input row is loaded ONCE per strip, and a k-chunk plane of a
-// row buffer is 2080 CONTIGUOUS bytes of global memory: one 1-D bulk copy (cp.async.bulk, TMA engine) per plane, no
+// row buffer is 2080 (dil = 1) CONTIGUOUS bytes of global memory: one 1-D bulk copy (cp.async.bulk, TMA engine) per plane, no
 // tensor map and no LSU instruction on the load path; zero padding comes from a zero buffer.  The row buffers form a
 // 5-deep ring; the 72 KB of weights of the layer
 //     B            : [kx 0..2][k-chunk 0..7][ky 0..2][c_out 0..N)[8 c_in]   (the three ky taps stacked along N)
@@ -40,10 +41,14 @@ namespace pnp {
 namespace tc {
 
 constexpr int kTileM = 128;                    // output pixels per tile
-constexpr int kSlots = kTileM + 2;             // staged input pixels per row
-constexpr int kPPad = 131;                     // slot pitch of a k-chunk plane (130 used; odd, so the 8 chunk planes start in 8 different bank groups)
+#ifndef PNP_TC_MAXDIL
+#define PNP_TC_MAXDIL 4                        // A/B builds: -DPNP_TC_MAXDIL=1 gives the undilated kernel's row-buffer pitch (131 slots)
+#endif
+constexpr int kMaxDil = PNP_TC_MAXDIL;         // largest dilation (IRCNN: 1, 2, 3, 4, 3, 2, 1)
+constexpr int kSlotsMax = kTileM + 2 * kMaxDil;    // staged input pixels per row: 128 + a halo of `dil` pixels on each side
+constexpr int kPPad = kSlotsMax + 1;           // slot pitch of a k-chunk plane (137; odd, so the 8 chunk planes start in 8 different bank groups)
 constexpr int kChunkBytes = kPPad * 16;        // = LBO of the A descriptor
-constexpr int kRowBytes = 8 * kChunkBytes;     // 16768
+constexpr int kRowBytes = 8 * kChunkBytes;     // 17536
 constexpr int kStages = 5;
 constexpr int kEpiGroups = 2;                  // epilogue groups of four warps; group g takes the output rows t = g (mod kEpiGroups)
 constexpr int kMmaWarp = 4 * kEpiGroups;       // warps [0, 4 g): epilogue, then the MMA warp, then the producer warps
@@ -61,7 +66,7 @@ constexpr int kOffOut = kOffBias + 64 * 4;     // staging tiles [8 chunks][128 p
 constexpr int kSmemBytes = kOffOut + 2 * kEpiGroups * kTileM * 128;
 
 // source of the zero padding (rows above / below the image, the pixel left / right of it)
-__device__ __align__(128) unsigned char g_zero[kSlots * 16];
+__device__ __align__(128) unsigned char g_zero[kSlotsMax * 16];
 
 struct ConvParams {
     const __nv_bfloat16* in;    // [B][H][8 chunks][W][8 channels]   (chunk-planar rows, see the file header)
@@ -71,8 +76,11 @@ struct ConvParams {
     long long resid_bstride;
     const void* w;              // packed weights of this layer (see file header)
     const float* bias;          // [64] (tail: [1])
-    int B, H, W, strip, xtiles, ystrips, items;
+    int B, H, W, xtiles, ystrips, items;
     int relu;
+    int dil;                    // dilation (= padding) of the 3x3 taps, 1..kMaxDil.  The rows y = py (mod dil) form `dil` independent
+                                // row-interleaved sub-images in which the taps are ADJACENT rows, so a work item is a strip of one
+                                // sub-image and the schedule is the undilated one; along x the tap shift is dil slots of the row buffer
     int kchunks;                // 8-channel chunks of the input that are real: 8 (64 channels) or 2 (a thin first layer, K = 16 per tap);
                                 // the input layout then is [B][H][kchunks][W][8] and a tap costs kchunks / 2 instructions
     int cout;                   // tail (NOUT = 16): real output channels, 1 (DnCNN / FDnCNN) or 4 (FFDNet, pixel-shuffled on the way out)
@@ -173,17 +181,21 @@ PNP_D uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// work item -> (image, x tile, y strip)
-struct Item { int b, x0, y0, rows; };
+// work item -> (image, x tile, row sub-image py, strip of its rows): output rows y = py + dil (j0 + j), j < rows.
+// A sub-image's rows are cut into `ystrips` nearly equal strips (never empty: the host checks H >= dil * ystrips).
+struct Item { int b, x0, py, j0, rows; };
 PNP_D Item decode_item(const ConvParams& p, int item) {
     Item it;
     const int xt = item % p.xtiles;
-    const int r = item / p.xtiles;
+    int r = item / p.xtiles;
     const int ys = r % p.ystrips;
-    it.b = r / p.ystrips;
+    r /= p.ystrips;
+    it.py = r % p.dil;
+    it.b = r / p.dil;
     it.x0 = xt * kTileM;
-    it.y0 = ys * p.strip;
-    it.rows = (p.H - it.y0 < p.strip) ? p.H - it.y0 : p.strip;
+    const int sub = (p.H - it.py + p.dil - 1) / p.dil;           // rows of this sub-image
+    it.j0 = (int)((long long)ys * sub / p.ystrips);
+    it.rows = (int)((long long)(ys + 1) * sub / p.ystrips) - it.j0;
     return it;
 }
 
@@ -288,24 +300,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
             const unsigned char* in_b = reinterpret_cast<const unsigned char*>(p.in);
             const size_t plane = (size_t)p.W * 16, rowb = (size_t)p.kchunks * plane;
             const int c1 = c0 + 8 / kProdWarps < p.kchunks ? c0 + 8 / kProdWarps : p.kchunks;   // this warp's planes: [c0, c1)
-            const uint32_t row_tx = (uint32_t)p.kchunks * kSlots * 16;
+            const uint32_t slots = kTileM + 2 * p.dil;
+            const uint32_t row_tx = (uint32_t)p.kchunks * slots * 16;
             uint32_t e = 0;
             for (int item = blockIdx.x; item < ((dbg & 128) ? 0 : p.items); item += gridDim.x) {
                 const Item it = decode_item(p, item);
-                const int xs = it.x0 - 1;
+                const int xs = it.x0 - p.dil;
                 const int lo = xs < 0 ? 0 : xs;
-                const int hi = it.x0 + kTileM + 1 < p.W ? it.x0 + kTileM + 1 : p.W;
-                const uint32_t nleft = lo - xs, nvalid = hi - lo, nright = kSlots - nleft - nvalid;
+                const int hi = it.x0 + kTileM + p.dil < p.W ? it.x0 + kTileM + p.dil : p.W;
+                const uint32_t nleft = lo - xs, nvalid = hi - lo, nright = slots - nleft - nvalid;
                 for (int r = 0; r < it.rows + 2; ++r, ++e) {
                     const uint32_t st = e % kStages;
                     mbar_wait_t(bEmpty(st), ((e / kStages) & 1u) ^ 1u, w0, prof);
                     const uint32_t bar = bFull(st), dst0 = ring + st * kRowBytes;
                     if (dbg & 1) { if (pw == 0) mbar_arrive(bar); continue; }
                     if (pw == 0) k1::mbar_arm_tx(bar, row_tx);       // the other producer warps' bytes may land first: fine
-                    const int y = it.y0 - 1 + r;
+                    const int y = it.py + p.dil * (it.j0 - 1 + r);
                     if (y < 0 || y >= p.H) {
 #pragma unroll 4
-                        for (int c = c0; c < c1; ++c) bulk_load(dst0 + c * kChunkBytes, g_zero, kSlots * 16, bar);
+                        for (int c = c0; c < c1; ++c) bulk_load(dst0 + c * kChunkBytes, g_zero, slots * 16, bar);
                     } else {
                         const unsigned char* src = in_b + ((size_t)it.b * p.H + y) * rowb + (size_t)lo * 16;
 #pragma unroll 4
@@ -332,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
         const uint64_t b_desc0 = make_desc(s0 + kOffW, 3 * NOUT * 16, 128);
         const bool leader = elect_one();
         const int ksteps = p.kchunks >> 1;             // K = 16 per instruction = two chunks
+        const int dil16 = p.dil * 16;                  // tap shift along x in bytes of the row buffer
         // The tensor pipe queues only an instruction or two, so whatever the issuing thread does between the last MMA
         // of a row and the first of the next is a bubble.  The waits for row e + 1 (pre) and the commits of row e - 1
         // (post) are therefore placed INSIDE row e's MMA stream; nothing but loop control sits between rows.
@@ -358,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                 const uint64_t b_dy = b_desc0 + (uint64_t)((dy * NOUT * 16) >> 4);
                 auto mma_ks = [&](int dx, int ks) {
                     // start-address field += byte offset / 16 (never carries out of its 14 bits: smem < 256 KB)
-                    const uint64_t ad = a_desc0 + (uint64_t)((dx * 16 + ks * 2 * kChunkBytes) >> 4);
+                    const uint64_t ad = a_desc0 + (uint64_t)((dx * dil16 + ks * 2 * kChunkBytes) >> 4);
                     const uint64_t bd = b_dy + (uint64_t)(((dx * 8 + ks * 2) * (3 * NOUT * 16)) >> 4);
                     tc_mma_bf16(d_tmem, ad, bd, idesc, 1);
                 };
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
                 mbar_wait_t(bTFull(b), (t / kBlocks) & 1u, w3, prof);
                 tc_fence_after();
                 const uint32_t taddr = lane_addr + b * NOUT;
-                const int x = it.x0 + quad * 32 + lane, y = it.y0 + j;
+                const int x = it.x0 + quad * 32 + lane, y = it.py + p.dil * (it.j0 + j);
                 if (NOUT == 64) {
                     uint32_t v[64];
                     if (!(dbg & 8)) {

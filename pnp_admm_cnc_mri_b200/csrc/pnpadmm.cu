@@ -1296,24 +1296,26 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, fl
 // ------------------------------------------------------------------------------------------
 // K5: DnCNN / FDnCNN forward on the tensor cores (dncnn_tc.cuh)
 // ------------------------------------------------------------------------------------------
-int conv_geometry(tc::ConvParams& p, int B, int H, int W, const char* who) {
+int conv_geometry(tc::ConvParams& p, int B, int H, int W, const char* who, int dil = 1) {
     if (B <= 0 || H <= 0 || W <= 0) return fail(PNPADMM_ERR_BAD_ARG, "%s: B=%d H=%d W=%d must be positive", who, B, H, W);
     if ((long long)B * H * W >= (1ll << 31)) return fail(PNPADMM_ERR_BAD_SIZE, "%s: B*H*W = %lld pixels exceeds 2^31", who, (long long)B * H * W);
+    if (dil < 1 || dil > tc::kMaxDil) return fail(PNPADMM_ERR_UNSUPPORTED, "%s: dilation %d (1..%d)", who, dil, tc::kMaxDil);
     p.B = B; p.H = H; p.W = W;
-    p.kchunks = 8; p.cout = 1;
-    p.strip = H < 64 ? H : 64;
+    p.kchunks = 8; p.cout = 1; p.dil = dil;
     p.xtiles = (W + tc::kTileM - 1) / tc::kTileM;
-    p.ystrips = (H + p.strip - 1) / p.strip;
-    p.items = B * p.xtiles * p.ystrips;
+    const int sub = (H + dil - 1) / dil;                      // rows of the largest row sub-image (ConvParams::dil)
+    p.ystrips = (sub + 63) / 64;                              // strips of <= 64 rows, nearly equal (tc::decode_item)
+    if (H < dil * p.ystrips) return fail(PNPADMM_ERR_BAD_SIZE, "%s: H=%d is smaller than the dilation %d", who, H, dil);
+    p.items = B * p.xtiles * p.ystrips * dil;
     return PNPADMM_OK;
 }
 
-int conv64_impl(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu, cudaStream_t st) {
+int conv64_impl(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu, cudaStream_t st, int dil = 1) {
     if (!in || !out || !w || !bias) return fail(PNPADMM_ERR_BAD_ARG, "conv64: NULL pointer");
     if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)w)) & 15) return fail(PNPADMM_ERR_BAD_ARG, "conv64: pointers must be 16-byte aligned");
     DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
     tc::ConvParams p{};
-    rc = conv_geometry(p, B, H, W, "conv64"); if (rc) return rc;
+    rc = conv_geometry(p, B, H, W, "conv64", dil); if (rc) return rc;
     p.in = static_cast<const __nv_bfloat16*>(in); p.out = static_cast<__nv_bfloat16*>(out);
     p.w = w; p.bias = bias; p.relu = relu;
     if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);
@@ -1325,7 +1327,7 @@ int conv64_impl(const void* in, void* out, const void* w, const float* bias, int
 
 int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W, int n_mid, const float* w_head,
                        const float* b_head, const void* w_mid, const float* b_mid, const void* w_tail, const float* b_tail,
-                       int residual, void* act0, void* act1, cudaStream_t st) {
+                       int residual, void* act0, void* act1, cudaStream_t st, const int* dil_mid = nullptr) {
     if (!x || !out || !w_head || !b_head || !w_tail || !b_tail || !act0 || !act1 || (n_mid > 0 && (!w_mid || !b_mid)))
         return fail(PNPADMM_ERR_BAD_ARG, "dncnn_forward: NULL pointer");
     if (cin != 1 && cin != 2) return fail(PNPADMM_ERR_UNSUPPORTED, "dncnn_forward: %d input channels (1 = DnCNN, 2 = FDnCNN)", cin);
@@ -1344,12 +1346,17 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
     p.relu = 1;
     if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);     // timing experiments only
     for (int l = 0; l < n_mid; ++l) {
+        if (dil_mid) {                         // IRCNN: per-layer dilation (work items are strips of row sub-images)
+            rc = conv_geometry(p, B, H, W, "dncnn_forward", dil_mid[l]); if (rc) return rc;
+        }
+        const int g = p.items < d->sm_count ? p.items : d->sm_count;
         p.in = act[l & 1]; p.out = act[(l + 1) & 1];
         p.w = static_cast<const unsigned char*>(w_mid) + (size_t)l * tc::kWBytesMax;
         p.bias = b_mid + 64 * l;
-        tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+        tc::conv64_tc_kernel<64><<<g, tc::kThreads, tc::kSmemBytes, st>>>(p);
     }
     LAUNCH_CHECK("conv64_tc_kernel<64>");
+    if (dil_mid) { rc = conv_geometry(p, B, H, W, "dncnn_forward", 1); if (rc) return rc; }
     p.in = act[n_mid & 1]; p.out = nullptr; p.out_f32 = out;
     p.w = w_tail; p.bias = b_tail; p.relu = 0;
     p.resid = residual ? x : nullptr;          // channel 0 of x
@@ -1851,6 +1858,19 @@ int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H
 }
 
 // debug only (not part of include/pnpadmm.h): the planner's per-device constants
+int pnpadmm_conv64_dilated_bf16(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu, int dilation,
+                                pnpadmm_stream_t s) {
+    return conv64_impl(in, out, w, bias, B, H, W, relu, ST(s), dilation);
+}
+int pnpadmm_dncnn_forward_dilated_bf16(const float* x, float* out, int B, int cin, int H, int W, int n_mid, const int* dilation_mid,
+                                       const float* w_head, const float* b_head, const void* w_mid, const float* b_mid,
+                                       const void* w_tail, const float* b_tail, int residual, void* act0, void* act1,
+                                       pnpadmm_stream_t s) {
+    if (n_mid > 0 && !dilation_mid) return fail(PNPADMM_ERR_BAD_ARG, "dncnn_forward_dilated: dilation_mid is NULL");
+    return dncnn_forward_impl(x, out, B, cin, H, W, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, residual, act0, act1, ST(s),
+                              dilation_mid);
+}
+
 int pnpadmm_ffdnet_forward_bf16(const float* x, float* out, int B, int H, int W, float sigma, int n_mid, const void* w_head,
                                 const float* b_head, const void* w_mid, const float* b_mid, const void* w_tail, const float* b_tail,
                                 void* act0, void* act1, pnpadmm_stream_t s) {

@@ -252,17 +252,17 @@ class Denoiser:
             if isinstance(sd, dict) and '0' in sd and isinstance(sd['0'], dict):
                 ircnn_weights, weights = sd, None
         net = model if model is not None else build_model(model_name, seed, weights)
-        # DnCNN / FDnCNN / FFDNet (all 64-channel conv3x3 chains) in bf16 on a GPU run on the hand-written tensor-core kernels
-        # (csrc/dncnn_tc.cuh) unless fused=False asks for the stock PyTorch module (the A/B baseline); IRCNN (dilated) and
-        # DRUNet stay in PyTorch.
-        can_fuse = self.arch in ('dncnn', 'fdncnn', 'ffdnet') and dtype == torch.bfloat16 and self.device.type == 'cuda'
+        # DnCNN / FDnCNN / IRCNN / FFDNet (all 64-channel conv3x3 chains; IRCNN's are dilated) in bf16 on a GPU run on the
+        # hand-written tensor-core kernels (csrc/dncnn_tc.cuh) unless fused=False asks for the stock PyTorch module (the A/B
+        # baseline); DRUNet stays in PyTorch.
+        can_fuse = self.arch in ('dncnn', 'fdncnn', 'ircnn', 'ffdnet') and dtype == torch.bfloat16 and self.device.type == 'cuda'
         if fused and not can_fuse:
-            raise ValueError('fused=True needs a DnCNN / FDnCNN / FFDNet in bf16 on a CUDA device')
+            raise ValueError('fused=True needs a DnCNN / FDnCNN / IRCNN / FFDNet in bf16 on a CUDA device')
         self.fused = None
         if can_fuse and fused is not False:
             from .dncnn_fused import FusedDnCNN, FusedFFDNet
             self.fused = (FusedFFDNet(net, device=self.device) if self.arch == 'ffdnet'
-                          else FusedDnCNN(net, residual=(self.arch == 'dncnn'), device=self.device))
+                          else FusedDnCNN(net, residual=(self.arch in ('dncnn', 'ircnn')), device=self.device))
         self.net = net.to(self.device, dtype).to(memory_format=torch.channels_last)
         self.sigmas = None
         self.noise_map = None
@@ -312,8 +312,10 @@ class Denoiser:
                     sets = self.ircnn_weights
                     sd = sets[str(idx)] if isinstance(sets, dict) and str(idx) in sets else sets[idx]
                     self.net.load_state_dict(sd, strict=True)
+                    if self.fused is not None:
+                        self.fused.repack(self.net)
                     self._ircnn_idx = idx
-            y = self._run(x)                                                                        # S3:56
+            y = self.fused(x) if self.fused is not None else self._run(x)                           # S3:56
         if mode:
             y = augment(y, augment_inverse_mode(mode))                                              # S3:46-50
         return y

@@ -1,5 +1,5 @@
-"""DnCNN / FDnCNN / FFDNet forward through the tensor-core kernels of the C ABI (``pnpadmm_dncnn_forward_bf16``,
-``pnpadmm_ffdnet_forward_bf16``).
+"""DnCNN / FDnCNN / IRCNN / FFDNet forward through the tensor-core kernels of the C ABI (``pnpadmm_dncnn_forward_bf16``,
+``pnpadmm_dncnn_forward_dilated_bf16``, ``pnpadmm_ffdnet_forward_bf16``).
 
 The reference runs its denoisers as stock ``torch.nn`` modules (models/network_dncnn.py:36-67, 120-141, called
 from S6:353-359 / S3:20-35).  On B200 the 64->64 layers are hand-written tcgen05 implicit GEMMs
@@ -8,6 +8,7 @@ and owns the two bf16 activation buffers.  Host logic only: there is no fallback
 """
 from __future__ import annotations
 
+import ctypes
 from typing import List, Tuple
 
 import torch
@@ -16,14 +17,21 @@ import torch.nn as nn
 from . import _abi
 
 
+MAX_DILATION = 4
+
+
 def conv_layers(net: nn.Module) -> List[nn.Conv2d]:
-    """The convolutions of a DnCNN / FDnCNN in forward order (``net.model`` is conv, ReLU, conv, ...)."""
+    """The convolutions of a DnCNN / FDnCNN / IRCNN in forward order (``net.model`` is conv, ReLU, conv, ...).  Middle layers
+    may be dilated (dilation = padding <= 4, IRCNN); the first and the last layer may not."""
     convs = [m for m in net.model if isinstance(m, nn.Conv2d)]
     if len(convs) < 2:
         raise ValueError('need at least a first and a last convolution')
     for k, c in enumerate(convs):
-        if c.kernel_size != (3, 3) or c.padding != (1, 1) or c.dilation != (1, 1) or c.stride != (1, 1) or c.bias is None:
-            raise ValueError(f'layer {k}: only conv3x3, stride 1, padding 1, dilation 1, with bias is supported')
+        d = c.dilation[0]
+        ok_d = d == 1 or (0 < k < len(convs) - 1 and 1 <= d <= MAX_DILATION)
+        if c.kernel_size != (3, 3) or c.dilation != (d, d) or c.padding != (d, d) or not ok_d or c.stride != (1, 1) or c.bias is None:
+            raise ValueError(f'layer {k}: only conv3x3, stride 1, padding = dilation (<= {MAX_DILATION} in middle layers, 1 in the '
+                             f'first and last), with bias is supported')
     if convs[0].out_channels != 64 or convs[-1].in_channels != 64 or convs[-1].out_channels != 1:
         raise ValueError('expected 64 feature channels and one output channel')
     for c in convs[1:-1]:
@@ -60,12 +68,15 @@ def pack_dncnn(net: nn.Module, device) -> Tuple[dict, int, int]:
                   else torch.zeros(0, dtype=torch.float32, device=dev)),
         'w_tail': pack_conv64(bf(tail.weight), 16),
         'b_tail': bf(tail.bias).float().contiguous(),
+        'dilations': [int(c.dilation[0]) for c in mids],
     }
     return packed, head.in_channels, len(mids)
 
 
 class FusedDnCNN:
-    """``y = D(x)`` for a DnCNN (residual, 1 input channel) or FDnCNN (non-residual, 2 input channels).
+    """``y = D(x)`` for a DnCNN / IRCNN (residual, 1 input channel; IRCNN's middle layers are dilated) or FDnCNN (non-residual,
+    2 input channels).  ``repack(net)`` re-reads the weights of a module with the same architecture (IRCNN's sigma-indexed
+    weight switch, S3:280-288).
 
     x: (B, cin, H, W) float32 CUDA tensor -> (B, 1, H, W) float32.  Work is enqueued on the current stream.
     The instance owns the two bf16 activation buffers (2 x B*H*W*128 bytes, re-allocated when the shape changes), so calls on
@@ -80,11 +91,16 @@ class FusedDnCNN:
         if self.device.type == 'cuda' and self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
         self.residual = bool(residual)
-        self.w, self.cin, self.n_mid = pack_dncnn(net, self.device)
-        if self.cin not in (1, 2):
-            raise ValueError(f'{self.cin} input channels: only DnCNN (1) and FDnCNN (2) are on the path')
+        self.repack(net)
         self._act = None
         self._act_key = None
+
+    def repack(self, net: nn.Module) -> None:
+        self.w, self.cin, self.n_mid = pack_dncnn(net, self.device)
+        if self.cin not in (1, 2):
+            raise ValueError(f'{self.cin} input channels: only DnCNN / IRCNN (1) and FDnCNN (2) are on the path')
+        dil = self.w['dilations']
+        self._dil = (ctypes.c_int * len(dil))(*dil) if any(d != 1 for d in dil) else None
 
     def _buffers(self, B, H, W):
         key = (B, H, W)
@@ -107,11 +123,15 @@ class FusedDnCNN:
         with torch.cuda.device(x.device):
             a0, a1 = self._buffers(B, H, W)
             out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
-            _abi.check(self.lib.pnpadmm_dncnn_forward_bf16(
-                x.data_ptr(), out.data_ptr(), B, self.cin, H, W, self.n_mid, w['w_head'].data_ptr(), w['b_head'].data_ptr(),
-                w['w_mid'].data_ptr() if self.n_mid else None, w['b_mid'].data_ptr() if self.n_mid else None,
-                w['w_tail'].data_ptr(), w['b_tail'].data_ptr(), int(self.residual), a0.data_ptr(), a1.data_ptr(),
-                torch.cuda.current_stream().cuda_stream))
+            tail_args = (w['w_head'].data_ptr(), w['b_head'].data_ptr(),
+                         w['w_mid'].data_ptr() if self.n_mid else None, w['b_mid'].data_ptr() if self.n_mid else None,
+                         w['w_tail'].data_ptr(), w['b_tail'].data_ptr(), int(self.residual), a0.data_ptr(), a1.data_ptr(),
+                         torch.cuda.current_stream().cuda_stream)
+            if self._dil is None:
+                _abi.check(self.lib.pnpadmm_dncnn_forward_bf16(x.data_ptr(), out.data_ptr(), B, self.cin, H, W, self.n_mid, *tail_args))
+            else:
+                _abi.check(self.lib.pnpadmm_dncnn_forward_dilated_bf16(x.data_ptr(), out.data_ptr(), B, self.cin, H, W, self.n_mid,
+                                                                       self._dil, *tail_args))
         return out
 
 
@@ -200,8 +220,9 @@ def from_chunk_planar(x_cp: torch.Tensor) -> torch.Tensor:
     return x_cp.permute(0, 1, 3, 2, 4).reshape(B, H, W, 64).contiguous()
 
 
-def conv64(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.Tensor:
-    """One 64 -> 64 layer through ``pnpadmm_conv64_bf16``: x (B, H, W, 64) bf16 CUDA -> same shape (parity tests)."""
+def conv64(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu: bool = True, dilation: int = 1) -> torch.Tensor:
+    """One 64 -> 64 layer through ``pnpadmm_conv64_bf16`` / ``pnpadmm_conv64_dilated_bf16``: x (B, H, W, 64) bf16 CUDA -> same
+    shape (parity tests)."""
     lib = _abi.load()
     if x_nhwc.dtype != torch.bfloat16 or x_nhwc.ndim != 4 or x_nhwc.shape[-1] != 64 or not x_nhwc.is_cuda:
         raise ValueError('expected a (B, H, W, 64) bf16 CUDA tensor')
@@ -211,6 +232,10 @@ def conv64(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu:
     bs = bias.to(x.device, torch.float32).contiguous()
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        _abi.check(lib.pnpadmm_conv64_bf16(x.data_ptr(), out.data_ptr(), wp.data_ptr(), bs.data_ptr(), B, H, W, int(relu),
-                                           torch.cuda.current_stream().cuda_stream))
+        st = torch.cuda.current_stream().cuda_stream
+        if dilation == 1:
+            _abi.check(lib.pnpadmm_conv64_bf16(x.data_ptr(), out.data_ptr(), wp.data_ptr(), bs.data_ptr(), B, H, W, int(relu), st))
+        else:
+            _abi.check(lib.pnpadmm_conv64_dilated_bf16(x.data_ptr(), out.data_ptr(), wp.data_ptr(), bs.data_ptr(), B, H, W, int(relu),
+                                                       int(dilation), st))
     return from_chunk_planar(out)

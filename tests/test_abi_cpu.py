@@ -25,7 +25,7 @@ def test_header_symbols_all_exported(lib):
     assert declared == sorted(_abi.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.pnpadmm_abi_version() == _abi.ABI_VERSION == 2
+    assert lib.pnpadmm_abi_version() == _abi.ABI_VERSION == 3
 
 
 def test_workspace_sizes(lib):

@@ -57,8 +57,12 @@ def test_pack_dncnn_layer_split():
     net2 = denoisers.build_model('fdncnn_gray')
     _, cin2, n_mid2 = df.pack_dncnn(net2, 'cpu')
     assert (cin2, n_mid2) == (2, 18)
+    p3, cin3, n_mid3 = df.pack_dncnn(denoisers.build_model('ircnn_gray'), 'cpu')      # dilated middle layers (IRCNN)
+    assert (cin3, n_mid3) == (1, 5) and p3['dilations'] == [2, 3, 4, 3, 2]
+    bad = denoisers.build_model('ircnn_gray')
+    bad.model[0].dilation = (2, 2); bad.model[0].padding = (2, 2)
     with pytest.raises(ValueError):
-        df.conv_layers(denoisers.build_model('ircnn_gray'))      # dilated convolutions are not on this kernel
+        df.conv_layers(bad)                                      # the first layer must be undilated
 
 
 def _simulate_input_stationary_schedule(strip_rows, blocks=8):
@@ -137,8 +141,27 @@ def test_conv64_layer_gpu(shape, relu):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('dil', [2, 3, 4])
+@pytest.mark.parametrize('shape', [(2, 64, 256), (3, 70, 200), (1, 7, 40), (2, 130, 129), (1, 256, 256)])
+def test_conv64_dilated_layer_gpu(shape, dil):
+    """IRCNN's dilated 64 -> 64 layers (dilation = padding = 2, 3, 4) on the same kernel: strips of row sub-images, tap shift
+    of `dil` slots along x.  Same gate as the undilated layer."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + H + W + dil)
+    x = torch.randn(B, H, W, 64, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24.0).to(torch.bfloat16).float().cuda()
+    b = torch.randn(64, generator=g).cuda()
+    got = df.conv64(x, w, b, relu=True, dilation=dil).float()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        want = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=dil, dilation=dil).permute(0, 2, 3, 1).clamp_min(0)
+    err = (got - want).abs()
+    assert float((err - (2.0 ** -8) * want.abs()).max()) < 2e-3, float(err.max())
+    assert _rel(got, want) < 3e-3
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('name,shape', [('dncnn_25', (4, 256, 256)), ('dncnn_25', (2, 96, 160)), ('dncnn3', (1, 64, 64)),
-                                        ('fdncnn_gray', (2, 128, 128))])
+                                        ('fdncnn_gray', (2, 128, 128)), ('ircnn_gray', (2, 256, 256)), ('ircnn_gray', (3, 70, 200))])
 def test_dncnn_forward_gpu(name, shape):
     B, H, W = shape
     net = denoisers.build_model(name, seed=3)
@@ -174,14 +197,14 @@ def _forward_with_bf16_rounding_points(net, x):
     h = x.to(torch.bfloat16).float()
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         for k, c in enumerate(convs):
-            h = F.conv2d(h, c.weight.to(torch.bfloat16).float(), c.bias.to(torch.bfloat16).float(), padding=1)
+            h = F.conv2d(h, c.weight.to(torch.bfloat16).float(), c.bias.to(torch.bfloat16).float(), padding=c.padding, dilation=c.dilation)
             if k < len(convs) - 1:
                 h = F.relu(h).to(torch.bfloat16).float()
     return h
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name,shape', [('dncnn_25', (2, 256, 256)), ('fdncnn_gray', (1, 96, 160))])
+@pytest.mark.parametrize('name,shape', [('dncnn_25', (2, 256, 256)), ('fdncnn_gray', (1, 96, 160)), ('ircnn_gray', (2, 131, 256))])
 def test_dncnn_forward_matches_same_rounding_points_gpu(name, shape):
     """Against an fp32 evaluation that rounds where K5 rounds, only the fp32 summation order is left, and the bf16 rounding
     flips it causes (a pre-rounding difference of 1e-6 relative moves ~1e-4 of the activations across a bf16 boundary per
@@ -283,3 +306,23 @@ def test_denoiser_dispatch_ffdnet_fused_gpu():
     y = d(x, 0)
     y_ref = denoisers.build_denoiser('ffdnet_gray', seed=1, fused=False)(x, 0)
     assert y.shape == y_ref.shape and _rel(y, y_ref) < 2e-2
+
+
+@pytest.mark.gpu
+def test_denoiser_dispatch_ircnn_fused_weight_switch_gpu():
+    """IRCNN through the Denoiser with the 25-set sigma-indexed weight switch (S3:280-288): the tensor-core path re-packs its
+    weights when the index changes and follows the stock bf16 module (same sets) at every iteration probed."""
+    sets = {str(k): denoisers.build_model('ircnn_gray', seed=100 + k).state_dict() for k in range(25)}
+    d = denoisers.build_denoiser('ircnn_gray', seed=1, iter_num=50, ircnn_weights=sets)
+    d_ref = denoisers.build_denoiser('ircnn_gray', seed=1, iter_num=50, ircnn_weights=sets, fused=False)
+    d32 = denoisers.build_denoiser('ircnn_gray', seed=1, iter_num=50, ircnn_weights=sets, dtype=torch.float32)
+    assert d.fused is not None and d_ref.fused is None
+    x = torch.rand(2, 1, 96, 160, device='cuda')
+    seen = set()
+    for i in (0, 1, 10, 25, 49):
+        y, y16, y32 = d(x, i), d_ref(x, i), d32(x, i)
+        seen.add(d._ircnn_idx)
+        assert d._ircnn_idx == d_ref._ircnn_idx == d32._ircnn_idx
+        n, n16, n32 = x - y, x - y16, x - y32
+        assert _rel(n, n32) < max(2.0 * _rel(n16, n32), 2e-2), (i, _rel(n, n32), _rel(n16, n32))
+    assert len(seen) >= 4

@@ -271,3 +271,40 @@ def test_pnp_drunet_50_iterations_three_images(env, cs_inputs, gold50):
         e = rel(x[k], gold50['cnc_drunet'][k])
         print(f'cnc_drunet {n}: 50 iterations, rel-L2 vs unmodified S6 {e:.2e}')
         assert e < CHAOTIC_TOL, (n, e)
+
+
+def test_pnp_l1_ffdnet_50_iterations_tensor_core_denoiser(env, cs_inputs, gold50):
+    """S3's FFDNet preset at its 50 iterations with the FFDNet on the tcgen05 kernels (bf16 operands, pnpadmm_ffdnet_forward_bf16)
+    against the unmodified script's float32 result: reported, and bounded at bf16-denoiser accuracy (the float32 denoiser is gated
+    at 1e-4 above); the stock PyTorch bf16 module in the same loop is the yardstick."""
+    pk, _, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_l1
+    it, reo = int(gold50['l1_ffdnet_params'][0]), float(gold50['l1_ffdnet_params'][1])
+    img = _img(cs_inputs, str(gold50['single_image']))
+    D16 = _D('ffdnet_gray', it, False, nz, torch.bfloat16)
+    assert D16.fused is not None
+    e = rel(pnp_admm_l1(img, m, nz, D16, iter_num=it, reo=reo), gold50['l1_ffdnet'])
+    from pnp_admm_cnc_mri_b200.denoisers import Denoiser
+    Dt = Denoiser('ffdnet_gray', iter_num=it, noises=nz, dtype=torch.bfloat16, seed=0, fused=False)
+    et = rel(pnp_admm_l1(img, m, nz, Dt, iter_num=it, reo=reo), gold50['l1_ffdnet'])
+    print(f'l1_ffdnet: 50 iterations vs unmodified S3: K5 (bf16 tcgen05) {e:.2e}, PyTorch bf16 module {et:.2e}')
+    assert e < max(CHAOTIC_TOL, 2 * et), (e, et)
+
+
+def test_pnp_l1_ircnn_50_iterations_tensor_core_denoiser(env, cs_inputs, gold50):
+    """S3's IRCNN preset (25 weight sets switched by sigma, S3:280-288) at 50 iterations with the dilated network on the tcgen05
+    kernels (pnpadmm_dncnn_forward_dilated_bf16) against the unmodified script's float32 result: reported, bounded at
+    bf16-denoiser accuracy, with the stock PyTorch bf16 module in the same loop as the yardstick."""
+    pk, _, m, nz = env
+    from pnp_admm_cnc_mri_b200.pnp import pnp_admm_l1
+    from pnp_admm_cnc_mri_b200.denoisers import Denoiser
+    it, reo = int(gold50['l1_ircnn_params'][0]), float(gold50['l1_ircnn_params'][1])
+    img = _img(cs_inputs, str(gold50['single_image']))
+    sets = _ircnn_sets(int(gold50['ircnn_seed0']))
+    D16 = Denoiser('ircnn_gray', iter_num=it, noises=nz, dtype=torch.bfloat16, seed=0, ircnn_weights=sets)
+    assert D16.fused is not None
+    e = rel(pnp_admm_l1(img, m, nz, D16, iter_num=it, reo=reo), gold50['l1_ircnn'])
+    Dt = Denoiser('ircnn_gray', iter_num=it, noises=nz, dtype=torch.bfloat16, seed=0, ircnn_weights=sets, fused=False)
+    et = rel(pnp_admm_l1(img, m, nz, Dt, iter_num=it, reo=reo), gold50['l1_ircnn'])
+    print(f'l1_ircnn: 50 iterations vs unmodified S3: K5 (bf16 tcgen05) {e:.2e}, PyTorch bf16 module {et:.2e}')
+    assert e < max(CHAOTIC_TOL, 2 * et), (e, et)

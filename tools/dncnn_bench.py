@@ -89,6 +89,31 @@ def main():
         t_l = timed(lambda: lib.pnpadmm_conv64_bf16(a.data_ptr(), out.data_ptr(), wp.data_ptr(), b.data_ptr(), B, H, W, 1, st))
         print(f'      one 64->64 layer: {t_l[0] * 1e3:.1f} us = {B * flops_mid / t_l[0] / 1e9:.0f} TFLOP/s, '
               f'{2 * a.numel() * 2 / t_l[0] / 1e6:.0f} GB/s of activations', flush=True)
+    # IRCNN (7 layers, dilations 1, 2, 3, 4, 3, 2, 1)
+    inet = denoisers.build_model('ircnn_gray', seed=0).cuda()
+    ifused = df.FusedDnCNN(inet, residual=True)
+    inet16 = denoisers.build_model('ircnn_gray', seed=0).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    x = torch.rand(2, 1, 256, 256, device='cuda')
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        want = inet(x)
+    print(f'IRCNN: ours vs fp32 {rel(x - ifused(x), x - want):.3e} (n(x) part), torch bf16 vs fp32 '
+          f'{rel(x - inet16(x.to(torch.bfloat16)).float(), x - want):.3e}', flush=True)
+    for B in Bs:
+        x = torch.rand(B, 1, H, W, device='cuda')
+        x16 = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        t_ours = timed(lambda: ifused(x))
+        t_torch = timed(lambda: inet16(x16))
+        fl = B * (5 * flops_mid + 2.0 * 64 * 9 * H * W * 2)
+        print(f'IRCNN B={B}: ours {t_ours[0]:.3f} ms (avg {t_ours[1]:.3f}) = {fl / t_ours[0] / 1e9:.0f} TFLOP/s | '
+              f'torch bf16 cuDNN {t_torch[0]:.3f} ms | speed-up {t_torch[0] / t_ours[0]:.2f}x', flush=True)
+        a = torch.randn(B, H, W, 64, device='cuda').to(torch.bfloat16)
+        wp = df.pack_conv64(torch.randn(64, 64, 3, 3, device='cuda') / 24)
+        b = torch.zeros(64, device='cuda')
+        out = torch.empty_like(a)
+        st = torch.cuda.current_stream().cuda_stream
+        for dil in (2, 4):
+            t_l = timed(lambda: ifused.lib.pnpadmm_conv64_dilated_bf16(a.data_ptr(), out.data_ptr(), wp.data_ptr(), b.data_ptr(), B, H, W, 1, dil, st))
+            print(f'      one 64->64 layer, dilation {dil}: {t_l[0] * 1e3:.1f} us = {B * flops_mid / t_l[0] / 1e9:.0f} TFLOP/s', flush=True)
     # FFDNet-15 (half resolution, 13 x conv64 between a thin first layer and a four-channel pixel-shuffled tail)
     fnet = denoisers.build_model('ffdnet_gray', seed=0).cuda()
     ffused = df.FusedFFDNet(fnet)
