@@ -388,6 +388,10 @@ def run_ours(args):
         return float(np.mean(ts))
 
     k1_ms = max_over_ranks(time_iterate('cluster', 2))    # all 32 planes on the cluster kernel: the K1 roofline leg (random mask)
+    # FFMA probe right beside the K1 leg (same clock / power state; after the tensor-core legs below the GPU sits power-capped at
+    # ~1.45 GHz for a while and the probe would read 53 instead of 72 TFLOP/s)
+    fl = ctypes.c_double()
+    _abi.check(lib.pnpadmm_measure_fp32_peak(fl, None))
     hyb_ms = max_over_ranks(time_iterate('auto', 2))      # what the step runs: K1 on most planes + K2 on the rest, concurrently
     del y, z0, x
 
@@ -449,6 +453,14 @@ def run_ours(args):
                   layer_ms=max_over_ranks(ev_time(lambda: _abi.check(lib.pnpadmm_conv64_bf16(
                       a5.data_ptr(), o5.data_ptr(), w5.data_ptr(), b5.data_ptr(), B3, N, N, 1, st5)), 5, 2)),
                   forward_ms=max_over_ranks(ev_time(lambda: D3.fused(x5), 5, 2)))
+        # the other 64-channel denoisers of the reference on the same kernels (IRCNN: dilated middle layers; FFDNet: half resolution,
+        # thin first layer, pixel-shuffled tail), each against its stock PyTorch bf16 module (cuDNN, channels_last)
+        k5['nets'] = {}
+        for nm in ('ircnn_gray', 'ffdnet_gray'):
+            Dk = pden.build_denoiser(nm, iter_num=50, seed=0, device=dev)
+            Dt = pden.build_denoiser(nm, iter_num=50, seed=0, device=dev, fused=False)
+            k5['nets'][nm] = dict(ms=max_over_ranks(ev_time(lambda: Dk(x5, 0), 5, 2)), torch_ms=max_over_ranks(ev_time(lambda: Dt(x5, 0), 3, 2)))
+            del Dk, Dt
         k5['clocks'] = s3c.stop() if rank == 0 else None
         del D3, im3, a5, o5, x5
         torch.cuda.empty_cache()
@@ -489,8 +501,6 @@ def run_ours(args):
                                   bytes_per_rank=int(B * N * N * 4))
             del all_imgs, out
 
-    fl = ctypes.c_double()
-    _abi.check(lib.pnpadmm_measure_fp32_peak(fl, None))
     sm, ncl = ctypes.c_int(), ctypes.c_int()
     _abi.check(lib.pnpadmm_device_info(sm, ncl, None, None))
     pc, ps, ch, la, ls, lr = (ctypes.c_int() for _ in range(6))
@@ -640,7 +650,11 @@ def run_ours(args):
                 'clocks': k5['clocks'],
                 'dncnn17_forward': {'ms': k5['forward_ms'], 'achieved': fwd_flop / (k5['forward_ms'] * 1e-3) / 1e12,
                                     'what': 'head (CUDA cores) + 15 x conv64_tc_kernel<64> + tail conv64_tc_kernel<16>; BASELINE config 3 '
-                                            'runs two of these per PnP-ADMM-CNC iteration'}}
+                                            'runs two of these per PnP-ADMM-CNC iteration'},
+                'other_networks': {nm: {'forward_ms': v['ms'], 'pytorch_bf16_forward_ms': v['torch_ms'], 'speedup': v['torch_ms'] / v['ms']}
+                                   for nm, v in k5['nets'].items()},
+                'other_networks_what': f"Denoiser.__call__ at B={k5['B']}, 256x256 (IRCNN: 5 dilated 64->64 layers, pnpadmm_dncnn_forward_dilated_bf16; "
+                                       'FFDNet: 14 layers at 128x128 + pack + shuffled tail, pnpadmm_ffdnet_forward_bf16) against the stock module'}
         if 'config4' in legs:
             r4 = legs['config4']
             line['config4'] = {'what': 'PnP-ADMM-L1 (S3:347 preset, reo 0.26), DRUNet random-init bf16 in PyTorch (4 x 288^2 quadrants per image, x8 '

@@ -1857,7 +1857,6 @@ int pnpadmm_dncnn_forward_bf16(const float* x, float* out, int B, int cin, int H
     return dncnn_forward_impl(x, out, B, cin, H, W, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, residual, act0, act1, ST(s));
 }
 
-// debug only (not part of include/pnpadmm.h): the planner's per-device constants
 int pnpadmm_conv64_dilated_bf16(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu, int dilation,
                                 pnpadmm_stream_t s) {
     return conv64_impl(in, out, w, bias, B, H, W, relu, ST(s), dilation);
@@ -1877,6 +1876,7 @@ int pnpadmm_ffdnet_forward_bf16(const float* x, float* out, int B, int H, int W,
     return ffdnet_forward_impl(x, out, B, H, W, sigma, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, act0, act1, ST(s));
 }
 
+// debug only (not part of include/pnpadmm.h): the planner's per-device constants
 int pnpadmm_debug_plan_constants(double* out4, int* calibrated) {
     DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
     out4[0] = d->tau1_us; out4[1] = d->k2_a_us; out4[2] = d->k2_b_us; out4[3] = d->k2_pro_us;
