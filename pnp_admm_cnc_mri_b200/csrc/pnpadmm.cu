@@ -1296,17 +1296,30 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, fl
 // ------------------------------------------------------------------------------------------
 // K5: DnCNN / FDnCNN forward on the tensor cores (dncnn_tc.cuh)
 // ------------------------------------------------------------------------------------------
-int conv_geometry(tc::ConvParams& p, int B, int H, int W, const char* who, int dil = 1) {
+// Work decomposition of one conv64 launch: B x xtiles x dil x ystrips items on `sms` persistent CTAs.  A strip of R output rows costs
+// R + 2 input rows (the halo), and the launch takes ceil(items / sms) strips per CTA: `ystrips` minimises waves x (R + 2).  Big
+// batches end up with long strips (DnCNN, B = 256, 256^2: 2 strips of 128 rows, 7 waves); small ones are cut until every SM has
+// work (B = 1: 37 strips of 7 rows instead of 4 of 64 on 8 SMs); FFDNet's half-resolution layers at B = 256 take 4 strips of 32
+// rows (7 waves x 34) instead of 2 of 64 (3.46 -> 4 waves x 66).
+int conv_geometry(tc::ConvParams& p, int B, int H, int W, const char* who, int sms, int dil = 1) {
     if (B <= 0 || H <= 0 || W <= 0) return fail(PNPADMM_ERR_BAD_ARG, "%s: B=%d H=%d W=%d must be positive", who, B, H, W);
     if ((long long)B * H * W >= (1ll << 31)) return fail(PNPADMM_ERR_BAD_SIZE, "%s: B*H*W = %lld pixels exceeds 2^31", who, (long long)B * H * W);
     if (dil < 1 || dil > tc::kMaxDil) return fail(PNPADMM_ERR_UNSUPPORTED, "%s: dilation %d (1..%d)", who, dil, tc::kMaxDil);
+    if (H < dil) return fail(PNPADMM_ERR_BAD_SIZE, "%s: H=%d is smaller than the dilation %d", who, H, dil);
     p.B = B; p.H = H; p.W = W;
     p.kchunks = 8; p.cout = 1; p.dil = dil;
     p.xtiles = (W + tc::kTileM - 1) / tc::kTileM;
-    const int sub = (H + dil - 1) / dil;                      // rows of the largest row sub-image (ConvParams::dil)
-    p.ystrips = (sub + 63) / 64;                              // strips of <= 64 rows, nearly equal (tc::decode_item)
-    if (H < dil * p.ystrips) return fail(PNPADMM_ERR_BAD_SIZE, "%s: H=%d is smaller than the dilation %d", who, H, dil);
-    p.items = B * p.xtiles * p.ystrips * dil;
+    const int sub_max = (H + dil - 1) / dil, sub_min = H / dil;      // rows of the largest / smallest row sub-image (ConvParams::dil)
+    const long long per_strip = (long long)B * p.xtiles * dil;
+    long long best = -1;
+    for (int ys = 1; ys <= sub_min && ys <= 64; ++ys) {             // ys <= sub_min: no strip of any sub-image is empty (tc::decode_item)
+        const int rows = (sub_max + ys - 1) / ys;
+        if (rows < 4 && ys > 1) break;                                // below four rows the halo alone is a third of the work
+        const long long waves = (per_strip * ys + sms - 1) / sms, cost = waves * (rows + 2);
+        if (best < 0 || cost < best) { best = cost; p.ystrips = ys; }
+    }
+    if (per_strip * p.ystrips >= (1ll << 31)) return fail(PNPADMM_ERR_BAD_SIZE, "%s: too many work items", who);
+    p.items = (int)(per_strip * p.ystrips);
     return PNPADMM_OK;
 }
 
@@ -1315,7 +1328,7 @@ int conv64_impl(const void* in, void* out, const void* w, const float* bias, int
     if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)w)) & 15) return fail(PNPADMM_ERR_BAD_ARG, "conv64: pointers must be 16-byte aligned");
     DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
     tc::ConvParams p{};
-    rc = conv_geometry(p, B, H, W, "conv64", dil); if (rc) return rc;
+    rc = conv_geometry(p, B, H, W, "conv64", d->sm_count, dil); if (rc) return rc;
     p.in = static_cast<const __nv_bfloat16*>(in); p.out = static_cast<__nv_bfloat16*>(out);
     p.w = w; p.bias = bias; p.relu = relu;
     if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);
@@ -1336,7 +1349,7 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
         return fail(PNPADMM_ERR_BAD_ARG, "dncnn_forward: activation / weight pointers must be 16-byte aligned");
     DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
     tc::ConvParams p{};
-    rc = conv_geometry(p, B, H, W, "dncnn_forward"); if (rc) return rc;
+    rc = conv_geometry(p, B, H, W, "dncnn_forward", d->sm_count); if (rc) return rc;
     __nv_bfloat16* act[2] = {static_cast<__nv_bfloat16*>(act0), static_cast<__nv_bfloat16*>(act1)};
     const unsigned hgrid = (unsigned)B * ((W + 31) / 32) * ((H + tc::kHeadRows - 1) / tc::kHeadRows);
     if (cin == 1) tc::dncnn_head_kernel<1><<<hgrid, 256, 0, st>>>(x, act[0], w_head, b_head, B, H, W);
@@ -1347,7 +1360,7 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
     if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);     // timing experiments only
     for (int l = 0; l < n_mid; ++l) {
         if (dil_mid) {                         // IRCNN: per-layer dilation (work items are strips of row sub-images)
-            rc = conv_geometry(p, B, H, W, "dncnn_forward", dil_mid[l]); if (rc) return rc;
+            rc = conv_geometry(p, B, H, W, "dncnn_forward", d->sm_count, dil_mid[l]); if (rc) return rc;
         }
         const int g = p.items < d->sm_count ? p.items : d->sm_count;
         p.in = act[l & 1]; p.out = act[(l + 1) & 1];
@@ -1356,7 +1369,7 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
         tc::conv64_tc_kernel<64><<<g, tc::kThreads, tc::kSmemBytes, st>>>(p);
     }
     LAUNCH_CHECK("conv64_tc_kernel<64>");
-    if (dil_mid) { rc = conv_geometry(p, B, H, W, "dncnn_forward", 1); if (rc) return rc; }
+    if (dil_mid) { rc = conv_geometry(p, B, H, W, "dncnn_forward", d->sm_count, 1); if (rc) return rc; }
     p.in = act[n_mid & 1]; p.out = nullptr; p.out_f32 = out;
     p.w = w_tail; p.bias = b_tail; p.relu = 0;
     p.resid = residual ? x : nullptr;          // channel 0 of x
@@ -1382,7 +1395,7 @@ int ffdnet_forward_impl(const float* x, float* out, int B, int H, int W, float s
     DeviceState* d; int rc = ensure_device(&d); if (rc) return rc;
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
     tc::ConvParams p{};
-    rc = conv_geometry(p, B, H2, W2, "ffdnet_forward"); if (rc) return rc;
+    rc = conv_geometry(p, B, H2, W2, "ffdnet_forward", d->sm_count); if (rc) return rc;
     __nv_bfloat16* act[2] = {static_cast<__nv_bfloat16*>(act0), static_cast<__nv_bfloat16*>(act1)};
     const size_t npx = (size_t)B * H2 * W2;
     tc::ffdnet_pack_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(x, act[1], sigma, B, H, W, H2, W2);

@@ -51,7 +51,7 @@ def timed(fn, reps=5, warm=2):
 
 
 def main():
-    Bs = [int(a) for a in sys.argv[1:]] or [64, 256]
+    Bs = [int(a) for a in sys.argv[1:]] or [64, 256]      # e.g. "1 15 256": small batches show the strip decomposition
     torch.cuda.set_device(0)
     bad = 0
     for shp in [(1, 8, 128), (2, 64, 256), (1, 70, 200)]:
