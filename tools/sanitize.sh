@@ -6,7 +6,7 @@ set -u
 # exercised by sanitize_run.py itself.
 export PNPADMM_NO_CALIBRATE=1
 out=gpurun_out/sanitizer; mkdir -p $out
-for job in memcheck:k1 memcheck:hybrid memcheck:fused memcheck:k3 memcheck:k2 racecheck:k1 racecheck:fused racecheck:k3 racecheck:k2 synccheck:k2 synccheck:k3 synccheck:k1; do
+for job in memcheck:k5 memcheck:k1 memcheck:hybrid memcheck:fused memcheck:k3 memcheck:k2 racecheck:k1 racecheck:fused racecheck:k3 racecheck:k2 synccheck:k2 synccheck:k3 synccheck:k1; do
     tool=${job%%:*}; w=${job##*:}
     timeout 180 compute-sanitizer --tool $tool --error-exitcode 1 --print-limit 20 python tools/sanitize_run.py $w > $out/${tool}_$w.log 2>&1
     echo "$tool $w rc=$?" | tee -a $out/summary.txt

@@ -63,3 +63,26 @@ if which in ('all', 'k2'):
     nz2 = data.make_noise(N2, seed=4)
     imgs = data.phantoms(3, N2, seed0=2)
     check(pk.admm_solve(imgs, m2, nz2, prox='cnc', kernel='streaming', **P), imgs, m2, nz2, 'K2 N=512 B=3', 1)
+if which in ('k5',):
+    # tensor-core denoisers on ragged sizes (partial x tiles, short strips, odd sizes for FFDNet's padding / crop, every dilation):
+    # one forward each, checked against the float32 module
+    import torch
+    from pnp_admm_cnc_mri_b200 import denoisers, dncnn_fused as df
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm())
+    for name, shape in (('dncnn_25', (2, 70, 200)), ('ircnn_gray', (2, 45, 150)), ('fdncnn_gray', (1, 33, 130))):
+        net = denoisers.build_model(name, seed=3).cuda()
+        cin = df.conv_layers(net)[0].in_channels
+        xin = torch.rand(shape[0], cin, shape[1], shape[2], device='cuda')
+        got = df.FusedDnCNN(net, residual=(cin == 1))(xin)
+        with torch.no_grad():
+            want = net(xin)
+        assert rel(got, want) < 2e-2, (name, rel(got, want))
+        print('K5', name, shape, 'ok', flush=True)
+    net = denoisers.build_model('ffdnet_gray', seed=3).cuda()
+    xin = torch.rand(2, 1, 65, 131, device='cuda')
+    got = df.FusedFFDNet(net)(xin, 15 / 255.)
+    with torch.no_grad():
+        want = net(xin, torch.full((1, 1, 1, 1), 15 / 255., device='cuda'))
+    assert rel(got, want) < 2e-2, rel(got, want)
+    print('K5 ffdnet_gray (2, 65, 131) ok', flush=True)
