@@ -407,6 +407,18 @@ def run_ours(args):
     # ---- config 5: ADMM-CNC, 512 images per GPU, N = 256 / 512 / 1024 (K1 + K2 hybrid at 256, K2 above; state >> L2) ----
     legs = {}
     if full:
+        # K5 layer timed ALONE first, before the long legs heat the GPU into its power cap: the measurement that belongs beside the
+        # burst bf16 peak (the same layer is timed again inside the config-3 section below, beside the sustained peak)
+        from pnp_admm_cnc_mri_b200 import dncnn_fused as pdf0
+        a0 = torch.randn(256, N, 8, N, 8, device=dev).to(torch.bfloat16)
+        o0 = torch.empty_like(a0)
+        w0 = pdf0.pack_conv64(torch.randn(64, 64, 3, 3, device=dev) / 24)
+        b0 = torch.zeros(64, device=dev)
+        st0 = torch.cuda.current_stream().cuda_stream
+        k5_alone_ms = max_over_ranks(ev_time(lambda: _abi.check(lib.pnpadmm_conv64_bf16(
+            a0.data_ptr(), o0.data_ptr(), w0.data_ptr(), b0.data_ptr(), 256, N, N, 1, st0)), 5, 2))
+        del a0, o0
+        torch.cuda.empty_cache()
         c5 = {}
         for N5 in (256, 512, 1024):
             B5 = 512
@@ -639,8 +651,12 @@ def run_ours(args):
             rec5, why5 = recorded_traffic('k5_conv64_b256')
             line['roofline_tensor'] = {
                 'bound': 'tensor', 'kernel': 'conv64_tc_kernel<64> (K5: one DnCNN conv3x3 64->64 + bias + ReLU layer, tcgen05 implicit GEMM)',
-                'achieved': layer_flop / (k5['layer_ms'] * 1e-3) / 1e12, 'peak': tpeak, 'unit': 'TFLOP/s',
-                'frac': layer_flop / (k5['layer_ms'] * 1e-3) / 1e12 / tpeak,
+                'achieved': layer_flop / (k5_alone_ms * 1e-3) / 1e12, 'peak': tpeak, 'unit': 'TFLOP/s',
+                'frac': layer_flop / (k5_alone_ms * 1e-3) / 1e12 / tpeak,
+                'launch_ms_alone': k5_alone_ms,
+                'timing': 'achieved / frac: the layer timed alone (5 launches, 7 ms in all: too short for the 100 ms clock sampler) before the long legs, against the burst peak; '
+                          'launch_ms / frac_of_sustained_peak: the same launch timed inside the config-3 section (GPU at its power cap), '
+                          'against the sustained peak',
                 'traffic': rec5['dram_bytes'] if rec5 else None, 'traffic_source': why5,
                 'flop_model': '2 x 64 x 64 x 9 = 73728 FLOP per pixel and layer', 'launch_ms': k5['layer_ms'],
                 'hbm_gbs_moved': 2 * 128.0 * N * N * k5['B'] / (k5['layer_ms'] * 1e-3) / 1e9,
