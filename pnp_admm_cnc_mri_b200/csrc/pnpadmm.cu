@@ -1279,6 +1279,10 @@ __global__ void unit_to_u8_kernel(const float* __restrict__ x, uint8_t* __restri
     }
 }
 
+__global__ void __launch_bounds__(256) debug_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // FP32 FMA throughput probe: 8 independent FMA chains per thread.
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float b, float c) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
@@ -1887,6 +1891,15 @@ int pnpadmm_ffdnet_forward_bf16(const float* x, float* out, int B, int H, int W,
                                 const float* b_head, const void* w_mid, const float* b_mid, const void* w_tail, const float* b_tail,
                                 void* act0, void* act1, pnpadmm_stream_t s) {
     return ffdnet_forward_impl(x, out, B, H, W, sigma, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, act0, act1, ST(s));
+}
+
+// debug only (not part of include/pnpadmm.h): copy kernel with 16-byte accesses; `dst` / `src` may be pinned host memory (zero-copy
+// over the host link: tools/pcie_probe.py compares it with the copy engines)
+int pnpadmm_debug_copy(void* dst, const void* src, size_t bytes, int blocks, pnpadmm_stream_t s) {
+    if (!dst || !src || (bytes & 15) || ((((uintptr_t)dst) | ((uintptr_t)src)) & 15)) return fail(PNPADMM_ERR_BAD_ARG, "debug_copy: 16-byte alignment");
+    debug_copy_kernel<<<blocks > 0 ? blocks : 296, 256, 0, ST(s)>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), bytes / 16);
+    LAUNCH_CHECK("debug_copy_kernel");
+    return PNPADMM_OK;
 }
 
 // debug only (not part of include/pnpadmm.h): the planner's per-device constants
