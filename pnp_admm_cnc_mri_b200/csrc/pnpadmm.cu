@@ -1893,6 +1893,17 @@ int pnpadmm_ffdnet_forward_bf16(const float* x, float* out, int B, int H, int W,
     return ffdnet_forward_impl(x, out, B, H, W, sigma, n_mid, w_head, b_head, w_mid, b_mid, w_tail, b_tail, act0, act1, ST(s));
 }
 
+// debug only (not part of include/pnpadmm.h): the work decomposition conv_geometry picks for a K5 layer on `sms` SMs (host logic,
+// no device needed: tests/test_dncnn_fused.py checks its invariants on the CPU)
+int pnpadmm_debug_conv_plan(int B, int H, int W, int dilation, int sms, int* xtiles, int* ystrips, int* items) {
+    if (sms <= 0 || !xtiles || !ystrips || !items) return fail(PNPADMM_ERR_BAD_ARG, "debug_conv_plan: bad argument");
+    tc::ConvParams p{};
+    const int rc = conv_geometry(p, B, H, W, "debug_conv_plan", sms, dilation);
+    if (rc) return rc;
+    *xtiles = p.xtiles; *ystrips = p.ystrips; *items = p.items;
+    return PNPADMM_OK;
+}
+
 // debug only (not part of include/pnpadmm.h): copy kernel with 16-byte accesses; `dst` / `src` may be pinned host memory (zero-copy
 // over the host link: tools/pcie_probe.py compares it with the copy engines)
 int pnpadmm_debug_copy(void* dst, const void* src, size_t bytes, int blocks, pnpadmm_stream_t s) {

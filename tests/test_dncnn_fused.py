@@ -234,6 +234,41 @@ def test_denoiser_dispatch_uses_fused_gpu():
     assert _rel(y, y_ref) < 1e-2
 
 
+def test_conv_plan_invariants_cpu():
+    """Host logic of the K5 work decomposition (conv_geometry through pnpadmm_debug_conv_plan, no device): every strip of every
+    row sub-image is non-empty, the items cover the image exactly once, and the chosen strips never cost more waves x rows than
+    the fixed 64-row strips of round 1."""
+    import ctypes
+    from pnp_admm_cnc_mri_b200 import _abi
+    lib = _abi.load()
+    f = lib.pnpadmm_debug_conv_plan
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int)] * 3
+    sms = 148
+    for B, H, W, d in [(1, 256, 256, 1), (15, 256, 256, 1), (256, 256, 256, 1), (256, 128, 128, 1), (3, 70, 200, 1), (2, 45, 150, 3),
+                       (1, 7, 40, 4), (64, 288, 288, 2), (1, 3, 40, 1), (5, 1024, 1024, 1), (2, 130, 129, 4)]:
+        xt, ys, it = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert f(B, H, W, d, sms, xt, ys, it) == 0
+        xt, ys, it = xt.value, ys.value, it.value
+        assert xt == (W + 127) // 128 and ys >= 1 and it == B * xt * ys * d
+        covered = 0
+        for py in range(d):
+            sub = (H - py + d - 1) // d
+            for k in range(ys):                                    # tc::decode_item's partition of a sub-image
+                j0, j1 = k * sub // ys, (k + 1) * sub // ys
+                assert j1 > j0, (B, H, W, d, py, k)
+                covered += j1 - j0
+        assert covered == H
+        waves = lambda n: -(-n // sms)                             # noqa: E731
+        sub_max = -(-H // d)
+        cost = waves(it) * (-(-sub_max // ys) + 2)
+        ys64 = max(1, -(-sub_max // 64))
+        if ys64 <= H // d:
+            assert cost <= waves(B * xt * ys64 * d) * (-(-sub_max // ys64) + 2), (B, H, W, d, ys, ys64)
+    bad = ctypes.c_int()
+    assert f(1, 3, 40, 4, sms, bad, bad, bad) != 0                # image shorter than the dilation: refused
+
+
 # ---------------------------------------------------------------------------------------- FFDNet on the same kernels
 def test_pack_ffdnet_layer_split():
     """CPU: the first layer of an FFDNet becomes a 64 -> 64 image with input channels 5..63 zero; the tail keeps 4 outputs."""
