@@ -222,6 +222,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
     constexpr int dbg = 0;
 #endif
     const bool prof = (dbg & 256) != 0;
+    // Programmatic dependent launch (the layers of a forward are launched with it): the next layer may be scheduled as soon as SMs
+    // free up and runs its set-up (weights, TMEM, barriers: nothing the previous layer wrote) while this one drains; it waits below,
+    // before it first touches an activation buffer.  A no-op for an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t s0 = smem_u32(smem);
     const uint32_t ring = s0 + kOffRing, bars = s0 + kOffBar;
     auto bFull = [&](uint32_t i) { return bars + 8 * i; };
@@ -285,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv64_tc_kernel(const ConvParams
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous layer is complete: its output may be read, its input overwritten
 
     if (warp > kMmaWarp) {
         // ------------------------------------------------------------------ producer: input rows -> ring
@@ -551,6 +556,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256) dncnn_head_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                          const float* __restrict__ w, const float* __restrict__ bias, int B,
                                                          int H, int W) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the first tensor-core layer may start its set-up
     const int ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float wr[CIN][8][9], br[8];
 #pragma unroll

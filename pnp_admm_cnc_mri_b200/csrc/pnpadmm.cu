@@ -1327,6 +1327,21 @@ int conv_geometry(tc::ConvParams& p, int B, int H, int W, const char* who, int s
     return PNPADMM_OK;
 }
 
+// A layer that follows another kernel of the same forward is launched with programmatic stream serialisation (see the kernel);
+// PNPADMM_NO_PDL=1 gives plain launches.
+template <int NOUT>
+void launch_conv(const tc::ConvParams& p, int grid, cudaStream_t st, bool dependent) {
+    static const bool pdl_on = [] { const char* e = getenv("PNPADMM_NO_PDL"); return !(e && atoi(e) != 0); }();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::kThreads); cfg.dynamicSmemBytes = tc::kSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (dependent && pdl_on) ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, tc::conv64_tc_kernel<NOUT>, p);
+}
+
 int conv64_impl(const void* in, void* out, const void* w, const float* bias, int B, int H, int W, int relu, cudaStream_t st, int dil = 1) {
     if (!in || !out || !w || !bias) return fail(PNPADMM_ERR_BAD_ARG, "conv64: NULL pointer");
     if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)w)) & 15) return fail(PNPADMM_ERR_BAD_ARG, "conv64: pointers must be 16-byte aligned");
@@ -1337,7 +1352,7 @@ int conv64_impl(const void* in, void* out, const void* w, const float* bias, int
     p.w = w; p.bias = bias; p.relu = relu;
     if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);
     const int grid = p.items < d->sm_count ? p.items : d->sm_count;
-    tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    launch_conv<64>(p, grid, st, false);
     LAUNCH_CHECK("conv64_tc_kernel<64>");
     return PNPADMM_OK;
 }
@@ -1370,7 +1385,7 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
         p.in = act[l & 1]; p.out = act[(l + 1) & 1];
         p.w = static_cast<const unsigned char*>(w_mid) + (size_t)l * tc::kWBytesMax;
         p.bias = b_mid + 64 * l;
-        tc::conv64_tc_kernel<64><<<g, tc::kThreads, tc::kSmemBytes, st>>>(p);
+        launch_conv<64>(p, g, st, true);
     }
     LAUNCH_CHECK("conv64_tc_kernel<64>");
     if (dil_mid) { rc = conv_geometry(p, B, H, W, "dncnn_forward", d->sm_count, 1); if (rc) return rc; }
@@ -1378,7 +1393,7 @@ int dncnn_forward_impl(const float* x, float* out, int B, int cin, int H, int W,
     p.w = w_tail; p.bias = b_tail; p.relu = 0;
     p.resid = residual ? x : nullptr;          // channel 0 of x
     p.resid_bstride = (long long)cin * H * W;
-    tc::conv64_tc_kernel<16><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    launch_conv<16>(p, grid, st, true);
     LAUNCH_CHECK("conv64_tc_kernel<16>");
     return PNPADMM_OK;
 }
@@ -1408,19 +1423,19 @@ int ffdnet_forward_impl(const float* x, float* out, int B, int H, int W, float s
     if (const char* e = getenv("PNPADMM_TC_DEBUG")) p.dbg = atoi(e);     // timing experiments only
     p.relu = 1;
     p.in = act[1]; p.out = act[0]; p.w = w_head; p.bias = b_head; p.kchunks = 2;
-    tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    launch_conv<64>(p, grid, st, false);               // after the pack kernel (an ordinary kernel without the early trigger)
     p.kchunks = 8;
     for (int l = 0; l < n_mid; ++l) {
         p.in = act[l & 1]; p.out = act[(l + 1) & 1];
         p.w = static_cast<const unsigned char*>(w_mid) + (size_t)l * tc::kWBytesMax;
         p.bias = b_mid + 64 * l;
-        tc::conv64_tc_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+        launch_conv<64>(p, grid, st, true);
     }
     LAUNCH_CHECK("conv64_tc_kernel<64>");
     p.in = act[n_mid & 1]; p.out = nullptr; p.out_f32 = out;
     p.w = w_tail; p.bias = b_tail; p.relu = 0; p.resid = nullptr;
     p.cout = 4; p.out_H = H; p.out_W = W;
-    tc::conv64_tc_kernel<16><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(p);
+    launch_conv<16>(p, grid, st, true);
     LAUNCH_CHECK("conv64_tc_kernel<16>");
     return PNPADMM_OK;
 }
