@@ -304,7 +304,7 @@ PNP_HD void col_blend(const Ctx<CL>& c, ThreadState& s, const cf32* Gs, uint32_t
     for (int j = 0; j < 16; ++j) {
         const cf32 gg = g[16 * j * R];
         const uint32_t code = (codes >> (2 * j)) & 3u;
-        const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
+        const float cf = blend_coef<true>(code, cf1);        // code in {0, 1, 2}, cf2 == 2 cf1 exactly: see blend_coef note in common.cuh
         s.a[j] = mk<float>(gg.re - cf * s.a[j].re, gg.im - cf * s.a[j].im);
     }
 }
@@ -389,7 +389,7 @@ PNP_HD void col_acquire_ms(const Ctx<CL>& c, ThreadState& s, cf32* Fsave, cf32* 
         const cf32 F = s.a[j];
         Fsave[i] = F;
         const uint32_t code = (codes >> (2 * j)) & 3u;
-        const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
+        const float cf = blend_coef<true>(code, cf1);        // code in {0, 1, 2}, cf2 == 2 cf1 exactly: see blend_coef note in common.cuh
         const cf32 nc = NcS[i], nh = nH[i];
         Gtile[i] = mk<float>(cf * F.re + (nc.re - hb * nc.im), cf * F.im + (nc.im + hb * nc.re));
         const float ms = 0.5f * (float)code;
@@ -483,7 +483,7 @@ PNP_HD void rsep_acquire_ms(const Ctx<16>& c, ThreadState& s, const cf32* NcSp, 
         const cf32 F = s.a[j];
         A0[n] = F;
         const uint32_t code = (codes >> (2 * j)) & 3u;
-        const float cf = code == 0 ? 0.f : (code == 1 ? ncf1 : ncf2);
+        const float cf = blend_coef<true>(code, ncf1);       // code in {0, 1, 2}, ncf2 == 2 ncf1 exactly: see blend_coef note in common.cuh
         const cf32 nc = NcSp[g0 + n], nh = nHp[g0 + n];
         Gp[n] = mk<float>(cf * F.re + (nc.re - hb * nc.im), cf * F.im + (nc.im + hb * nc.re));
         const float ms = (0.5f * (float)kN) * (float)code;
@@ -513,7 +513,7 @@ PNP_HD void rsep_blend(const Ctx<16>& c, ThreadState& s, uint32_t codes, float n
     for (int j = 0; j < 16; ++j) {
         const cf32 gg = Gp[16 * j];
         const uint32_t code = (codes >> (2 * j)) & 3u;
-        const float cf = code == 0 ? 0.f : (code == 1 ? ncf1 : ncf2);
+        const float cf = blend_coef<true>(code, ncf1);       // code in {0, 1, 2}, ncf2 == 2 ncf1 exactly: see blend_coef note in common.cuh
         s.a[j] = mk<float>(gg.re - cf * s.a[j].re, gg.im - cf * s.a[j].im);
     }
 }
@@ -599,7 +599,7 @@ PNP_HD void col_blend_g(const Ctx<16>& c, ThreadState& s, const cf32* Gtile, uin
     for (int j = 0; j < 16; ++j) {
         const cf32 gg = ld_g(g + 256 * j);
         const uint32_t code = (codes >> (2 * j)) & 3u;
-        const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
+        const float cf = blend_coef<true>(code, cf1);        // code in {0, 1, 2}, cf2 == 2 cf1 exactly: see blend_coef note in common.cuh
         s.a[j] = mk<float>(gg.re - cf * s.a[j].re, gg.im - cf * s.a[j].im);
     }
 }

@@ -123,6 +123,19 @@ PNP_HD void prox_dual(const ProxParams<T>& p, T x, T& z, T& w) {
     else prox_dual_m<PM_CNC>(p, x, z, w);
 }
 
+// blend_coef note.  The data-consistency residual uses cf[code] with code = m[k] + m[-k] in {0, 1, 2} and cf = {0, g / 2 N^2, g / N^2}
+// (pnpadmm.cu: both rounded from the same double, so cf[2] == 2 cf[1] bit for bit).  The fp32 kernels therefore compute the coefficient as
+// (float)code * cf[1]: one conversion and one multiply (blend_coef below).  The obvious `code == 0 ? 0 : (code == 1 ? cf1 : cf2)` compiles to divergent
+// branches inside the unrolled 16-point loops (BSSY / BSYNC per point); replacing it is bit-identical and made K3 7 % (N = 256) to 23 %
+// (N = 1024), K1 2-3 % and the columns pass at N = 1024 4 % faster (profiles/r2_measured_runs.md).
+// MUL = true: (float)code * cf1 (one conversion, one multiply).  MUL = false: the select chain, kept for the columns pass at N = 256, the one
+// kernel that measured slower with the product (7.77 -> 8.08 ms at B = 2048; an exact magic-number conversion without I2FP measured the same,
+// so it is not the conversion pipe).
+template <bool MUL> PNP_HD float blend_coef(uint32_t code, float cf1) {
+    if (MUL) return (float)code * cf1;
+    return code == 0 ? 0.f : (code == 1 ? cf1 : cf1 + cf1);
+}
+
 template <typename T> PNP_HD T clamp01(T v) { return pmin(pmax(v, T(0)), T(1)); }
 
 }  // namespace pnp

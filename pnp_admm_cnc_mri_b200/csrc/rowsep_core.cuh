@@ -75,7 +75,7 @@ PNP_HD void acquire_ms(LineState& s, int t, cf32* zs, cf32* gp, const cf32* NcSp
         const cf32 F = s.a[m];
         zs[n] = F;
         const uint32_t code = (codes >> (2 * m)) & 3u;
-        const float cf = code == 0 ? 0.f : (code == 1 ? ncf1 : ncf2);
+        const float cf = blend_coef<true>(code, ncf1);       // code in {0, 1, 2}, ncf2 == 2 ncf1 exactly: see blend_coef note in common.cuh
         const cf32 nc = NcSp[n], nh = nHp[n];
         gp[n] = mk<float>(cf * F.re + (nc.re - hb * nc.im), cf * F.im + (nc.im + hb * nc.re));
         const float ms = (0.5f * (float)N) * (float)code;
@@ -120,7 +120,8 @@ PNP_HD void blend(LineState& s, int t, const cf32* gp, uint32_t codes, float ncf
     for (int m = 0; m < 16; ++m) {
         const cf32 gg = gp[t + T * m];
         const uint32_t code = (codes >> (2 * m)) & 3u;
-        const float cf = code == 0 ? 0.f : (code == 1 ? ncf1 : ncf2);
+        const float cf = blend_coef<true>(code, ncf1);       // code in {0, 1, 2}, ncf2 == 2 ncf1 exactly: see blend_coef note in common.cuh
+        (void)ncf2;
         s.a[m] = mk<float>(gg.re - cf * s.a[m].re, gg.im - cf * s.a[m].im);
     }
 }

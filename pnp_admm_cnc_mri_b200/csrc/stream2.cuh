@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
     const bool aux_batched = (MODE == CM_FWD_BLEND_INV) ? true : (p.noise_batched != 0);
     pdl_wait();
     pdl_launch_dependents();
-    const float cf1 = (MODE == CM_FWD_BLEND_INV) ? p.cf[1] : 0.f, cf2 = (MODE == CM_FWD_BLEND_INV) ? p.cf[2] : 0.f;
+    const float cf1 = (MODE == CM_FWD_BLEND_INV) ? p.cf[1] : 0.f;      // cf[2] == 2 cf[1]: common.cuh, blend_coef note
 
     // tile copy: N rows x (C * 8) bytes = N * C / 2 pieces of 16 bytes, 8 per thread
     // `permute`: land the rows in the ColLine order (K tiles); the G / noise tile is read in natural order
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(ColsGeo<N>::kThreads, ColsGeo<N>::kCtasPerSm) 
                 for (int m = 0; m < 16; ++m) {
                     const cf32 gg = g[(t + T * m) * C];
                     const uint32_t code = (codes >> (2 * m)) & 3u;
-                    const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
+                    const float cf = blend_coef<(N != 256)>(code, cf1);        // code in {0, 1, 2}, cf2 == 2 cf1 exactly: see blend_coef note in common.cuh
                     a[m] = mk<float>(gg.re - cf * a[m].re, gg.im - cf * a[m].im);
                 }
                 fft_regs<true, N, true>(a, t, ln, TW, tw3);
@@ -404,7 +404,7 @@ cols2_tma_kernel(const StreamParams<float> p, const uint32_t* __restrict__ mpack
     __syncthreads();
     pdl_wait();                    // tables and barriers are set up; the K plane of the previous pass is complete from here on
     pdl_launch_dependents();
-    const float cf1 = p.cf[1], cf2 = p.cf[2];
+    const float cf1 = p.cf[1];                 // cf[2] == 2 cf[1]: common.cuh, blend_coef note
 
     // one thread: expect the tile's bytes, then one box per 256 rows
     auto issue = [&](const CUtensorMap* tm, int tile, uint32_t dst, uint32_t bar) {
@@ -445,7 +445,7 @@ cols2_tma_kernel(const StreamParams<float> p, const uint32_t* __restrict__ mpack
         for (int m = 0; m < 16; ++m) {
             const cf32 gg = g[(t + T * m) * C];
             const uint32_t code = (codes >> (2 * m)) & 3u;
-            const float cf = code == 0 ? 0.f : (code == 1 ? cf1 : cf2);
+            const float cf = blend_coef<(N != 256)>(code, cf1);        // code in {0, 1, 2}, cf2 == 2 cf1 exactly: see blend_coef note in common.cuh
             a[m] = mk<float>(gg.re - cf * a[m].re, gg.im - cf * a[m].im);
         }
         fft_regs<true, N, true>(a, t, ln, TW, tw3);
