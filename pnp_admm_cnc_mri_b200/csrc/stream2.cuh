@@ -33,6 +33,7 @@ PNP_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 PNP_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 constexpr int kRowsThreads = 128;
+template <int V> struct IntC { static constexpr int value = V; };      // compile-time int tag for generic lambdas
 
 template <int N> struct ColsGeo {
 #ifndef PNP_COLS512_C
@@ -211,6 +212,26 @@ __global__ void __launch_bounds__(kRowsThreads, 4) rows2_kernel(const StreamPara
     }
     if (MODE == RM_INV_PROX_FWD) {
         const int pm = prox_mode(p.prox);
+        // The common case (both images of the plane present, not the last iteration, L1 or CNC in clamp form) runs a loop without a single
+        // run-time condition: with the mode / has_b / last tests inside it, every pixel of the unrolled loop becomes its own basic blocks and
+        // the 32 independent prox chains cannot be interleaved.  Everything else takes the general loop below.
+        if (has_b && !p.last && pm != PM_GENERAL) {
+            auto fast = [&](auto mode_c) {
+                constexpr int PM = decltype(mode_c)::value;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int n = t + T * m;
+                    float za = za_s[n], wa = wa_s[n], zb = zb_s[n], wb = wb_s[n];
+                    const float xa = pabs((za - wa) + a[m].re), xb = pabs((zb - wb) + a[m].im);
+                    prox_dual_m<PM>(p.prox, xa, za, wa);
+                    prox_dual_m<PM>(p.prox, xb, zb, wb);
+                    p.z[ga + n] = za; p.w[ga + n] = wa;
+                    p.z[gb + n] = zb; p.w[gb + n] = wb;
+                    a[m] = mk<float>(za - wa, zb - wb);
+                }
+            };
+            if (pm == PM_CNC) fast(IntC<PM_CNC>{}); else fast(IntC<PM_L1>{});
+        } else
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             const int n = t + T * m;
