@@ -222,3 +222,19 @@ def test_k3n_emulated_rowsep_solve_matches_oracle(s2emu, N, prox):
         xr, zr, wr, _ = fn(np.float32(u8[k] / 255.), m.astype(np.float64), nz, return_state=True, **P)
         assert np.linalg.norm(x[k] - xr) / np.linalg.norm(xr) < 1e-4, (N, prox, k)
         assert np.linalg.norm(z[k] - zr) / np.linalg.norm(zr) < 1e-4
+
+
+def test_blend_coefficient_product_is_exact():
+    """common.cuh blend_coef: the kernels compute cf[code] as (float)code * cf[1] (and cf[1] + cf[1] in the select form) instead of
+    reading cf[2].  pnpadmm.cu rounds cf[1] = 0.5 g / N^2 and cf[2] = g / N^2 from the same double, so the three forms agree bit for bit
+    for every reo and N the library accepts (checked here in NumPy float32 / float64 arithmetic, which is IEEE like the device's)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for N in (16, 64, 256, 512, 1024, 2048):
+        for reo in np.concatenate([[0.015, 0.05, 0.26, 0.45, 0.8], rng.uniform(1e-4, 10.0, 200)]):
+            g = 1.0 / (1.0 + 1.0 / (2.0 * reo))                    # g = 1 / (1 + La2), La2 = 1 / (2 reo)      (S1:117)
+            for denom in (float(N) * N, float(N)):                  # cf = g ms / N^2 (K1 / K2) and N cf = g ms / N (K3)
+                c1, c2 = np.float32(0.5 * g / denom), np.float32(g / denom)
+                assert np.float32(2.0) * c1 == c2 and c1 + c1 == c2 and np.float32(0.0) * c1 == 0.0
+                c1d, c2d = 0.5 * g / denom, g / denom
+                assert 2.0 * c1d == c2d
